@@ -1,0 +1,194 @@
+"""Generate tests/golden/* by running the REAL reference (imported from /root/reference)
+on CPU.  TEST INFRASTRUCTURE ONLY.  Run in the build container (the reference is not
+present on the GPU box):
+
+    python oracle/make_golden.py
+
+Writes
+  tests/golden/tiny_a.npz, tiny_b.npz     tiny dims, every weight/input/output/gradient
+  tests/golden/fullsize_anchors.json       shipped-JSON dims (1 enc + 3 dec, d 768) and the
+                                           BASELINE cfg-1 literal reading (2+2, d 512):
+                                           seeds -> checksums / slices / loss / grad norms /
+                                           greedy ids, produced by the reference's own
+                                           MMT4Caption constructor + modules.
+All runs: fp32, eval() (dropout off), torch.backends.mha fast path disabled.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import ref_shims  # noqa: E402
+
+GOLD = os.path.join(ROOT, "tests", "golden")
+CPU = torch.device("cpu")
+
+
+def synth_inputs(B, T, Din, S1, V, seed=1234, padded=True, vid_padded=False):
+    """SURVEY section 8d / Appendix C synthetic inputs."""
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(B, T, Din, generator=g)
+    lo = 1000 if V > 2000 else 104
+    tok = torch.randint(lo, V, (B, S1), generator=g)
+    tok[:, 0] = 101
+    if padded:
+        lens = torch.randint(min(6, S1 - 1), S1 + 1, (B,), generator=g)
+        lens[0] = S1
+        for b in range(B):
+            tok[b, lens[b] - 1] = 102
+            tok[b, lens[b]:] = 0
+    else:
+        tok[:, -1] = 102
+    vm = torch.zeros(B, T, dtype=torch.bool)
+    if vid_padded:
+        vlen = torch.randint(2, T + 1, (B,), generator=g)
+        vlen[0] = T
+        for b in range(B):
+            vm[b, vlen[b]:] = True
+            x[b, vlen[b]:] = 0.0          # dataloader.py:233-247 zero-pads features
+    return x, vm, tok
+
+
+class _TokStub:
+    """ids -> "id id id" so greedy_decode's string output exposes the cut ids (Q11)."""
+
+    def convert_ids_to_tokens(self, ids):
+        return [str(i) for i in ids]
+
+    def convert_tokens_to_string(self, toks):
+        return " ".join(toks)
+
+
+def ref_greedy(ref, enc, dec, x, vm, max_len):
+    """Drive the reference's own MMT4Caption.greedy_decode (model/MMT4Caption.py:146-184)
+    on a stand-in ``self`` so the loop / cut semantics are the reference's, not ours."""
+    ns = types.SimpleNamespace(
+        device=CPU, video_encoder=enc, cap_decoder=dec,
+        cap_preprocessor=types.SimpleNamespace(start_id=101, end_id=102, tokenizer=_TokStub()))
+    captured = {}
+    orig_cat = torch.cat
+
+    def spy_cat(tensors, dim=0, **kw):
+        out = orig_cat(tensors, dim=dim, **kw)
+        if out.dtype == torch.long and out.dim() == 2 and out.shape[0] == x.shape[0]:
+            captured["ys"] = out
+        return out
+
+    torch.cat = spy_cat
+    try:
+        with torch.no_grad():
+            strings = ref.MMT4Caption.MMT4Caption.greedy_decode(ns, [x], None if vm is None else [vm], max_len)
+    finally:
+        torch.cat = orig_cat
+    return captured["ys"], strings
+
+
+def make_tiny(ref, name, Din, d, h, F, Le, Ld, V, T, S1, B, alpha, seed):
+    torch.manual_seed(seed)
+    enc = ref.MMEncoder.MultiModalEncoder([Din], d, h, F, Le, 0.3, "gelu", "avg", True, "encoding", False, CPU)
+    dec = ref.CapDecoder.CapDecoder(Ld, d, h, F, 0.3, V, 0, alpha, None, "gelu", CPU)
+    # nn.Transformer* deep-copies one layer (Q15): break the symmetry so a layer mix-up is caught
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        for p in list(enc.parameters()) + list(dec.parameters()):
+            p.add_(0.02 * torch.randn(p.shape, generator=g))
+        dec.tgt_to_emb.weight[0].zero_()
+    enc.eval(); dec.eval()
+    x, vm, tok = synth_inputs(B, T, Din, S1, V, seed=seed + 2, padded=True, vid_padded=True)
+    mem, gmask, _ = enc([x], [vm])
+    logits, loss = dec(mem, tok, tok == 0)
+    loss.backward()
+    out = {"in/feats": x.numpy(), "in/vid_pad": vm.numpy(), "in/ids": tok.numpy(),
+           "out/memory": mem.detach().numpy(), "out/logits": logits.detach().numpy(),
+           "out/loss": loss.detach().numpy(),
+           "cfg": np.array(json.dumps(dict(Din=Din, d=d, nhead=h, F=F, L_enc=Le, L_dec=Ld, V=V, T=T, S1=S1, B=B,
+                                           alpha=alpha)))}
+    for pre, mod in (("video_encoder.", enc), ("cap_decoder.", dec)):
+        for k, v in mod.state_dict().items():
+            if k.endswith("pos_embedding"):      # constant sinusoid buffers: keep the first 64 rows only,
+                v = v[:64]                       # tests rebuild the full table and compare these rows bit-exactly
+            elif k.endswith("temp_emb.pe"):
+                v = v[:, :64]
+            out["sd/" + pre + k] = v.detach().numpy()
+        for k, p in mod.named_parameters():
+            out["grad/" + pre + k] = (p.grad if p.grad is not None else torch.zeros_like(p)).numpy()
+    ys, strings = ref_greedy(ref, enc, dec, x, None, max_len=S1 + 2)
+    out["out/greedy_ys"] = ys.numpy()
+    out["out/greedy_strings"] = np.array(json.dumps(strings))
+    ys_m, _ = ref_greedy(ref, enc, dec, x[:, :T], None, max_len=4)
+    out["out/greedy_ys_len4"] = ys_m.numpy()
+    np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+    print(name, "loss", float(loss), "greedy", ys.shape, strings[:2])
+
+
+def checksum(sd):
+    return {k: [float(v.double().sum()), float(v.double().abs().sum())] for k, v in sd.items()
+            if v.is_floating_point()}
+
+
+def make_fullsize(ref, tokdir):
+    anchors = {"torch": torch.__version__, "seed_model": 666, "seed_inputs": 1234, "configs": {}}
+    for tag, over in (("json", {}), ("literal", {"embed_dim": 512, "enc_layer": 2, "dec_layer": 2})):
+        cfg = ref_shims.shipped_model_config(tokdir)
+        if over:
+            cfg["embed_dim"] = over["embed_dim"]
+            cfg["video_encoder"]["layer"] = over["enc_layer"]
+            cfg["caption_decoder"]["layer"] = over["dec_layer"]
+        torch.manual_seed(666)
+        model = ref.MMT4Caption.MMT4Caption(cfg, device=CPU)
+        model.mode("caption")
+        model.eval()
+        rec = {"state_checksum": checksum(model.state_dict()),
+               "n_params_total": sum(p.numel() for p in model.parameters()),
+               "n_params_trainable": sum(p.numel() for p in model.parameters() if p.requires_grad),
+               "cases": {}}
+        for case, padded in (("padded", True), ("unpadded", False)):
+            x, vm, tok = synth_inputs(8, 12, 512, 21, 30522, 1234, padded=padded)
+            model.zero_grad(set_to_none=True)
+            mem, _, _ = model.video_encoder([x], [vm])
+            logits, loss = model.cap_decoder(mem, tok, tok == 0)
+            loss.backward()
+            gn = {k: float(p.grad.double().norm()) for k, p in model.named_parameters() if p.grad is not None}
+            rec["cases"][case] = {
+                "loss": float(loss),
+                "memory_0_0_0:6": mem[0, 0, :6].tolist(), "memory_7_12_-6:": mem[7, 12, -6:].tolist(),
+                "logits_0_0_0:6": logits[0, 0, :6].tolist(), "logits_7_19_-6:": logits[7, 19, -6:].tolist(),
+                "mean_abs_logits": float(logits.abs().mean()),
+                "logits_argmax_row0": logits[0].argmax(-1).tolist(),
+                "grad_norms": gn,
+            }
+        x, vm, tok = synth_inputs(8, 12, 512, 21, 30522, 1234, padded=False)
+        ys, strings = ref_greedy(ref, model.video_encoder, model.cap_decoder, x, vm, max_len=6)
+        with torch.no_grad():
+            mem, _, _ = model.video_encoder([x], [vm])
+            lg = model.cap_decoder.decode_word(mem, ys[:, :1], None)
+            top2 = lg.topk(2, dim=1).values
+        rec["greedy"] = {"max_len": 6, "ys": ys.tolist(), "strings": strings,
+                         "first_step_logits_0_0:6": lg[0, :6].tolist(),
+                         "first_step_min_margin": float((top2[:, 0] - top2[:, 1]).min())}
+        anchors["configs"][tag] = rec
+        print(tag, {c: r["loss"] for c, r in rec["cases"].items()}, "greedy", ys[0].tolist())
+    with open(os.path.join(GOLD, "fullsize_anchors.json"), "w") as f:
+        json.dump(anchors, f, indent=1)
+
+
+def main():
+    os.makedirs(GOLD, exist_ok=True)
+    torch.backends.mha.set_fastpath_enabled(False)
+    torch.set_num_threads(os.cpu_count())
+    ref = ref_shims.import_reference_model()
+    make_tiny(ref, "tiny_a", Din=24, d=32, h=2, F=48, Le=2, Ld=2, V=211, T=5, S1=8, B=4, alpha=0.5, seed=11)
+    make_tiny(ref, "tiny_b", Din=16, d=48, h=2, F=64, Le=1, Ld=3, V=157, T=7, S1=6, B=3, alpha=1.0, seed=23)
+    tokdir = ref_shims.make_tokenizer_dir(os.path.join(ROOT, "gpurun_out", "_tok"))
+    make_fullsize(ref, tokdir)
+
+
+if __name__ == "__main__":
+    main()

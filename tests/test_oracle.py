@@ -1,0 +1,108 @@
+"""The oracle (oracle/vct_oracle.py) pinned against (1) golden vectors produced by the real
+reference (tests/golden, made by oracle/make_golden.py) and (2) the live reference whenever
+/root/reference is mounted.  CPU only."""
+import json
+
+import pytest
+import torch
+
+from oracle import ref_shims
+from oracle import vct_oracle as O
+from helpers import load_tiny, load_anchors, synth_inputs
+
+TOL = dict(rtol=2e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+def test_oracle_forward_matches_reference_golden(name):
+    cfg, sd, ins, outs, _ = load_tiny(name)
+    mem, logits, loss = O.caption_forward(sd, ins["feats"], ins["vid_pad"], ins["ids"], cfg["nhead"], cfg["nhead"],
+                                          cfg["alpha"])
+    torch.testing.assert_close(mem, torch.from_numpy(outs["memory"]), **TOL)
+    torch.testing.assert_close(logits, torch.from_numpy(outs["logits"]), **TOL)
+    assert abs(float(loss) - float(outs["loss"])) < 2e-6 * max(1.0, abs(float(outs["loss"])))
+
+
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+def test_oracle_gradients_match_reference_golden(name):
+    cfg, sd, ins, _, grads = load_tiny(name)
+    _, g = O.caption_grads(sd, ins["feats"], ins["vid_pad"], ins["ids"], cfg["nhead"], cfg["nhead"], cfg["alpha"])
+    assert set(g) == set(grads)
+    for k in grads:
+        torch.testing.assert_close(g[k], grads[k], rtol=1e-4, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
+
+
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+def test_oracle_greedy_matches_reference_golden(name):
+    cfg, sd, ins, outs, _ = load_tiny(name)
+    ys = O.greedy_decode_ids(sd, ins["feats"], None, cfg["nhead"], cfg["nhead"], max_len=cfg["S1"] + 2)
+    assert ys.tolist() == outs["greedy_ys"].tolist()
+    strings = [" ".join(str(t) for t in O.cut_caption_ids(r)) for r in ys.tolist()]
+    assert strings == json.loads(str(outs["greedy_strings"]))
+    ys4 = O.greedy_decode_ids(sd, ins["feats"], None, cfg["nhead"], cfg["nhead"], max_len=4)
+    assert ys4.tolist() == outs["greedy_ys_len4"].tolist()
+
+
+def test_sce_closed_form_matches_reference_expression():
+    """model/loss.py:78-92 written out literally vs the closed form."""
+    g = torch.Generator().manual_seed(5)
+    z = torch.randn(37, 1531, generator=g) * 3.0
+    y = torch.randint(0, 1531, (37,), generator=g)
+    y[:5] = 0
+    ce = torch.nn.functional.cross_entropy(z, y, ignore_index=0)
+    p = torch.clamp(torch.softmax(z, dim=1), min=1e-7, max=1.0)
+    oh = torch.clamp(torch.nn.functional.one_hot(y, 1531).float(), min=1e-4, max=1.0)
+    want = 0.5 * ce + 0.5 * (-(p * torch.log(oh)).sum(1)).mean()
+    got = O.sce_loss(z, y, 0.5, 0.5, 0)
+    assert abs(float(want) - float(got)) < 1e-5
+
+
+def test_causal_and_cut_semantics():
+    m = O.causal_mask(4)
+    assert m[0, 1] == float("-inf") and m[1, 0] == 0 and m[3, 3] == 0
+    assert O.cut_caption_ids([101, 5, 6, 102, 7]) == [5, 6]
+    assert O.cut_caption_ids([101, 5, 6, 7]) == [5, 6]          # Q11: no [SEP] drops the last token
+    assert O.cut_caption_ids([101, 102]) == []
+
+
+def test_adam_matches_torch_optim():
+    g = torch.Generator().manual_seed(3)
+    p0 = torch.randn(1000, generator=g)
+    p = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([p], lr=1e-4, betas=(0.9, 0.999))
+    po, m, v = p0.clone(), torch.zeros(1000), torch.zeros(1000)
+    for step in range(1, 4):
+        gr = torch.randn(1000, generator=g)
+        p.grad = gr.clone()
+        opt.step()
+        po, m, v = O.adam_step(po, gr, m, v, step, 1e-4)
+        torch.testing.assert_close(po, p.detach(), rtol=1e-6, atol=1e-7)
+
+
+# ---- live reference (build container only) -------------------------------------------------
+needs_ref = pytest.mark.skipif(not ref_shims.reference_available(), reason="/root/reference not mounted")
+
+
+@needs_ref
+def test_oracle_matches_live_reference_fullsize(tokenizer_dir):
+    """Shipped JSON dims through the reference's own MMT4Caption ctor, vs the oracle on its
+    state_dict, vs the committed anchors."""
+    torch.backends.mha.set_fastpath_enabled(False)
+    ref = ref_shims.import_reference_model()
+    cfg = ref_shims.shipped_model_config(tokenizer_dir)
+    torch.manual_seed(666)
+    model = ref.MMT4Caption.MMT4Caption(cfg, device=torch.device("cpu"))
+    model.mode("caption")
+    model.eval()
+    x, vm, tok = synth_inputs(8, 12, 512, 21, 30522, 1234, padded=True)
+    with torch.no_grad():
+        mem, _, _ = model.video_encoder([x], [vm])
+        logits, loss = model.cap_decoder(mem, tok, tok == 0)
+        sd = {k: v for k, v in model.state_dict().items()}
+        omem, ologits, oloss = O.caption_forward(sd, x, vm, tok, 8, 8, 0.5)
+    torch.testing.assert_close(omem, mem, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(ologits, logits, rtol=1e-4, atol=2e-5)
+    assert abs(float(oloss) - float(loss)) < 1e-5
+    anchor = load_anchors()["configs"]["json"]["cases"]["padded"]
+    assert abs(anchor["loss"] - float(loss)) < 1e-5
+    assert logits[0].argmax(-1).tolist() == anchor["logits_argmax_row0"]
