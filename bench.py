@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""Benchmark of the caption hot path (BASELINE.json metric: captions/sec of one train step).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (B200 kernels)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+
+Workload (config.workload): BASELINE configs[1] -- the shipped MSR-VTT clip4clip model (1 encoder + 3
+decoder layers, d_model 768, 8 heads, FFN 2048, vocab 30522, dropout 0.3, SCE loss), batch 64 per GPU,
+synthetic [64, 12, 512] frame features + random token ids (S = 20 decoder positions), one full train
+step = forward + backward + gradient all-reduce (N > 1) + Adam.  Weak scaling: 64 captions per GPU.
+
+Prints ONE JSON line (rank 0).  value = device-timed throughput with inputs resident in HBM; e2e = the
+same step driven through the public API with pinned HOST inputs (H2D copies + loss read-back inside the
+timed region).  roofline = the dominant kernel of the step, timed live with CUDA events.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(ROOT, "video-captioning-transformer_b200"))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+WORKLOAD = "msrvtt-clip4clip 1enc+3dec d768 h8 ff2048 V30522 dropout0.3, train step, B=64/GPU, T=12, S=20"
+B_PER_GPU, T, DIN, S1 = 64, 12, 512, 21
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_train_steps(batch: int, steps: int, warmup: int, threads: int):
+    """fp32 CPU train step of the reference algorithm (oracle/vct_oracle.py restatement: forward,
+    autograd backward, Adam) on synthetic inputs.  Returns (median seconds per step, steps run).
+    NOTE: dropout (p = 0.3 in the reference) is not applied by the port, which only makes this baseline
+    faster than the reference's own CPU path (its bernoulli masks cost ~14 % of a step)."""
+    from oracle import vct_oracle as O
+    from vct.synthetic import synth_batch
+    torch.set_num_threads(threads)
+    d, Fd, V, H = 768, 2048, 30522, 8
+    g = torch.Generator().manual_seed(666)
+
+    def rnd(*shape, scale=0.02):
+        return (torch.randn(*shape, generator=g) * scale)
+
+    sd = {"video_encoder.unify.0.weight": rnd(d, DIN), "video_encoder.unify.0.bias": torch.zeros(d),
+          "video_encoder.temp_emb.pe": O.temporal_sinusoid_table(512, d).unsqueeze(0),
+          "video_encoder.transformer_encoder.norm.weight": torch.ones(d),
+          "video_encoder.transformer_encoder.norm.bias": torch.zeros(d),
+          "cap_decoder.decoder.norm.weight": torch.ones(d), "cap_decoder.decoder.norm.bias": torch.zeros(d),
+          "cap_decoder.generator.weight": rnd(V, d), "cap_decoder.generator.bias": torch.zeros(V),
+          "cap_decoder.tgt_to_emb.weight": rnd(V, d, scale=1.0),
+          "cap_decoder.positional_encoding.pos_embedding": O.sinusoid_table(5000, d)}
+
+    def layer(pre, cross):
+        for a in (["self_attn"] + (["multihead_attn"] if cross else [])):
+            sd[pre + a + ".in_proj_weight"] = rnd(3 * d, d); sd[pre + a + ".in_proj_bias"] = torch.zeros(3 * d)
+            sd[pre + a + ".out_proj.weight"] = rnd(d, d); sd[pre + a + ".out_proj.bias"] = torch.zeros(d)
+        sd[pre + "linear1.weight"] = rnd(Fd, d); sd[pre + "linear1.bias"] = torch.zeros(Fd)
+        sd[pre + "linear2.weight"] = rnd(d, Fd); sd[pre + "linear2.bias"] = torch.zeros(d)
+        for n in (("norm1", "norm2", "norm3") if cross else ("norm1", "norm2")):
+            sd[pre + n + ".weight"] = torch.ones(d); sd[pre + n + ".bias"] = torch.zeros(d)
+
+    layer("video_encoder.transformer_encoder.layers.0.", False)
+    for l in range(3):
+        layer(f"cap_decoder.decoder.layers.{l}.", True)
+    x, vm, tok = synth_batch(batch, T, DIN, S1)
+    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()
+             if not k.endswith(("pos_embedding", "temp_emb.pe"))}
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        _, grads = O.caption_grads(sd, x, vm, tok, H, H, 0.5)
+        for k, gk in grads.items():
+            m, v = state[k]
+            sd[k], m, v = O.adam_step(sd[k], gk, m, v, it + 1, 1e-4)
+            state[k] = (m, v)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    return statistics.median(times), len(times)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # bound the run: probe one small step, then pick the per-step sample so the whole run stays ~2 minutes
+    t_probe, _ = cpu_train_steps(8, 1, 0, threads)
+    est64 = t_probe * 8 * 0.6
+    budget = 150.0
+    batch = 64
+    while batch > 8 and est64 * (batch / 64) * (args.steps + args.warmup) > budget:
+        batch //= 2
+    sec, n = cpu_train_steps(batch, args.steps, args.warmup, threads)
+    val = batch / sec
+    line = {"impl": "reference", "metric": "captions/sec (train step)", "value": val, "unit": "captions/s",
+            "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": sec * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "cpu_sample_batch": batch},
+            "cpu_baseline": {"value": val, "unit": "captions/s", "cores": threads, "kind": "port",
+                             "sample": f"{n} train steps of batch {batch} (fwd+bwd+Adam, fp32, torch CPU kernels, no dropout)"},
+            "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def profile_calls(engine, plans):
+    """Per-launch device time of every C-ABI call of the given plans (CUDA events on the launching
+    stream, eager).  Returns [(name, ms, call)] in issue order."""
+    stream = torch.cuda.current_stream()
+    out = []
+    for plan in plans:
+        for name, fn, a in plan.calls:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rc = fn(*a, stream.cuda_stream)
+            e1.record(stream)
+            if rc != 0:
+                raise RuntimeError(f"{name} failed rc={rc}")
+            out.append((name, e0, e1, a))
+    torch.cuda.synchronize()
+    return [(n, e0.elapsed_time(e1), a) for n, e0, e1, a in out]
+
+
+def gemm_flops(a):
+    g = a[0]._obj
+    return 2.0 * g.M * g.N * g.K
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU")
+    ap.add_argument("--precision", default=os.environ.get("VCT_PRECISION", "bf16"))
+    ap.add_argument("--gemm", default=os.environ.get("VCT_GEMM"))
+    ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    args.warmup = max(args.warmup, 3)
+
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from model.MMT4Caption import MMT4Caption
+    from vct.synthetic import make_tokenizer_dir, shipped_model_config, synth_batch
+    from vct.trainer import CaptionTrainer
+
+    tokdir = os.path.join(ROOT, "gpurun_out", "_tok") if rank == 0 else None
+    if rank == 0:
+        make_tokenizer_dir(tokdir)
+    if world > 1:
+        dist.barrier()
+    tokdir = os.path.join(ROOT, "gpurun_out", "_tok")
+    torch.manual_seed(666)
+    model = MMT4Caption(shipped_model_config(tokdir), device=dev).to(dev)
+    model.vct_precision, model.vct_gemm = args.precision, args.gemm
+    model.mode("caption")
+    model.train()
+    trainer = CaptionTrainer(model, lr=1e-4, betas=(0.9, 0.999), use_graph=not args.no_graph)
+    eng = trainer.engine
+    B = args.batch
+    x, vm, tok = synth_batch(B, T, DIN, S1, seed=1234 + rank)
+    xd, vd, td = x.to(dev), vm.to(dev), tok.to(dev)
+    xh, vh, th = x.pin_memory(), vm.pin_memory(), tok.pin_memory()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- warm-up (also builds plans / captures the graph: needs >= 3 steps) -------------------------
+    for _ in range(max(args.warmup, 3)):
+        trainer.step(xd, vd, td)
+    sync_all()
+    # ---- value: device-resident inputs ----------------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    e0.record()
+    for _ in range(args.steps):
+        loss = trainer.step(xd, vd, td)
+    e1.record()
+    sync_all()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = eng.launches - launches0
+    final_loss = float(loss.item())
+    # ---- e2e: pinned host inputs, H2D + loss read-back every step -----------------------------------
+    sync_all()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        loss = trainer.step(xh, vh, th)
+        _ = loss.item()
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    clocks = sampler.stop() if rank == 0 else None
+    h2d = x.numel() * 4 + vm.numel() + tok.numel() * 8
+    # ---- roofline of the dominant kernel (rank 0): per-launch CUDA-event times of one eager step ------
+    roofline, breakdown = None, None
+    if rank == 0:
+        ws = eng.workspace(B, T, S1 - 1, True)
+        plans = [eng.plan_forward(ws, fused_grad=True, part="all"), eng.plan_backward(ws, sce_first=False, part="all")]
+        profile_calls(eng, plans)                      # warm
+        reps = [profile_calls(eng, plans) for _ in range(3)]
+        names = [r[0] for r in reps[0]]
+        med = [statistics.median(rep[i][1] for rep in reps) for i in range(len(names))]
+        calls = [r[2] for r in reps[0]]
+        a = eng.arena
+        e_ad0, e_ad1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e_ad0.record(); eng.adam(1.0); e_ad1.record(); torch.cuda.synchronize()
+        adam_ms = e_ad0.elapsed_time(e_ad1)
+        total = sum(med) + adam_ms
+        groups = {}
+        for n, m in zip(names, med):
+            k = n.split(":")[0] if not n.startswith("vct_gemm") else ("vct_gemm:generator" if "generator" in n else "vct_gemm:layers")
+            groups[k] = groups.get(k, 0.0) + m
+        groups["vct_adam"] = adam_ms
+        breakdown = {k: round(v, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1])}
+        peaks = measured_peaks()
+        top = max(range(len(names)), key=lambda i: med[i])
+        if adam_ms >= med[top]:
+            nbytes = a.numel * (16 + 12 + (2 if eng.precision == "bf16" else 0))
+            ach = nbytes / (adam_ms * 1e-3) / 1e9
+            roofline = {"kernel": "vct_adam", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms": adam_ms, "peak_source": peaks["src"]}
+        elif names[top].startswith("vct_gemm"):
+            fl = gemm_flops(calls[top])
+            ach = fl / (med[top] * 1e-3) / 1e12
+            roofline = {"kernel": names[top], "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
+                        "frac": ach / peaks["tflops"], "traffic": None, "ms": med[top], "flops": fl,
+                        "peak_source": peaks["src"], "share_of_step": med[top] / total}
+        else:
+            roofline = {"kernel": names[top], "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                        "frac": None, "traffic": None, "ms": med[top], "peak_source": peaks["src"]}
+    # ---- cpu baseline (rank 0, N = 1 only) --------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sec, n = cpu_train_steps(64, 4, 1, threads)
+        cpu = {"value": 64 / sec, "unit": "captions/s", "cores": threads, "kind": "port",
+               "sample": f"{n} train steps of batch 64 (fwd+bwd+Adam, fp32, torch CPU kernels, no dropout), median"}
+    if rank == 0:
+        ms_step = ms_total / args.steps
+        line = {"metric": "captions/sec (train step)", "value": B * world / (ms_step * 1e-3), "unit": "captions/s",
+                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "bf16" if eng.precision == "bf16" else "f32", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                           "gemm": "tcgen05" if eng.gemm_impl == 1 else "simt", "cuda_graph": not args.no_graph,
+                           "l2": "no explicit flush: one step streams ~2.5 GB of weights/moments/activations, 20x the 126 MB L2"},
+                "e2e": {"value": B * world * args.steps / float(e2e_s.item()), "unit": "captions/s",
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+                "gpu_launches": launches, "loss": final_loss, "clocks": clocks, "roofline": roofline,
+                "cpu_baseline": cpu, "kernel_ms": breakdown}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

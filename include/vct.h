@@ -1,0 +1,239 @@
+/*
+ * vct.h -- C ABI of libvct_b200.so: the B200 (sm_100a) kernels behind the
+ * Video-Captioning-Transformer hot path.
+ *
+ * The reference (Kamino666/Video-Captioning-Transformer) has no FFI / plugin interface: its
+ * arithmetic is reached through PyTorch modules.  This header is the
+ * boundary a maintainer would bind instead; every entry point names the reference call it
+ * replaces (file:line under /root/reference, or torch/... for the un-vendored PyTorch code the
+ * reference calls into).  INTEGRATION.md shows the ctypes stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; all pointers are DEVICE pointers unless the name says host
+ *   - caller allocates every output and workspace; nothing is allocated inside
+ *   - asynchronous on the given CUDA stream (a cudaStream_t passed as void*); no host sync
+ *   - returns 0 on success, <0 on error (VCT_ERR_*); text via vct_last_error() (thread-local)
+ *   - row-major, batch-first; "ld" arguments are row strides in ELEMENTS
+ *   - dtype codes: VCT_F32 = 0, VCT_BF16 = 1 (storage type; arithmetic/accumulation is fp32)
+ *   - masks: uint8, 1 = ignore (torch.bool True), like the reference's padding masks
+ *   - dropout: counter-based (Philox4x32-10).  `rng_state` is a device array of two uint64
+ *     {seed, step}; `site` identifies the dropout call site; the mask is a pure function of
+ *     (seed, step, site, element index), so backward regenerates it.  drop_p <= 0 disables.
+ */
+#ifndef VCT_B200_H
+#define VCT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VCT_F32 0
+#define VCT_BF16 1
+
+#define VCT_ERR_INVALID (-1) /* bad argument / unsupported shape */
+#define VCT_ERR_CUDA (-2)    /* CUDA runtime error (launch, attribute, driver entry point) */
+
+typedef void* vct_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------------- */
+int vct_version(void);
+const char* vct_last_error(void);
+/* sm count / compute capability of the current device; fails unless it is sm_100. */
+int vct_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- per-step state ----------------------------------------------------------------------
+ * rng_state: {seed, step}; adam_hyper: float[8] = {lr, beta1, beta2, eps, weight_decay, step,
+ * 1-beta1^step, 1-beta2^step}.  One launch: step += 1 in both, bias corrections recomputed.
+ * Replaces the Python-side bookkeeping of torch.optim.Adam.step (train.py:126) and of the
+ * global torch RNG that nn.Dropout draws from; being a kernel it is CUDA-graph capturable. */
+int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, vct_stream_t stream);
+
+/* ---- GEMM with fused epilogue --------------------------------------------------------------
+ * C[M,N] = epilogue( sum_k opA[m,k] * opB[n,k] )
+ *   a_trans = 0: A is [M,K] (K contiguous);  1: A is stored [K,M] (M contiguous)
+ *   b_trans = 0: B is [N,K] (K contiguous) -- the nn.Linear weight layout;  1: B stored [K,N]
+ * epilogue, in order: + bias[n]; + row_table[(m % row_period), n]; activation; + addend[m,n];
+ * store C (c_dtype) and optionally C2.
+ *   act = VCT_ACT_NONE
+ *   act = VCT_ACT_GELU_FWD : C  = z (pre-activation), C2 = dropout(gelu(z))   [FFN linear1]
+ *   act = VCT_ACT_GELU_BWD : C  = acc * gelu'(aux[m,n]) * dropmask[m,n]        [FFN backward]
+ * Replaces nn.Linear / F.linear calls: model/MMEncoder.py:246 (unify), model/CapDecoder.py:55
+ * (generator), torch/nn/functional.py _in_projection_packed + out_proj inside
+ * multi_head_attention_forward, torch/nn/modules/transformer.py:980-982,1197-1199 (FFN), and the
+ * autograd dgrad / wgrad of each.
+ * impl: VCT_GEMM_SIMT (fp32 FFMA tiles; any dtype mix; the exact path) or VCT_GEMM_TCGEN05
+ * (bf16 operands, TMA + tcgen05.mma, fp32 accumulation in TMEM). */
+#define VCT_ACT_NONE 0
+#define VCT_ACT_GELU_FWD 1
+#define VCT_ACT_GELU_BWD 2
+#define VCT_GEMM_SIMT 0
+#define VCT_GEMM_TCGEN05 1
+
+typedef struct {
+    int M, N, K;
+    const void* A; int a_dtype; long long lda; int a_trans;
+    const void* B; int b_dtype; long long ldb; int b_trans;
+    void* C; int c_dtype; long long ldc;
+    void* C2; int c2_dtype; long long ldc2;          /* optional (NULL) */
+    const float* bias;                               /* [N] or NULL */
+    const float* row_table; int row_period;          /* fp32 [row_period, N] or NULL */
+    const float* addend; long long ld_addend;        /* fp32 [M, N] or NULL (may alias C if c_dtype is F32) */
+    int act;
+    const void* aux; int aux_dtype; long long ld_aux;/* z for VCT_ACT_GELU_BWD */
+    float drop_p; const unsigned long long* rng_state; unsigned int site;
+    int impl;
+} vct_gemm_args;
+
+int vct_gemm(const vct_gemm_args* args, vct_stream_t stream);
+
+/* ---- frame staging -----------------------------------------------------------------------
+ * feats fp32 [B,T,Din] -> out [B*(T+1), Din]: row 0 of each batch element = mean over ALL T
+ * frames (padded ones included), rows 1..T = the frames.  Because unify is linear,
+ * unify(mean) == mean(unify): this lets one GEMM produce the global token and the frame tokens
+ * (model/MMEncoder.py:246-250, GlobalAggregation avg :183-197). */
+int vct_prep_frames(const float* feats, void* out, int out_dtype, int B, int T, int Din, vct_stream_t stream);
+
+/* ---- attention core ------------------------------------------------------------------------
+ * softmax(scale * Q K^T + mask) V per (batch, head), one warp per (b,h), warp-shuffle softmax.
+ * element (b, i, h, c) of q is q[b*q_bs + i*q_ld + h*dh + c]; same for k, v (Lk rows), o.
+ * key_pad: uint8 [B, Lk] or NULL; causal: key j > query i masked (requires Lq == Lk).
+ * probs: optional fp32 [B,H,Lq,Lk] post-softmax, pre-dropout probabilities (need_weights).
+ * Replaces F.scaled_dot_product_attention / the softmax path of
+ * torch/nn/functional.py multi_head_attention_forward incl. mask merge (:6607-6620) and
+ * attention-probability dropout.  Limits: Lq, Lk <= 64, dh <= 128, dh % 4 == 0. */
+typedef struct {
+    int B, H, Lq, Lk, dh;
+    int dtype;                          /* storage type of q, k, v, o and their gradients */
+    const void* q; long long q_ld;
+    const void* k; long long k_ld;
+    const void* v; long long v_ld;
+    void* o; long long o_ld;
+    const unsigned char* key_pad;
+    int causal;
+    float scale;
+    float drop_p; const unsigned long long* rng_state; unsigned int site;
+    float* probs;
+    /* backward only */
+    const void* d_o; long long do_ld;
+    void* dq; long long dq_ld;
+    void* dk; long long dk_ld;
+    void* dv; long long dv_ld;
+    /* batch strides in elements; 0 = dense default (Lq * ld for q/o/dq/d_o, Lk * ld for k/v/dk/dv).
+     * Non-default strides let incremental decoding attend over a [B, Lmax, 3d] K/V cache. */
+    long long q_bs, k_bs, v_bs, o_bs, do_bs, dq_bs, dk_bs, dv_bs;
+} vct_attn_args;
+
+int vct_attn_fwd(const vct_attn_args* args, vct_stream_t stream);
+int vct_attn_bwd(const vct_attn_args* args, vct_stream_t stream);
+
+/* ---- the three attention flavours of the reference (projection + core) ----------------------
+ * x      : [B*L, d]   (x_dtype)            query-side input rows
+ * mem    : [B*Lk, d]  cross only; NULL for self-attention
+ * w_in   : [3d, d] packed q,k,v (w_dtype), b_in fp32 [3d]   (nn.MultiheadAttention.in_proj_*)
+ * qkv    : workspace / saved-for-backward [B*L, 3d] (self) ; q [B*L, d] + kv [B*Lk, 2d] (cross)
+ * o      : [B*L, d] attention output BEFORE out_proj
+ * enc self  : key-padding mask [B,L]   (torch/nn/modules/transformer.py:961-978)
+ * dec self  : causal + key-padding     (torch/nn/modules/transformer.py:1158-1175)
+ * dec cross : NO mask      (torch/nn/modules/transformer.py:1177-1195); if kv_ready
+ *             is nonzero the K/V projection of `mem` is taken from `kv` as is (decode reuses it). */
+typedef struct {
+    int B, L, Lk, d, H;
+    int dtype;                           /* storage type of x, mem, w_in, qkv/q/kv, o */
+    const void* x; const void* mem;
+    const void* w_in; const float* b_in;
+    void* qkv; void* kv; int kv_ready;
+    void* o;
+    const unsigned char* key_pad;
+    float drop_p; const unsigned long long* rng_state; unsigned int site;
+    float* probs;
+    int gemm_impl;
+} vct_mha_args;
+
+int vct_attn_enc_self_fwd(const vct_mha_args* args, vct_stream_t stream);
+int vct_attn_dec_self_fwd(const vct_mha_args* args, vct_stream_t stream);
+int vct_attn_dec_cross_fwd(const vct_mha_args* args, vct_stream_t stream);
+
+/* ---- residual + dropout + LayerNorm ---------------------------------------------------------
+ * s = x + dropout(r)   (x may be NULL: s = r, no dropout)   ;  y = LN(s) * gamma + beta, eps 1e-5
+ * writes y (fp32), optionally y_c (y_c_dtype copy for the next GEMM), s_out (fp32 pre-LN sum,
+ * may alias r), mean/rstd [R] for backward.  One warp per row.  d % 4 == 0, d <= 1024.
+ * Replaces x = norm(x + dropout(sublayer(x))) of torch/nn/modules/transformer.py:946-959,
+ * 1131-1156 and the final nn.LayerNorm of both stacks (model/MMEncoder.py:238,
+ * model/CapDecoder.py:20). */
+int vct_ln_residual_fwd(const float* x, const float* r, const float* gamma, const float* beta,
+                        float* y, void* y_c, int y_c_dtype, float* s_out, float* mean, float* rstd,
+                        int R, int d, float drop_p, const unsigned long long* rng_state, unsigned int site,
+                        vct_stream_t stream);
+
+/* backward: dy fp32 [R,d] -> ds fp32 (gradient wrt s: goes to the residual input as is) and
+ * dr_c (dr_dtype) = ds * dropmask (gradient wrt the branch output r; GEMM operand).
+ * Column sums: dgamma += sum dy*xhat, dbeta += sum dy, dbias_r = sum dr (bias gradient of the
+ * linear that produced r; NULL to skip).  `partials` is a fp32 workspace of
+ * vct_ln_bwd_workspace_floats(R, d) floats, `counter` a zero-initialised uint32 (self-resetting).
+ * dgamma/dbeta/dbias_r are OVERWRITTEN (deterministic two-level reduction, no atomics on data). */
+long long vct_ln_bwd_workspace_floats(int R, int d);
+int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
+                        float* ds, void* dr_c, int dr_dtype, float* dgamma, float* dbeta, float* dbias_r,
+                        float* partials, unsigned int* counter,
+                        int R, int d, float drop_p, const unsigned long long* rng_state, unsigned int site,
+                        vct_stream_t stream);
+
+/* ---- token embedding + positional table ------------------------------------------------------
+ * x[b,s,:] = dropout(E[ids[b*ids_ld + s], :] + pos[s, :])   (no sqrt(d) scaling)
+ * model/CapDecoder.py:48 + model/Embedding.py:23-25.  ids int64.  Writes x fp32 and optional x_c.
+ * pos_offset: position of column 0 (incremental decode embeds one new column at a time). */
+int vct_embed_fwd(const long long* ids, long long ids_ld, const float* E, const float* pos,
+                  float* x, void* x_c, int x_c_dtype, int B, int S, int d, int V, int pos_offset,
+                  float drop_p, const unsigned long long* rng_state, unsigned int site, vct_stream_t stream);
+/* dE[ids] += dropmask * dx  (dE pre-zeroed; rows with id == pad_id receive nothing: padding_idx) */
+int vct_embed_bwd(const long long* ids, long long ids_ld, const float* dx, float* dE, int B, int S, int d, int V,
+                  int pad_id, float drop_p, const unsigned long long* rng_state, unsigned int site,
+                  vct_stream_t stream);
+
+/* ---- SCE loss (model/loss.py:69-92; closed form SURVEY Q9) -----------------------------------
+ * logits fp32 [N, ld_logits] (N = B*S), label of row (b,s) = ids[b*ids_ld + s + 1].
+ * loss = alpha * mean_{label != pad}(lse - z_y) + beta * mean_all( A * sum_{c != y} clamp(p_c,1e-7,1) )
+ * (alpha == 1: plain cross entropy, model/CapDecoder.py:28-30).
+ * One CTA per row; the row is staged in shared memory once (bulk async copy) and all passes run
+ * from there.  If loss_out != NULL writes the scalar loss (row_parts: fp32 workspace [N,2],
+ * counter: zero-initialised uint32, self-resetting).  If dlogits != NULL writes
+ * d loss / d logits * (*upstream or 1) in dl_dtype with row stride ld_dl (columns V..ld_dl-1 are
+ * zeroed so the buffer can feed a GEMM whose K is padded). */
+int vct_sce(const float* logits, long long ld_logits, const long long* ids, long long ids_ld,
+            int B, int S, int V, float alpha, float beta, int pad_id,
+            float* loss_out, float* row_parts, unsigned int* counter,
+            void* dlogits, int dl_dtype, long long ld_dl, const float* upstream,
+            vct_stream_t stream);
+
+/* ---- column sums (bias gradients): out[n] = sum_m X[m,n]; deterministic ----------------------
+ * partials: fp32 workspace vct_colsum_workspace_floats(M, N); counter as above. */
+long long vct_colsum_workspace_floats(int M, int N);
+int vct_colsum(const void* X, int dtype, long long ld, int M, int N, float* out, float* partials,
+               unsigned int* counter, vct_stream_t stream);
+
+/* ---- Adam over the flat parameter arena (torch.optim.Adam semantics, train.py:22-31,126) -----
+ * p, g, m, v: fp32 [n]; hyper: the float[8] of vct_step_tick (already ticked for this step);
+ * grad_scale multiplies g first (1/world_size after a SUM all-reduce).  If p_c != NULL also
+ * writes the bf16 shadow copy the tensor-core GEMMs read next step. */
+int vct_adam(float* p, const float* g, float* m, float* v, void* p_c, long long n, const float* hyper,
+             float grad_scale, vct_stream_t stream);
+
+/* fp32 -> dtype copy (initial bf16 shadow of the parameters, input staging) */
+int vct_cast(const float* src, void* dst, int dst_dtype, long long n, vct_stream_t stream);
+
+/* ---- greedy decode step tail (model/MMT4Caption.py:165-172) ----------------------------------
+ * next[b] = argmax_v logits[b, :V] (lowest index on ties, like torch.max); ys[b, t] = next[b];
+ * ended[b] |= (next[b] == end_id); *n_ended = number of ended rows (device int32). */
+int vct_argmax_append(const float* logits, long long ld_logits, int B, int V, long long* ys, long long ys_ld, int t,
+                      int end_id, int* ended, int* n_ended, vct_stream_t stream);
+
+/* ---- debug: the keep mask (1 = kept) of `n` elements of a dropout site ----------------------- */
+int vct_dropout_mask(unsigned char* out, long long n, float drop_p, const unsigned long long* rng_state,
+                     unsigned int site, vct_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VCT_B200_H */

@@ -1,0 +1,70 @@
+"""world_size-2 gloo test (CPU) of the data-parallel gradient exchange used by CaptionTrainer:
+bucketed SUM all-reduce over the flat gradient arena + the 1/world scale folded into Adam gives every
+rank the mean gradient and keeps the replicas bit-identical."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, ret):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "video-captioning-transformer_b200"))
+    sys.path.insert(0, root)
+    from vct.arena import ParamArena
+    from vct.trainer import gradient_buckets, all_reduce_flat
+    from oracle import vct_oracle as O
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(0)                         # identical replicas
+    enc, dec = torch.nn.Linear(64, 96), torch.nn.Linear(96, 33)
+    named = [("video_encoder." + n, p) for n, p in enc.named_parameters()] + \
+            [("cap_decoder." + n, p) for n, p in dec.named_parameters()]
+    arena = ParamArena(named, torch.device("cpu"))
+    buckets = gradient_buckets(arena, ["video_encoder.", "cap_decoder."], max_bytes=4 * 1000)
+    # rank-local shard of a global batch (rows [r*B/N, (r+1)*B/N))
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(8, 64, generator=g), torch.randn(8, 33, generator=g)
+    xs, ys = X[rank * 4:(rank + 1) * 4], Y[rank * 4:(rank + 1) * 4]
+    loss = ((dec(torch.relu(enc(xs))) - ys) ** 2).mean()
+    grads = torch.autograd.grad(loss, [p for _, p in named])
+    for (n, _), gr in zip(named, grads):
+        arena.grad_view(n).copy_(gr)
+    all_reduce_flat(arena.grad, buckets)
+    m, v = torch.zeros_like(arena.p32), torch.zeros_like(arena.p32)
+    p_new, _, _ = O.adam_step(arena.p32, arena.grad * (1.0 / world), m, v, 1, 1e-3)
+    # single-process reference on the full batch: equal shard sizes => mean of shard grads == global grad
+    torch.manual_seed(0)
+    enc2, dec2 = torch.nn.Linear(64, 96), torch.nn.Linear(96, 33)
+    full = ((dec2(torch.relu(enc2(X))) - Y) ** 2).mean()
+    gfull = torch.autograd.grad(full, list(enc2.parameters()) + list(dec2.parameters()))
+    ok = True
+    for (n, _), gr in zip(named, gfull):
+        ok &= torch.allclose(arena.grad_view(n) / world, gr, rtol=1e-5, atol=1e-6)
+    gathered = [torch.zeros_like(p_new) for _ in range(world)]
+    dist.all_gather(gathered, p_new)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    if rank == 0:
+        ret["ok"], ret["same"] = bool(ok), bool(same)
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_gives_mean_gradient_and_identical_replicas():
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret["ok"], "mean of per-rank gradients != global-batch gradient"
+    assert ret["same"], "replicas diverged after the update"

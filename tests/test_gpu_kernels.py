@@ -1,0 +1,392 @@
+"""Kernel-level parity: every C-ABI entry point against fp32 PyTorch arithmetic / the oracle on the same
+seeded inputs (run on the B200 box: ``pytest -m gpu``).  Tolerances are written next to each check."""
+import ctypes as C
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from vct import lib as L  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def lib():
+    return L.load()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def tdt(code):
+    return torch.bfloat16 if code == L.BF16 else torch.float32
+
+
+def run_gemm(lib, A, B, a_trans, b_trans, M, N, K, c_dtype=L.F32, impl=L.GEMM_SIMT, **kw):
+    g = L.GemmArgs()
+    g.M, g.N, g.K = M, N, K
+    dt = L.BF16 if A.dtype == torch.bfloat16 else L.F32
+    g.A, g.a_dtype, g.lda, g.a_trans = A.data_ptr(), dt, A.stride(0), a_trans
+    g.B, g.b_dtype, g.ldb, g.b_trans = B.data_ptr(), dt, B.stride(0), b_trans
+    ldc = kw.get("ldc", N)
+    Cc = torch.full((M, ldc), float("nan"), dtype=tdt(c_dtype), device=DEV)
+    g.C, g.c_dtype, g.ldc = Cc.data_ptr(), c_dtype, ldc
+    C2 = None
+    if kw.get("c2_dtype") is not None:
+        C2 = torch.full((M, N), float("nan"), dtype=tdt(kw["c2_dtype"]), device=DEV)
+        g.C2, g.c2_dtype, g.ldc2 = C2.data_ptr(), kw["c2_dtype"], N
+    keep = []
+    for name in ("bias", "row_table", "addend", "aux", "rng_state"):
+        t = kw.get(name)
+        if t is not None:
+            keep.append(t)
+            setattr(g, name, t.data_ptr())
+    g.row_period = kw.get("row_period", 0)
+    g.ld_addend = N
+    g.ld_aux = N
+    g.aux_dtype = L.BF16 if (kw.get("aux") is not None and kw["aux"].dtype == torch.bfloat16) else L.F32
+    g.act = kw.get("act", L.ACT_NONE)
+    g.drop_p = kw.get("drop_p", 0.0)
+    g.site = kw.get("site", 0)
+    g.impl = impl
+    L.check(lib.vct_gemm(C.byref(g), stream()), "vct_gemm")
+    torch.cuda.synchronize()
+    return Cc, C2
+
+
+def make_operands(M, N, K, a_trans, b_trans, dtype, seed=0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    Ad = (A.t().contiguous() if a_trans else A).to(DEV, dtype)
+    Bd = (B.t().contiguous() if b_trans else B).to(DEV, dtype)
+    # reference operands after the storage rounding
+    Ar = (Ad.t() if a_trans else Ad).float()
+    Br = (Bd.t() if b_trans else Bd).float()
+    return Ad, Bd, Ar, Br
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("a_trans,b_trans", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 136, 72), (37, 211, 40), (260, 48, 1000)])
+def test_gemm_simt_layouts(lib, dtype, a_trans, b_trans, M, N, K):
+    if dtype == torch.bfloat16 and (M % 8 or N % 8 or K % 8):
+        M, N, K = (M + 7) // 8 * 8, (N + 7) // 8 * 8, (K + 7) // 8 * 8
+    Ad, Bd, Ar, Br = make_operands(M, N, K, a_trans, b_trans, dtype)
+    Cc, _ = run_gemm(lib, Ad, Bd, a_trans, b_trans, M, N, K)
+    want = Ar.double() @ Br.double().t()
+    # fp32 accumulation of exactly-represented products: error ~ K * eps * |terms|
+    torch.testing.assert_close(Cc.double(), want, rtol=1e-4, atol=1e-4 * math.sqrt(K))
+
+
+def test_gemm_epilogue_bias_table_addend_and_bf16_out(lib):
+    M, N, K = 130, 96, 64
+    Ad, Bd, Ar, Br = make_operands(M, N, K, 0, 0, torch.float32, seed=1)
+    g = torch.Generator().manual_seed(2)
+    bias = torch.randn(N, generator=g).to(DEV)
+    table = torch.randn(13, N, generator=g).to(DEV)
+    addend = torch.randn(M, N, generator=g).to(DEV)
+    Cc, C2 = run_gemm(lib, Ad, Bd, 0, 0, M, N, K, bias=bias, row_table=table, row_period=13, addend=addend,
+                      c2_dtype=L.BF16)
+    rows = torch.arange(M, device=DEV) % 13
+    want = Ar @ Br.t() + bias + table[rows] + addend
+    torch.testing.assert_close(Cc, want, rtol=1e-4, atol=1e-3)
+    torch.testing.assert_close(C2.float(), want, rtol=1e-2, atol=1e-2)     # bf16 rounding of the same values
+
+
+def test_gemm_gelu_forward_and_backward_epilogues(lib):
+    M, N, K = 64, 128, 48
+    Ad, Bd, Ar, Br = make_operands(M, N, K, 0, 0, torch.float32, seed=3)
+    bias = torch.randn(N, generator=torch.Generator().manual_seed(4)).to(DEV)
+    z, h = run_gemm(lib, Ad, Bd, 0, 0, M, N, K, bias=bias, act=L.ACT_GELU_FWD, c2_dtype=L.F32)
+    zw = Ar @ Br.t() + bias
+    torch.testing.assert_close(z, zw, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(h, torch.nn.functional.gelu(zw), rtol=1e-4, atol=1e-4)
+    # backward epilogue: C = acc * gelu'(aux)
+    zz = zw.clone().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    Cc, _ = run_gemm(lib, Ad, Bd, 0, 0, M, N, K, act=L.ACT_GELU_BWD, aux=zw.contiguous())
+    torch.testing.assert_close(Cc, (Ar @ Br.t()) * zz.grad, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_dropout_mask_is_consistent_between_forward_backward_and_debug_entry(lib):
+    M, N, K = 64, 256, 32
+    Ad, Bd, Ar, Br = make_operands(M, N, K, 0, 0, torch.float32, seed=5)
+    rng = torch.tensor([1234, 7], dtype=torch.int64, device=DEV)
+    p = 0.3
+    z, h = run_gemm(lib, Ad, Bd, 0, 0, M, N, K, act=L.ACT_GELU_FWD, c2_dtype=L.F32, drop_p=p, rng_state=rng, site=42)
+    mask = torch.empty(M * N, dtype=torch.uint8, device=DEV)
+    L.check(lib.vct_dropout_mask(mask.data_ptr(), M * N, p, rng.data_ptr(), 42, stream()))
+    torch.cuda.synchronize()
+    keep = mask.view(M, N).bool()
+    want = torch.nn.functional.gelu(z) * keep / (1 - p)
+    torch.testing.assert_close(h, want, rtol=1e-5, atol=1e-6)
+    rate = keep.float().mean().item()
+    assert abs(rate - (1 - p)) < 0.02, rate                     # keep-rate statistics
+    Cc, _ = run_gemm(lib, Ad, Bd, 0, 0, M, N, K, act=L.ACT_GELU_BWD, aux=z.contiguous(), drop_p=p, rng_state=rng, site=42)
+    zz = z.clone().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    torch.testing.assert_close(Cc, (Ar @ Br.t()) * zz.grad * keep / (1 - p), rtol=1e-4, atol=1e-4)
+    # a different step or site gives a different mask
+    rng2 = torch.tensor([1234, 8], dtype=torch.int64, device=DEV)
+    mask2 = torch.empty(M * N, dtype=torch.uint8, device=DEV)
+    L.check(lib.vct_dropout_mask(mask2.data_ptr(), M * N, p, rng2.data_ptr(), 42, stream()))
+    torch.cuda.synchronize()
+    assert (mask2 != mask).float().mean().item() > 0.2
+
+
+def torch_attention(q, k, v, key_pad, causal, scale):
+    s = torch.einsum("bihc,bjhc->bhij", q, k) * scale
+    if key_pad is not None:
+        s = s.masked_fill(key_pad[:, None, None, :].bool(), float("-inf"))
+    if causal:
+        L_ = s.shape[-1]
+        s = s + torch.triu(torch.full((L_, L_), float("-inf"), device=s.device), diagonal=1)
+    p = torch.softmax(s, dim=-1)
+    return torch.einsum("bhij,bjhc->bihc", p, v), p
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,causal,pad", [(3, 8, 13, 13, 96, 0, True), (4, 8, 20, 20, 96, 1, True),
+                                                     (2, 8, 20, 13, 64, 0, False), (2, 4, 33, 33, 96, 0, True),
+                                                     (2, 2, 7, 40, 16, 0, True), (5, 2, 1, 9, 24, 0, False)])
+def test_attention_forward_backward(lib, dtype, B, H, Lq, Lk, dh, causal, pad):
+    g = torch.Generator().manual_seed(B * 100 + Lq)
+    d = H * dh
+    q = torch.randn(B, Lq, H, dh, generator=g).to(DEV, dtype)
+    k = torch.randn(B, Lk, H, dh, generator=g).to(DEV, dtype)
+    v = torch.randn(B, Lk, H, dh, generator=g).to(DEV, dtype)
+    do = torch.randn(B, Lq, H, dh, generator=g).to(DEV, dtype)
+    key_pad = None
+    if pad:
+        key_pad = torch.zeros(B, Lk, dtype=torch.uint8)
+        for b in range(1, B):
+            key_pad[b, Lk - b:] = 1                      # column 0 never padded
+        key_pad = key_pad.to(DEV)
+    o = torch.full_like(q, float("nan"))
+    probs = torch.zeros(B, H, Lq, Lk, device=DEV)
+    dq, dk, dv = torch.full_like(q, float("nan")), torch.full_like(k, float("nan")), torch.full_like(v, float("nan"))
+    a = L.AttnArgs()
+    a.B, a.H, a.Lq, a.Lk, a.dh = B, H, Lq, Lk, dh
+    a.dtype = L.BF16 if dtype == torch.bfloat16 else L.F32
+    a.q, a.q_ld, a.k, a.k_ld, a.v, a.v_ld, a.o, a.o_ld = q.data_ptr(), d, k.data_ptr(), d, v.data_ptr(), d, o.data_ptr(), d
+    a.key_pad = key_pad.data_ptr() if key_pad is not None else None
+    a.causal, a.scale = causal, 1.0 / math.sqrt(dh)
+    a.probs = probs.data_ptr()
+    a.d_o, a.do_ld, a.dq, a.dq_ld, a.dk, a.dk_ld, a.dv, a.dv_ld = do.data_ptr(), d, dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d
+    L.check(lib.vct_attn_fwd(C.byref(a), stream()), "fwd")
+    L.check(lib.vct_attn_bwd(C.byref(a), stream()), "bwd")
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    ow, pw = torch_attention(qf, kf, vf, key_pad, causal, a.scale)
+    (ow * do.float()).sum().backward()
+    tol = dict(rtol=2e-2, atol=2e-2) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=2e-5)
+    torch.testing.assert_close(probs, pw.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(o.float(), ow.detach(), **tol)
+    torch.testing.assert_close(dq.float(), qf.grad, **tol)
+    torch.testing.assert_close(dk.float(), kf.grad, **tol)
+    torch.testing.assert_close(dv.float(), vf.grad, **tol)
+
+
+@pytest.mark.parametrize("R,d", [(40, 768), (1280, 768), (33, 512), (7, 32), (100, 48), (9, 1024)])
+def test_ln_residual_forward_backward(lib, R, d):
+    g = torch.Generator().manual_seed(R + d)
+    x = torch.randn(R, d, generator=g).to(DEV)
+    r = torch.randn(R, d, generator=g).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(d, generator=g)).to(DEV)
+    beta = (0.1 * torch.randn(d, generator=g)).to(DEV)
+    dy = torch.randn(R, d, generator=g).to(DEV)
+    y = torch.empty(R, d, device=DEV)
+    y_c = torch.empty(R, d, device=DEV, dtype=torch.bfloat16)
+    s = torch.empty(R, d, device=DEV)
+    mean, rstd = torch.empty(R, device=DEV), torch.empty(R, device=DEV)
+    L.check(lib.vct_ln_residual_fwd(x.data_ptr(), r.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                    y_c.data_ptr(), L.BF16, s.data_ptr(), mean.data_ptr(), rstd.data_ptr(), R, d, 0.0,
+                                    None, 0, stream()))
+    xs = (x + r).requires_grad_(True)
+    gp, bp = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    yw = torch.nn.functional.layer_norm(xs, (d,), gp, bp, 1e-5)
+    yw.backward(dy)
+    torch.cuda.synchronize()
+    torch.testing.assert_close(s, xs.detach(), rtol=0, atol=0)
+    torch.testing.assert_close(y, yw.detach(), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(y_c.float(), yw.detach(), rtol=1e-2, atol=1e-2)
+    ds = torch.empty(R, d, device=DEV)
+    dr = torch.empty(R, d, device=DEV)
+    dgamma, dbeta, dbias = torch.empty(d, device=DEV), torch.empty(d, device=DEV), torch.empty(d, device=DEV)
+    nws = lib.vct_ln_bwd_workspace_floats(R, d)
+    partials = torch.empty(nws, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    for _ in range(2):   # twice: the self-resetting counter must allow re-use
+        L.check(lib.vct_ln_residual_bwd(dy.data_ptr(), s.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                        ds.data_ptr(), dr.data_ptr(), L.F32, dgamma.data_ptr(), dbeta.data_ptr(),
+                                        dbias.data_ptr(), partials.data_ptr(), counter.data_ptr(), R, d, 0.0, None, 0, stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(ds, xs.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dr, xs.grad, rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(dgamma, gp.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dbeta, bp.grad, rtol=1e-4, atol=1e-4)
+    torch.testing.assert_close(dbias, xs.grad.sum(0), rtol=1e-4, atol=1e-4)
+    assert int(counter.item()) == 0
+
+
+def test_ln_without_residual_and_with_dropout(lib):
+    R, d, p = 64, 768, 0.3
+    g = torch.Generator().manual_seed(9)
+    x = torch.randn(R, d, generator=g).to(DEV)
+    r = torch.randn(R, d, generator=g).to(DEV)
+    gamma, beta = torch.ones(d, device=DEV), torch.zeros(d, device=DEV)
+    y = torch.empty(R, d, device=DEV)
+    L.check(lib.vct_ln_residual_fwd(None, r.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), None, L.F32, None,
+                                    None, None, R, d, p, None, 0, stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(y, torch.nn.functional.layer_norm(r, (d,)), rtol=1e-5, atol=1e-5)
+    rng = torch.tensor([5, 3], dtype=torch.int64, device=DEV)
+    s = torch.empty(R, d, device=DEV)
+    L.check(lib.vct_ln_residual_fwd(x.data_ptr(), r.data_ptr(), gamma.data_ptr(), beta.data_ptr(), y.data_ptr(), None, L.F32,
+                                    s.data_ptr(), None, None, R, d, p, rng.data_ptr(), 77, stream()))
+    mask = torch.empty(R * d, dtype=torch.uint8, device=DEV)
+    L.check(lib.vct_dropout_mask(mask.data_ptr(), R * d, p, rng.data_ptr(), 77, stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(s, x + r * mask.view(R, d) / (1 - p), rtol=1e-6, atol=1e-6)
+
+
+def test_embedding_forward_backward(lib):
+    B, S, d, V = 5, 9, 64, 300
+    g = torch.Generator().manual_seed(11)
+    ids = torch.randint(0, V, (B, S + 1), generator=g)
+    ids[0, 3] = 0
+    ids[1, 2] = ids[1, 5]                       # duplicate token: scatter-add
+    E = torch.randn(V, d, generator=g).to(DEV)
+    pos = torch.randn(50, d, generator=g).to(DEV)
+    idd = ids.to(DEV)
+    x = torch.empty(B * S, d, device=DEV)
+    x_c = torch.empty(B * S, d, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vct_embed_fwd(idd.data_ptr(), S + 1, E.data_ptr(), pos.data_ptr(), x.data_ptr(), x_c.data_ptr(), L.BF16,
+                              B, S, d, V, 0, 0.0, None, 0, stream()))
+    torch.cuda.synchronize()
+    want = E[idd[:, :S]] + pos[:S]
+    torch.testing.assert_close(x.view(B, S, d), want, rtol=0, atol=0)
+    torch.testing.assert_close(x_c.float().view(B, S, d), want, rtol=1e-2, atol=1e-2)
+    dx = torch.randn(B * S, d, generator=g).to(DEV)
+    dE = torch.zeros(V, d, device=DEV)
+    L.check(lib.vct_embed_bwd(idd.data_ptr(), S + 1, dx.data_ptr(), dE.data_ptr(), B, S, d, V, 0, 0.0, None, 0, stream()))
+    torch.cuda.synchronize()
+    Ew = E.clone().requires_grad_(True)
+    torch.nn.functional.embedding(idd[:, :S], Ew, padding_idx=0).backward(dx.view(B, S, d))
+    torch.testing.assert_close(dE, Ew.grad, rtol=1e-5, atol=1e-6)
+    assert dE[0].abs().sum().item() == 0.0      # padding_idx row
+
+
+@pytest.mark.parametrize("alpha", [0.5, 1.0])
+@pytest.mark.parametrize("B,S,V", [(4, 7, 211), (8, 20, 30522), (3, 5, 1000)])
+def test_sce_forward_backward_against_oracle(lib, alpha, B, S, V):
+    from oracle import vct_oracle as O
+    g = torch.Generator().manual_seed(V + B)
+    N = B * S
+    Vp = (V + 7) // 8 * 8
+    logits = (torch.randn(N, V, generator=g) * 2.0)
+    ids = torch.randint(1, V, (B, S + 1), generator=g)
+    ids[1, 4:] = 0
+    zz = logits.clone().requires_grad_(True)
+    want = O.sce_loss(zz, ids[:, 1:].reshape(-1), alpha, 1 - alpha, 0)
+    want.backward()
+    z = torch.zeros(N, Vp)
+    z[:, :V] = logits
+    z, idd = z.to(DEV), ids.to(DEV)
+    loss = torch.zeros(1, device=DEV)
+    parts = torch.empty(N, 2, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dl = torch.full((N, Vp), float("nan"), device=DEV)
+    for _ in range(2):
+        L.check(lib.vct_sce(z.data_ptr(), Vp, idd.data_ptr(), S + 1, B, S, V, alpha, 1 - alpha, 0, loss.data_ptr(),
+                            parts.data_ptr(), counter.data_ptr(), dl.data_ptr(), L.F32, Vp, None, stream()))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - want.item()) < 2e-5 * max(1.0, abs(want.item()))
+    torch.testing.assert_close(dl[:, :V].cpu(), zz.grad, rtol=2e-4, atol=1e-8)
+    assert dl[:, V:].abs().sum().item() == 0.0
+    # upstream scaling + bf16 gradient output
+    up = torch.tensor([0.25], device=DEV)
+    dlb = torch.empty((N, Vp), device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vct_sce(z.data_ptr(), Vp, idd.data_ptr(), S + 1, B, S, V, alpha, 1 - alpha, 0, None, None, None,
+                        dlb.data_ptr(), L.BF16, Vp, up.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dlb[:, :V].float().cpu(), 0.25 * zz.grad, rtol=1e-2, atol=1e-7)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("M,N,ld", [(1280, 768, 768), (100, 30522, 30528), (7, 40, 48)])
+def test_colsum(lib, dtype, M, N, ld):
+    X = torch.randn(M, ld, generator=torch.Generator().manual_seed(M)).to(DEV, dtype)
+    out = torch.empty(N, device=DEV)
+    partials = torch.empty(lib.vct_colsum_workspace_floats(M, N), device=DEV)
+    counters = torch.zeros(256, dtype=torch.int32, device=DEV)
+    for _ in range(2):
+        L.check(lib.vct_colsum(X.data_ptr(), L.BF16 if dtype == torch.bfloat16 else L.F32, ld, M, N, out.data_ptr(),
+                               partials.data_ptr(), counters.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(out, X[:, :N].float().sum(0), rtol=1e-4, atol=1e-3)
+    assert int(counters.sum().item()) == 0
+
+
+def test_adam_matches_torch_optim_and_writes_bf16_shadow(lib):
+    from oracle import vct_oracle as O
+    n = 4096 + 64
+    g = torch.Generator().manual_seed(21)
+    p0 = torch.randn(n, generator=g)
+    p = p0.clone().to(DEV)
+    m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    shadow = torch.empty(n, device=DEV, dtype=torch.bfloat16)
+    hyper = torch.tensor([1e-4, 0.9, 0.999, 1e-8, 0.0, 0.0, 0.0, 0.0], device=DEV)
+    rng = torch.tensor([1, 0], dtype=torch.int64, device=DEV)
+    tp = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.Adam([tp], lr=1e-4, betas=(0.9, 0.999))
+    for step in range(1, 4):
+        gr = torch.randn(n, generator=g)
+        tp.grad = gr.clone()
+        opt.step()
+        L.check(lib.vct_step_tick(rng.data_ptr(), hyper.data_ptr(), stream()))
+        L.check(lib.vct_adam(p.data_ptr(), gr.to(DEV).data_ptr(), m.data_ptr(), v.data_ptr(), shadow.data_ptr(), n,
+                             hyper.data_ptr(), 1.0, stream()))
+        torch.cuda.synchronize()
+        torch.testing.assert_close(p.cpu(), tp.detach(), rtol=1e-6, atol=1e-7)
+    assert int(rng[1].item()) == 3 and hyper[5].item() == 3.0
+    torch.testing.assert_close(shadow.float(), p.to(torch.bfloat16).float(), rtol=0, atol=0)
+
+
+def test_prep_frames_and_cast(lib):
+    B, T, Din = 3, 12, 512
+    feats = torch.randn(B, T, Din, generator=torch.Generator().manual_seed(4)).to(DEV)
+    out = torch.empty(B * (T + 1), Din, device=DEV)
+    L.check(lib.vct_prep_frames(feats.data_ptr(), out.data_ptr(), L.F32, B, T, Din, stream()))
+    torch.cuda.synchronize()
+    o = out.view(B, T + 1, Din)
+    torch.testing.assert_close(o[:, 1:], feats, rtol=0, atol=0)
+    torch.testing.assert_close(o[:, 0], feats.mean(1), rtol=1e-6, atol=1e-6)
+    src = torch.randn(1003, device=DEV)
+    dst = torch.empty(1003, device=DEV, dtype=torch.bfloat16)
+    L.check(lib.vct_cast(src.data_ptr(), dst.data_ptr(), L.BF16, 1003, stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dst, src.to(torch.bfloat16), rtol=0, atol=0)
+
+
+def test_argmax_append_ties_and_end_flags(lib):
+    B, V, ld = 4, 30522, 30528
+    logits = torch.randn(B, ld, generator=torch.Generator().manual_seed(8)).to(DEV)
+    logits[0, 77] = 50.0
+    logits[0, 5000] = 50.0                       # tie -> lowest index (torch.max semantics, Q11)
+    logits[1, 102] = 60.0                        # end token
+    logits[2, V:] = 1e9                          # padding columns must be ignored
+    ys = torch.zeros(B, 6, dtype=torch.int64, device=DEV)
+    ended = torch.zeros(B, dtype=torch.int32, device=DEV)
+    n_ended = torch.zeros(1, dtype=torch.int32, device=DEV)
+    L.check(lib.vct_argmax_append(logits.data_ptr(), ld, B, V, ys.data_ptr(), 6, 2, 102, ended.data_ptr(),
+                                  n_ended.data_ptr(), stream()))
+    torch.cuda.synchronize()
+    assert ys[1:, 2].tolist() == logits[1:, :V].argmax(1).tolist()
+    assert ys[0, 2].item() == 77 and ys[1, 2].item() == 102
+    assert ended.tolist() == [0, 1, 0, 0] and n_ended.item() == 1

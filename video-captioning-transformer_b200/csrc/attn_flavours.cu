@@ -1,0 +1,81 @@
+// The three attention flavours of the reference as single C-ABI calls:
+// packed in-projection (GEMM with bias epilogue) followed by the attention core.
+#include "common.cuh"
+
+using namespace vct;
+
+namespace {
+
+size_t esize(int dtype) { return dtype == VCT_BF16 ? 2 : 4; }
+
+int project(const void* x, int rows, int d, int n_out, const void* w, const float* b, void* out, int dtype, int impl,
+            vct_stream_t stream) {
+    vct_gemm_args g;
+    memset(&g, 0, sizeof(g));
+    g.M = rows; g.N = n_out; g.K = d;
+    g.A = x; g.a_dtype = dtype; g.lda = d; g.a_trans = 0;
+    g.B = w; g.b_dtype = dtype; g.ldb = d; g.b_trans = 0;
+    g.C = out; g.c_dtype = dtype; g.ldc = n_out;
+    g.bias = b;
+    g.act = VCT_ACT_NONE;
+    g.impl = impl;
+    return vct_gemm(&g, stream);
+}
+
+int self_attention(const vct_mha_args* a, int causal, vct_stream_t stream, const char* who) {
+    VCT_REQUIRE(a && a->x && a->w_in && a->qkv && a->o, "%s: null argument", who);
+    VCT_REQUIRE(a->d % a->H == 0, "%s: d %% H != 0", who);
+    const int d = a->d, rows = a->B * a->L;
+    if (int e = project(a->x, rows, d, 3 * d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream)) return e;
+    vct_attn_args t;
+    memset(&t, 0, sizeof(t));
+    const char* base = (const char*)a->qkv;
+    t.B = a->B; t.H = a->H; t.Lq = a->L; t.Lk = a->L; t.dh = d / a->H; t.dtype = a->dtype;
+    t.q = base; t.q_ld = 3 * d;
+    t.k = base + (size_t)d * esize(a->dtype); t.k_ld = 3 * d;
+    t.v = base + (size_t)2 * d * esize(a->dtype); t.v_ld = 3 * d;
+    t.o = a->o; t.o_ld = d;
+    t.key_pad = a->key_pad; t.causal = causal;
+    t.scale = 1.0f / sqrtf((float)t.dh);
+    t.drop_p = a->drop_p; t.rng_state = a->rng_state; t.site = a->site;
+    t.probs = a->probs;
+    return vct_attn_fwd(&t, stream);
+}
+
+}  // namespace
+
+extern "C" int vct_attn_enc_self_fwd(const vct_mha_args* a, vct_stream_t stream) {
+    return self_attention(a, 0, stream, "vct_attn_enc_self_fwd");
+}
+
+extern "C" int vct_attn_dec_self_fwd(const vct_mha_args* a, vct_stream_t stream) {
+    return self_attention(a, 1, stream, "vct_attn_dec_self_fwd");
+}
+
+extern "C" int vct_attn_dec_cross_fwd(const vct_mha_args* a, vct_stream_t stream) {
+    VCT_REQUIRE(a && a->x && a->w_in && a->qkv && a->kv && a->o, "vct_attn_dec_cross_fwd: null argument");
+    VCT_REQUIRE(a->kv_ready || a->mem, "vct_attn_dec_cross_fwd: mem is required unless kv_ready");
+    VCT_REQUIRE(a->d % a->H == 0, "vct_attn_dec_cross_fwd: d %% H != 0");
+    const int d = a->d;
+    const size_t es = esize(a->dtype);
+    // q = x W_in[0:d]^T + b_in[0:d]
+    if (int e = project(a->x, a->B * a->L, d, d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream)) return e;
+    if (!a->kv_ready) {
+        const char* w_kv = (const char*)a->w_in + (size_t)d * d * es;
+        if (int e = project(a->mem, a->B * a->Lk, d, 2 * d, w_kv, a->b_in ? a->b_in + d : nullptr, a->kv, a->dtype,
+                            a->gemm_impl, stream))
+            return e;
+    }
+    vct_attn_args t;
+    memset(&t, 0, sizeof(t));
+    t.B = a->B; t.H = a->H; t.Lq = a->L; t.Lk = a->Lk; t.dh = d / a->H; t.dtype = a->dtype;
+    t.q = a->qkv; t.q_ld = d;
+    t.k = a->kv; t.k_ld = 2 * d;
+    t.v = (const char*)a->kv + (size_t)d * es; t.v_ld = 2 * d;
+    t.o = a->o; t.o_ld = d;
+    t.key_pad = nullptr; t.causal = 0;    // cross-attention is never masked
+    t.scale = 1.0f / sqrtf((float)t.dh);
+    t.drop_p = a->drop_p; t.rng_state = a->rng_state; t.site = a->site;
+    t.probs = a->probs;
+    return vct_attn_fwd(&t, stream);
+}

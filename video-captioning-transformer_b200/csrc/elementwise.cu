@@ -1,0 +1,585 @@
+// HBM-bound kernels of the hot path: frame staging, residual+dropout+LayerNorm (fwd/bwd),
+// embedding (fwd/bwd), column sums, Adam, casts, greedy argmax, step tick, error plumbing.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace vct {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: launch failed: %s", what, cudaGetErrorString(e));
+        return VCT_ERR_CUDA;
+    }
+    return 0;
+}
+
+}  // namespace vct
+
+using namespace vct;
+
+extern "C" int vct_version(void) { return 100; }
+extern "C" const char* vct_last_error(void) { return vct::g_err; }
+
+extern "C" int vct_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    VCT_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    VCT_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (sm_count) *sm_count = prop.multiProcessorCount;
+    if (cc_major) *cc_major = prop.major;
+    if (cc_minor) *cc_minor = prop.minor;
+    VCT_REQUIRE(prop.major == 10, "libvct_b200 is built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// step tick
+// ------------------------------------------------------------------------------------------------
+__global__ void step_tick_kernel(unsigned long long* rng_state, float* hyper) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        if (rng_state) rng_state[1] += 1ull;
+        if (hyper) {
+            float step = hyper[5] + 1.f;
+            hyper[5] = step;
+            hyper[6] = 1.f - powf(hyper[1], step);
+            hyper[7] = 1.f - powf(hyper[2], step);
+        }
+    }
+}
+
+extern "C" int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, vct_stream_t stream) {
+    step_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rng_state, adam_hyper);
+    return check_launch("vct_step_tick");
+}
+
+// ------------------------------------------------------------------------------------------------
+// frame staging: [B,T,Din] fp32 -> [B*(T+1), Din] with the mean row first
+// ------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void prep_frames_kernel(const float* __restrict__ feats, TO* __restrict__ out, int B, int T, int Din) {
+    const int nv = Din >> 2;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * nv) return;
+    const int b = (int)(gid / nv), c = (int)(gid % nv) * 4;
+    const float* src = feats + (long long)b * T * Din + c;
+    TO* dst = out + (long long)b * (T + 1) * Din + c;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int t = 0; t < T; ++t) {
+        float4 v = ld4(src + (long long)t * Din);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        st4(dst + (long long)(t + 1) * Din, v);
+    }
+    const float inv = 1.f / (float)T;
+    st4(dst, make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
+}
+
+extern "C" int vct_prep_frames(const float* feats, void* out, int out_dtype, int B, int T, int Din, vct_stream_t stream) {
+    VCT_REQUIRE(Din % 4 == 0 && B > 0 && T > 0, "vct_prep_frames: Din %% 4 != 0 or empty input");
+    long long n = (long long)B * (Din / 4);
+    int blocks = (int)((n + 255) / 256);
+    if (out_dtype == VCT_BF16)
+        prep_frames_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feats, (__nv_bfloat16*)out, B, T, Din);
+    else
+        prep_frames_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feats, (float*)out, B, T, Din);
+    return check_launch("vct_prep_frames");
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual + dropout + LayerNorm forward: one warp per row, NV float4 per lane
+// ------------------------------------------------------------------------------------------------
+constexpr int kLnWarps = 8;
+
+template <int NV, typename TC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_fwd_kernel(const float* __restrict__ x, const float* r, const float* __restrict__ gamma,
+              const float* __restrict__ beta, float* __restrict__ y, TC* __restrict__ y_c, float* s_out,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out, int R, int d, float drop_p,
+              const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * kLnWarps + warp;
+    if (row >= R) return;
+    const int nv = d >> 2;
+    const Rng rng = make_rng(rng_state, x != nullptr ? drop_p : 0.f);
+    const long long base = (long long)row * d;
+    float4 v[NV];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+            float4 rv = ld4(r + base + c * 4);
+            if (x != nullptr) {
+                float4 sc = dropout_scale4(rng, site, (unsigned long long)(base >> 2) + c);
+                float4 xv = ld4(x + base + c * 4);
+                rv = make_float4(xv.x + rv.x * sc.x, xv.y + rv.y * sc.y, xv.z + rv.z * sc.z, xv.w + rv.w * sc.w);
+            }
+            v[i] = rv;
+            sum += rv.x + rv.y + rv.z + rv.w;
+        }
+    }
+    const float mean = warp_sum(sum) / (float)d;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+            float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
+            sq += a * a + b * b + e * e + f * f;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)d + 1e-5f);
+    if (lane == 0) {
+        if (mean_out) mean_out[row] = mean;
+        if (rstd_out) rstd_out[row] = rstd;
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+            if (s_out) st4(s_out + base + c * 4, v[i]);
+            float4 g = ld4(gamma + c * 4), b = ld4(beta + c * 4);
+            float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
+                                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+            if (y) st4(y + base + c * 4, o);
+            if (y_c) st4(y_c + base + c * 4, o);
+        }
+    }
+}
+
+template <typename TC>
+static int launch_ln_fwd(const float* x, const float* r, const float* gamma, const float* beta, float* y, TC* y_c,
+                         float* s_out, float* mean, float* rstd, int R, int d, float drop_p,
+                         const unsigned long long* rng_state, unsigned int site, cudaStream_t st) {
+    const int blocks = (R + kLnWarps - 1) / kLnWarps;
+    const int nvl = (d / 4 + 31) / 32;
+#define LN_FWD_CASE(NVV)                                                                                         \
+    ln_fwd_kernel<NVV, TC><<<blocks, kLnWarps * 32, 0, st>>>(x, r, gamma, beta, y, y_c, s_out, mean, rstd, R, d, \
+                                                              drop_p, rng_state, site)
+    if (nvl <= 1) LN_FWD_CASE(1);
+    else if (nvl <= 2) LN_FWD_CASE(2);
+    else if (nvl <= 4) LN_FWD_CASE(4);
+    else if (nvl <= 6) LN_FWD_CASE(6);
+    else LN_FWD_CASE(8);
+#undef LN_FWD_CASE
+    return check_launch("vct_ln_residual_fwd");
+}
+
+extern "C" int vct_ln_residual_fwd(const float* x, const float* r, const float* gamma, const float* beta, float* y,
+                                   void* y_c, int y_c_dtype, float* s_out, float* mean, float* rstd, int R, int d,
+                                   float drop_p, const unsigned long long* rng_state, unsigned int site,
+                                   vct_stream_t stream) {
+    VCT_REQUIRE(d % 4 == 0 && d <= 1024 && R > 0, "vct_ln_residual_fwd: need d %% 4 == 0, d <= 1024 (d=%d)", d);
+    VCT_REQUIRE(r && gamma && beta, "vct_ln_residual_fwd: null input");
+    if (y_c_dtype == VCT_BF16)
+        return launch_ln_fwd<__nv_bfloat16>(x, r, gamma, beta, y, (__nv_bfloat16*)y_c, s_out, mean, rstd, R, d, drop_p,
+                                            rng_state, site, (cudaStream_t)stream);
+    return launch_ln_fwd<float>(x, r, gamma, beta, y, (float*)y_c, s_out, mean, rstd, R, d, drop_p, rng_state, site,
+                                (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// residual + dropout + LayerNorm backward
+// ------------------------------------------------------------------------------------------------
+static inline int ln_bwd_rows_per_cta(int R) {
+    int rows = (R + kNumSMs - 1) / kNumSMs;
+    rows = ((rows + kLnWarps - 1) / kLnWarps) * kLnWarps;
+    return rows < 4 * kLnWarps ? 4 * kLnWarps : rows;
+}
+static inline int ln_bwd_blocks(int R) {
+    const int rows = ln_bwd_rows_per_cta(R);
+    return (R + rows - 1) / rows;
+}
+
+extern "C" long long vct_ln_bwd_workspace_floats(int R, int d) { return (long long)ln_bwd_blocks(R) * 3 * d; }
+
+template <int NV, typename TC>
+__global__ void __launch_bounds__(kLnWarps * 32)
+ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ mean,
+              const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ ds,
+              TC* __restrict__ dr_c, float* __restrict__ dgamma, float* __restrict__ dbeta,
+              float* __restrict__ dbias_r, float* __restrict__ partials, unsigned int* counter, int R, int d,
+              int rows_per_cta, float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    extern __shared__ float sm[];  // [3][d]
+    __shared__ bool is_last;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nv = d >> 2;
+    const Rng rng = make_rng(rng_state, drop_p);
+    float4 acc_g[NV], acc_b[NV], acc_r[NV];
+    float4 gam[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        acc_g[i] = acc_b[i] = acc_r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        const int c = lane + 32 * i;
+        gam[i] = c < nv ? ld4(gamma + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const int row_end = min(R, (blockIdx.x + 1) * rows_per_cta);
+#pragma unroll 1
+    for (int row = blockIdx.x * rows_per_cta + warp; row < row_end; row += kLnWarps) {
+        const long long base = (long long)row * d;
+        const float mu = mean[row], rs = rstd[row];
+        float4 g[NV], xh[NV];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nv) {
+                float4 dyv = ld4(dy + base + c * 4), sv = ld4(s + base + c * 4);
+                xh[i] = make_float4((sv.x - mu) * rs, (sv.y - mu) * rs, (sv.z - mu) * rs, (sv.w - mu) * rs);
+                g[i] = make_float4(dyv.x * gam[i].x, dyv.y * gam[i].y, dyv.z * gam[i].z, dyv.w * gam[i].w);
+                c1 += g[i].x + g[i].y + g[i].z + g[i].w;
+                c2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
+                acc_g[i].x += dyv.x * xh[i].x; acc_g[i].y += dyv.y * xh[i].y;
+                acc_g[i].z += dyv.z * xh[i].z; acc_g[i].w += dyv.w * xh[i].w;
+                acc_b[i].x += dyv.x; acc_b[i].y += dyv.y; acc_b[i].z += dyv.z; acc_b[i].w += dyv.w;
+            }
+        }
+        c1 = warp_sum(c1) / (float)d;
+        c2 = warp_sum(c2) / (float)d;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nv) {
+                float4 o = make_float4(rs * (g[i].x - c1 - xh[i].x * c2), rs * (g[i].y - c1 - xh[i].y * c2),
+                                       rs * (g[i].z - c1 - xh[i].z * c2), rs * (g[i].w - c1 - xh[i].w * c2));
+                if (ds) st4(ds + base + c * 4, o);
+                float4 sc = dropout_scale4(rng, site, (unsigned long long)(base >> 2) + c);
+                float4 dr = make_float4(o.x * sc.x, o.y * sc.y, o.z * sc.z, o.w * sc.w);
+                if (dr_c) st4(dr_c + base + c * 4, dr);
+                acc_r[i].x += dr.x; acc_r[i].y += dr.y; acc_r[i].z += dr.z; acc_r[i].w += dr.w;
+            }
+        }
+    }
+    // cross-warp reduction in shared memory, warp by warp (deterministic order)
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    for (int w = 0; w < kLnWarps; ++w) {
+        if (warp == w) {
+#pragma unroll
+            for (int i = 0; i < NV; ++i) {
+                const int c = lane + 32 * i;
+                if (c < nv) {
+                    float* p0 = sm + c * 4;
+                    p0[0] += acc_g[i].x; p0[1] += acc_g[i].y; p0[2] += acc_g[i].z; p0[3] += acc_g[i].w;
+                    float* p1 = sm + d + c * 4;
+                    p1[0] += acc_b[i].x; p1[1] += acc_b[i].y; p1[2] += acc_b[i].z; p1[3] += acc_b[i].w;
+                    float* p2 = sm + 2 * d + c * 4;
+                    p2[0] += acc_r[i].x; p2[1] += acc_r[i].y; p2[2] += acc_r[i].z; p2[3] += acc_r[i].w;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    float* mine = partials + (long long)blockIdx.x * 3 * d;
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) mine[i] = sm[i];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(counter, 1u);
+        is_last = (prev == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
+            float a = 0.f;
+            for (unsigned int b = 0; b < gridDim.x; ++b) a += __ldcg(partials + (long long)b * 3 * d + i);
+            if (i < d) { if (dgamma) dgamma[i] = a; }
+            else if (i < 2 * d) { if (dbeta) dbeta[i - d] = a; }
+            else { if (dbias_r) dbias_r[i - 2 * d] = a; }
+        }
+        if (threadIdx.x == 0) *counter = 0u;
+    }
+}
+
+template <typename TC>
+static int launch_ln_bwd(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
+                         float* ds, TC* dr_c, float* dgamma, float* dbeta, float* dbias_r, float* partials,
+                         unsigned int* counter, int R, int d, float drop_p, const unsigned long long* rng_state,
+                         unsigned int site, cudaStream_t st) {
+    const int rows = ln_bwd_rows_per_cta(R), blocks = ln_bwd_blocks(R);
+    const int nvl = (d / 4 + 31) / 32;
+    const size_t smem = (size_t)3 * d * sizeof(float);
+#define LN_BWD_CASE(NVV)                                                                                          \
+    ln_bwd_kernel<NVV, TC><<<blocks, kLnWarps * 32, smem, st>>>(dy, s, mean, rstd, gamma, ds, dr_c, dgamma, dbeta, \
+                                                                 dbias_r, partials, counter, R, d, rows, drop_p,  \
+                                                                 rng_state, site)
+    if (nvl <= 1) LN_BWD_CASE(1);
+    else if (nvl <= 2) LN_BWD_CASE(2);
+    else if (nvl <= 4) LN_BWD_CASE(4);
+    else if (nvl <= 6) LN_BWD_CASE(6);
+    else LN_BWD_CASE(8);
+#undef LN_BWD_CASE
+    return check_launch("vct_ln_residual_bwd");
+}
+
+extern "C" int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
+                                   const float* gamma, float* ds, void* dr_c, int dr_dtype, float* dgamma,
+                                   float* dbeta, float* dbias_r, float* partials, unsigned int* counter, int R, int d,
+                                   float drop_p, const unsigned long long* rng_state, unsigned int site,
+                                   vct_stream_t stream) {
+    VCT_REQUIRE(d % 4 == 0 && d <= 1024 && R > 0, "vct_ln_residual_bwd: need d %% 4 == 0, d <= 1024 (d=%d)", d);
+    VCT_REQUIRE(dy && s && mean && rstd && gamma && partials && counter, "vct_ln_residual_bwd: null input");
+    if (dr_dtype == VCT_BF16)
+        return launch_ln_bwd<__nv_bfloat16>(dy, s, mean, rstd, gamma, ds, (__nv_bfloat16*)dr_c, dgamma, dbeta, dbias_r,
+                                            partials, counter, R, d, drop_p, rng_state, site, (cudaStream_t)stream);
+    return launch_ln_bwd<float>(dy, s, mean, rstd, gamma, ds, (float*)dr_c, dgamma, dbeta, dbias_r, partials, counter,
+                                R, d, drop_p, rng_state, site, (cudaStream_t)stream);
+}
+
+// ------------------------------------------------------------------------------------------------
+// embedding
+// ------------------------------------------------------------------------------------------------
+template <typename TC>
+__global__ void embed_fwd_kernel(const long long* __restrict__ ids, long long ids_ld, const float* __restrict__ E,
+                                 const float* __restrict__ pos, float* __restrict__ x, TC* __restrict__ x_c, int B,
+                                 int S, int d, int V, int pos_offset, float drop_p,
+                                 const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    const int nv = d >> 2;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * S * nv) return;
+    const int c = (int)(gid % nv);
+    const long long row = gid / nv;
+    const int b = (int)(row / S), sidx = (int)(row % S);
+    long long id = ids[(long long)b * ids_ld + sidx];
+    id = id < 0 ? 0 : (id >= V ? V - 1 : id);
+    const Rng rng = make_rng(rng_state, drop_p);
+    float4 e = ld4(E + id * d + c * 4), p = ld4(pos + (long long)(sidx + pos_offset) * d + c * 4);
+    float4 sc = dropout_scale4(rng, site, (unsigned long long)gid);
+    float4 o = make_float4((e.x + p.x) * sc.x, (e.y + p.y) * sc.y, (e.z + p.z) * sc.z, (e.w + p.w) * sc.w);
+    if (x) st4(x + row * d + c * 4, o);
+    if (x_c) st4(x_c + row * d + c * 4, o);
+}
+
+extern "C" int vct_embed_fwd(const long long* ids, long long ids_ld, const float* E, const float* pos, float* x,
+                             void* x_c, int x_c_dtype, int B, int S, int d, int V, int pos_offset, float drop_p,
+                             const unsigned long long* rng_state, unsigned int site, vct_stream_t stream) {
+    VCT_REQUIRE(d % 4 == 0 && B > 0 && S > 0, "vct_embed_fwd: need d %% 4 == 0 and non-empty input");
+    long long n = (long long)B * S * (d / 4);
+    int blocks = (int)((n + 255) / 256);
+    if (x_c_dtype == VCT_BF16)
+        embed_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, E, pos, x, (__nv_bfloat16*)x_c, B, S, d,
+                                                                   V, pos_offset, drop_p, rng_state, site);
+    else
+        embed_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, E, pos, x, (float*)x_c, B, S, d, V,
+                                                                   pos_offset, drop_p, rng_state, site);
+    return check_launch("vct_embed_fwd");
+}
+
+__global__ void embed_bwd_kernel(const long long* __restrict__ ids, long long ids_ld, const float* __restrict__ dx,
+                                 float* __restrict__ dE, int B, int S, int d, int V, int pad_id, float drop_p,
+                                 const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    const int nv = d >> 2;
+    long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * S * nv) return;
+    const int c = (int)(gid % nv);
+    const long long row = gid / nv;
+    const int b = (int)(row / S), sidx = (int)(row % S);
+    const long long id = ids[(long long)b * ids_ld + sidx];
+    if (id == pad_id || id < 0 || id >= V) return;
+    const Rng rng = make_rng(rng_state, drop_p);
+    float4 g = ld4(dx + row * d + c * 4);
+    float4 sc = dropout_scale4(rng, site, (unsigned long long)gid);
+    float* dst = dE + id * d + c * 4;
+    atomicAdd(dst + 0, g.x * sc.x);
+    atomicAdd(dst + 1, g.y * sc.y);
+    atomicAdd(dst + 2, g.z * sc.z);
+    atomicAdd(dst + 3, g.w * sc.w);
+}
+
+extern "C" int vct_embed_bwd(const long long* ids, long long ids_ld, const float* dx, float* dE, int B, int S, int d,
+                             int V, int pad_id, float drop_p, const unsigned long long* rng_state, unsigned int site,
+                             vct_stream_t stream) {
+    VCT_REQUIRE(d % 4 == 0 && B > 0 && S > 0, "vct_embed_bwd: need d %% 4 == 0 and non-empty input");
+    long long n = (long long)B * S * (d / 4);
+    int blocks = (int)((n + 255) / 256);
+    embed_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, dx, dE, B, S, d, V, pad_id, drop_p,
+                                                               rng_state, site);
+    return check_launch("vct_embed_bwd");
+}
+
+// ------------------------------------------------------------------------------------------------
+// column sums (bias gradients): deterministic two-level reduction in one launch
+// ------------------------------------------------------------------------------------------------
+constexpr int kCsCols = 256, kCsRows = 64;
+
+extern "C" long long vct_colsum_workspace_floats(int M, int N) {
+    return (long long)((M + kCsRows - 1) / kCsRows) * N;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kCsCols)
+colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, float* __restrict__ out,
+              float* __restrict__ partials, unsigned int* counters) {
+    __shared__ bool is_last;
+    const int n = blockIdx.x * kCsCols + threadIdx.x;
+    const int m0 = blockIdx.y * kCsRows, m1 = min(M, m0 + kCsRows);
+    if (n < N) {
+        float a = 0.f;
+        for (int m = m0; m < m1; ++m) a += to_f32(X[(long long)m * ld + n]);
+        partials[(long long)blockIdx.y * N + n] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int prev = atomicAdd(counters + blockIdx.x, 1u);
+        is_last = (prev == gridDim.y - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        if (n < N) {
+            float a = 0.f;
+            for (unsigned int b = 0; b < gridDim.y; ++b) a += __ldcg(partials + (long long)b * N + n);
+            out[n] = a;
+        }
+        if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
+    }
+}
+
+extern "C" int vct_colsum(const void* X, int dtype, long long ld, int M, int N, float* out, float* partials,
+                          unsigned int* counter, vct_stream_t stream) {
+    VCT_REQUIRE(M > 0 && N > 0 && N <= 65536, "vct_colsum: need 0 < N <= 65536 (counter array has 256 entries)");
+    dim3 grid((N + kCsCols - 1) / kCsCols, (M + kCsRows - 1) / kCsRows);
+    if (dtype == VCT_BF16)
+        colsum_kernel<<<grid, kCsCols, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ld, M, N, out, partials, counter);
+    else
+        colsum_kernel<<<grid, kCsCols, 0, (cudaStream_t)stream>>>((const float*)X, ld, M, N, out, partials, counter);
+    return check_launch("vct_colsum");
+}
+
+// ------------------------------------------------------------------------------------------------
+// Adam over the flat arena
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+            __nv_bfloat16* __restrict__ p_c, long long n4, const float* __restrict__ hyper, float grad_scale) {
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+    const float step_size = lr / hyper[6], inv_sqrt_bc2 = rsqrtf(hyper[7]);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 pv = ld4(p + i * 4), gv = ld4(g + i * 4), mv = ld4(m + i * 4), vv = ld4(v + i * 4);
+        float pe[4] = {pv.x, pv.y, pv.z, pv.w}, ge[4] = {gv.x, gv.y, gv.z, gv.w};
+        float me[4] = {mv.x, mv.y, mv.z, mv.w}, ve[4] = {vv.x, vv.y, vv.z, vv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float gg = ge[k] * grad_scale;
+            if (wd != 0.f) gg += wd * pe[k];
+            me[k] = b1 * me[k] + (1.f - b1) * gg;
+            ve[k] = b2 * ve[k] + (1.f - b2) * gg * gg;
+            const float denom = sqrtf(ve[k]) * inv_sqrt_bc2 + eps;
+            pe[k] -= step_size * (me[k] / denom);
+        }
+        float4 po = make_float4(pe[0], pe[1], pe[2], pe[3]);
+        st4(p + i * 4, po);
+        st4(m + i * 4, make_float4(me[0], me[1], me[2], me[3]));
+        st4(v + i * 4, make_float4(ve[0], ve[1], ve[2], ve[3]));
+        if (p_c) st4(p_c + i * 4, po);
+    }
+}
+
+extern "C" int vct_adam(float* p, const float* g, float* m, float* v, void* p_c, long long n, const float* hyper,
+                        float grad_scale, vct_stream_t stream) {
+    VCT_REQUIRE(n > 0 && n % 4 == 0, "vct_adam: arena length must be a positive multiple of 4 (n=%lld)", n);
+    const long long n4 = n / 4;
+    long long want = (n4 + 255) / 256;
+    int blocks = (int)(want < (long long)kNumSMs * 8 ? want : (long long)kNumSMs * 8);
+    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_c, n4, hyper, grad_scale);
+    return check_launch("vct_adam");
+}
+
+// ------------------------------------------------------------------------------------------------
+// cast
+// ------------------------------------------------------------------------------------------------
+template <typename TO>
+__global__ void cast_kernel(const float* __restrict__ src, TO* __restrict__ dst, long long n) {
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
+        st4(dst + i * 4, ld4(src + i * 4));
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) dst[n4 * 4 + threadIdx.x] = from_f32<TO>(src[n4 * 4 + threadIdx.x]);
+}
+
+extern "C" int vct_cast(const float* src, void* dst, int dst_dtype, long long n, vct_stream_t stream) {
+    VCT_REQUIRE(n > 0, "vct_cast: empty");
+    long long want = (n / 4 + 255) / 256 + 1;
+    int blocks = (int)(want < (long long)kNumSMs * 8 ? want : (long long)kNumSMs * 8);
+    if (dst_dtype == VCT_BF16)
+        cast_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+    else
+        cast_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (float*)dst, n);
+    return check_launch("vct_cast");
+}
+
+// ------------------------------------------------------------------------------------------------
+// greedy argmax + append
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+argmax_append_kernel(const float* __restrict__ logits, long long ld, int V, long long* __restrict__ ys, long long ys_ld,
+                     int t, int end_id, int* __restrict__ ended, int* __restrict__ n_ended) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    const int b = blockIdx.x;
+    const float* row = logits + (long long)b * ld;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < V; i += blockDim.x) {
+        float v = row[i];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; ++w)
+            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+        if (bi == 0x7fffffff) bi = 0;
+        ys[(long long)b * ys_ld + t] = bi;
+        if (bi == end_id && ended && !ended[b]) {
+            ended[b] = 1;
+            if (n_ended) atomicAdd(n_ended, 1);
+        }
+    }
+}
+
+extern "C" int vct_argmax_append(const float* logits, long long ld_logits, int B, int V, long long* ys, long long ys_ld,
+                                 int t, int end_id, int* ended, int* n_ended, vct_stream_t stream) {
+    VCT_REQUIRE(B > 0 && V > 0 && logits && ys, "vct_argmax_append: bad arguments");
+    argmax_append_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, ld_logits, V, ys, ys_ld, t, end_id, ended, n_ended);
+    return check_launch("vct_argmax_append");
+}
+
+// ------------------------------------------------------------------------------------------------
+// debug: dropout keep mask
+// ------------------------------------------------------------------------------------------------
+__global__ void dropout_mask_kernel(unsigned char* out, long long n, float p, const unsigned long long* rng_state,
+                                    unsigned int site) {
+    const Rng rng = make_rng(rng_state, p);
+    long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i4 * 4 >= n) return;
+    float4 sc = dropout_scale4(rng, site, (unsigned long long)i4);
+    float e[4] = {sc.x, sc.y, sc.z, sc.w};
+    for (int k = 0; k < 4; ++k)
+        if (i4 * 4 + k < n) out[i4 * 4 + k] = e[k] != 0.f;
+}
+
+extern "C" int vct_dropout_mask(unsigned char* out, long long n, float drop_p, const unsigned long long* rng_state,
+                                unsigned int site, vct_stream_t stream) {
+    VCT_REQUIRE(n > 0, "vct_dropout_mask: empty");
+    long long n4 = (n + 3) / 4;
+    dropout_mask_kernel<<<(int)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, drop_p, rng_state, site);
+    return check_launch("vct_dropout_mask");
+}

@@ -1,0 +1,794 @@
+"""Host-side sequencing of the hot path over libvct_b200.so.
+
+``CaptionEngine`` owns the parameter arena, the per-shape activation workspaces and the launch
+plans (lists of pre-built C-ABI calls) for
+
+  * caption forward   (model/MMT4Caption.py:114-121 -> MMEncoder.py:244-276 -> CapDecoder.py:34-60
+                       -> loss.py:78-92)
+  * its backward      (train.py:125 ``loss.backward()``)
+  * Adam              (train.py:126)
+  * greedy decoding   (model/MMT4Caption.py:146-184, KV-cached; SURVEY Q18 shows equivalence)
+
+PyTorch is used for device memory and streams only; every arithmetic step is a kernel of the
+shared library.  There is no CPU path: constructing an engine without CUDA raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from types import SimpleNamespace
+from typing import Dict, List, Optional, Tuple
+
+import torch
+
+from . import lib as L
+from .arena import ParamArena
+
+F32, BF16 = L.F32, L.BF16
+_ESIZE = {F32: 4, BF16: 2}
+_TDT = {F32: torch.float32, BF16: torch.bfloat16}
+
+# dropout call sites (unique per layer / position; see include/vct.h "dropout")
+SITE_EMBED = 1
+def _enc_site(layer: int, k: int) -> int: return 100 + 16 * layer + k      # 0 probs, 1 dropout1, 2 ffn, 3 dropout2
+def _dec_site(layer: int, k: int) -> int: return 1000 + 16 * layer + k     # 0 self probs, 1 dropout1, 2 cross probs, 3 dropout2, 4 ffn, 5 dropout3
+
+
+class Plan:
+    """A pre-built sequence of C-ABI calls; ``run(stream)`` issues them in order."""
+
+    def __init__(self):
+        self.calls: List[Tuple] = []
+        self.keep: List = []      # keeps ctypes structs / tensors alive
+
+    def add(self, name: str, fn, *args):
+        self.calls.append((name, fn, args))
+
+    def run(self, stream: int) -> int:
+        for name, fn, args in self.calls:
+            rc = fn(*args, stream)
+            if rc != 0:
+                L.check(rc, name)
+        return len(self.calls)
+
+    def __len__(self):
+        return len(self.calls)
+
+
+class CaptionEngine:
+    def __init__(self, video_encoder, cap_decoder, *, dims: dict, device: torch.device, precision: str = "bf16",
+                 gemm_impl: Optional[str] = None, seed: int = 666):
+        if device.type != "cuda" or not torch.cuda.is_available():
+            raise RuntimeError("vct_b200 has no CPU path: a CUDA (sm_100a) device is required")
+        self.lib = L.load()
+        sm, maj, mnr = C.c_int(), C.c_int(), C.c_int()
+        with torch.cuda.device(device):
+            L.check(self.lib.vct_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "vct_device_info")
+        self.device = device
+        self.dims = SimpleNamespace(**dims)   # Din d H_enc H_dec F_enc F_dec L_enc L_dec V pad_id alpha dropout
+        if precision not in ("bf16", "fp32"):
+            raise ValueError("precision must be 'bf16' or 'fp32'")
+        self.precision = precision
+        self.cdt = BF16 if precision == "bf16" else F32
+        impl = gemm_impl or os.environ.get("VCT_GEMM", "tcgen05" if precision == "bf16" else "simt")
+        if impl not in ("simt", "tcgen05"):
+            raise ValueError("gemm_impl must be 'simt' or 'tcgen05'")
+        if impl == "tcgen05" and precision != "bf16":
+            raise ValueError("the tcgen05 GEMM takes bf16 operands")
+        self.gemm_impl = L.GEMM_TCGEN05 if impl == "tcgen05" else L.GEMM_SIMT
+        self.video_encoder, self.cap_decoder = video_encoder, cap_decoder
+        named = []
+        if video_encoder is not None:
+            named += [("video_encoder." + n, p) for n, p in video_encoder.named_parameters()]
+        if cap_decoder is not None:
+            named += [("cap_decoder." + n, p) for n, p in cap_decoder.named_parameters()]
+        self.arena = ParamArena(named, device)
+        # constant sinusoid buffers (state_dict entries of the reference)
+        self.pos = cap_decoder.positional_encoding.pos_embedding if cap_decoder is not None else None   # [5000, d]
+        self.pe = video_encoder.temp_emb.pe if video_encoder is not None else None                      # [1, 512, d]
+        # per-step device state
+        self.rng_state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        self.hyper = torch.zeros(8, dtype=torch.float32, device=device)
+        self.counters = torch.zeros(1024, dtype=torch.int32, device=device)
+        self.upstream = torch.ones(1, dtype=torch.float32, device=device)
+        self._tempo: Dict[int, torch.Tensor] = {}
+        self._ws: Dict[Tuple, SimpleNamespace] = {}
+        self._shadow_version = None
+        self.launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    # parameter access
+    # ------------------------------------------------------------------------------------------
+    def _w(self, name: str, row_off: int = 0) -> int:
+        """pointer to a GEMM weight in the compute dtype (bf16 shadow or fp32 master)."""
+        a = self.arena
+        cols = a.shape[name][1] if len(a.shape[name]) > 1 else 1
+        off = a.offset[name] + row_off * cols
+        base = a.ensure_shadow() if self.cdt == BF16 else a.p32
+        return base.data_ptr() + off * _ESIZE[self.cdt]
+
+    def _p(self, name: str, off: int = 0) -> int:
+        return self.arena.p32.data_ptr() + 4 * (self.arena.offset[name] + off)
+
+    def _g(self, name: str, off: int = 0) -> int:
+        return self.arena.grad.data_ptr() + 4 * (self.arena.offset[name] + off)
+
+    def refresh_shadow(self, force: bool = False) -> None:
+        """Re-derive the bf16 shadow weights if anything outside vct_adam touched the masters
+        (torch optimizer step, load_state_dict, manual edits)."""
+        if self.cdt != BF16:
+            return
+        a = self.arena
+        ver = a.version()
+        if force or a.shadow is None or self._shadow_version != ver:
+            sh = a.ensure_shadow()
+            L.check(self.lib.vct_cast(a.p32.data_ptr(), sh.data_ptr(), BF16, a.numel, self._stream()), "vct_cast")
+            self.launches += 1
+            self._shadow_version = ver
+
+    def check_arena(self) -> None:
+        if not self.arena.is_current():
+            raise RuntimeError("model parameters were re-allocated after the vct engine was built "
+                               "(.to()/.half()?); rebuild the engine (model.reset_engine())")
+
+    def _stream(self) -> int:
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def tempo_table(self, T: int) -> torch.Tensor:
+        """[T+1, d] temporal-encoding rows: row 0 zeros (global token), row i = pe[i-1]
+        (model/MMEncoder.py:89-104 for one modality: indices = linspace(0, T-1, T) = 0..T-1).
+        Constant per T, so it is built once instead of per forward."""
+        if T not in self._tempo:
+            if T > self.pe.shape[1]:
+                raise ValueError(f"T={T} exceeds the temporal table ({self.pe.shape[1]})")
+            t = torch.zeros(T + 1, self.dims.d, dtype=torch.float32, device=self.device)
+            t[1:] = self.pe[0, :T].to(self.device, torch.float32)
+            self._tempo[T] = t
+        return self._tempo[T]
+
+    # ------------------------------------------------------------------------------------------
+    # small call builders
+    # ------------------------------------------------------------------------------------------
+    def _gemm(self, plan: Plan, tag: str, M, N, K, A, lda, a_trans, B, ldb, b_trans, Cp, c_dtype, ldc, *, bias=None,
+              C2=None, c2_dtype=F32, ldc2=0, row_table=None, row_period=0, addend=None, ld_addend=0, act=L.ACT_NONE,
+              aux=None, ld_aux=0, drop_p=0.0, site=0, in_dtype=None):
+        g = L.GemmArgs()
+        g.M, g.N, g.K = M, N, K
+        dt = self.cdt if in_dtype is None else in_dtype
+        g.A, g.a_dtype, g.lda, g.a_trans = A, dt, lda, a_trans
+        g.B, g.b_dtype, g.ldb, g.b_trans = B, dt, ldb, b_trans
+        g.C, g.c_dtype, g.ldc = Cp, c_dtype, ldc
+        g.C2, g.c2_dtype, g.ldc2 = C2, c2_dtype, ldc2
+        g.bias = bias
+        g.row_table, g.row_period = row_table, row_period
+        g.addend, g.ld_addend = addend, ld_addend
+        g.act = act
+        g.aux, g.aux_dtype, g.ld_aux = aux, self.cdt, ld_aux
+        g.drop_p, g.rng_state, g.site = drop_p, self.rng_state.data_ptr(), site
+        g.impl = self.gemm_impl
+        plan.keep.append(g)
+        plan.add("vct_gemm:" + tag, self.lib.vct_gemm, C.byref(g))
+
+    def _colsum(self, plan: Plan, tag: str, X, ld, M, N, out, ws):
+        plan.add("vct_colsum:" + tag, self.lib.vct_colsum, X, self.cdt, ld, M, N, out, ws.partials.data_ptr(),
+                 self.counters.data_ptr() + 4 * 8)
+
+    def _ln_fwd(self, plan: Plan, tag, x, r, gname, bname, y, y_c, s_out, mean, rstd, R, p, site):
+        plan.add("vct_ln_residual_fwd:" + tag, self.lib.vct_ln_residual_fwd, x, r, self._p(gname), self._p(bname), y, y_c,
+                 self.cdt, s_out, mean, rstd, R, self.dims.d, p, self.rng_state.data_ptr(), site)
+
+    def _ln_bwd(self, plan: Plan, tag, dy, s, mean, rstd, gname, bname, ds, dr_c, dbias, R, p, site, ws):
+        plan.add("vct_ln_residual_bwd:" + tag, self.lib.vct_ln_residual_bwd, dy, s, mean, rstd, self._p(gname), ds, dr_c,
+                 self.cdt, self._g(gname), self._g(bname), dbias, ws.partials.data_ptr(), self.counters.data_ptr(),
+                 R, self.dims.d, p, self.rng_state.data_ptr(), site)
+
+    def _attn(self, plan: Plan, tag, bwd, *, B, H, Lq, Lk, q, q_ld, k, k_ld, v, v_ld, o, o_ld, key_pad=None, causal=0,
+              p=0.0, site=0, probs=None, d_o=None, do_ld=0, dq=None, dq_ld=0, dk=None, dk_ld=0, dv=None, dv_ld=0,
+              q_bs=0, k_bs=0, v_bs=0, o_bs=0):
+        a = L.AttnArgs()
+        a.B, a.H, a.Lq, a.Lk, a.dh = B, H, Lq, Lk, self.dims.d // H
+        a.dtype = self.cdt
+        a.q, a.q_ld, a.k, a.k_ld, a.v, a.v_ld, a.o, a.o_ld = q, q_ld, k, k_ld, v, v_ld, o, o_ld
+        a.key_pad, a.causal, a.scale = key_pad, causal, 1.0 / math.sqrt(self.dims.d // H)
+        a.drop_p, a.rng_state, a.site = p, self.rng_state.data_ptr(), site
+        a.probs = probs
+        a.d_o, a.do_ld, a.dq, a.dq_ld, a.dk, a.dk_ld, a.dv, a.dv_ld = d_o, do_ld, dq, dq_ld, dk, dk_ld, dv, dv_ld
+        a.q_bs, a.k_bs, a.v_bs, a.o_bs = q_bs, k_bs, v_bs, o_bs
+        plan.keep.append(a)
+        plan.add(("vct_attn_bwd:" if bwd else "vct_attn_fwd:") + tag,
+                 self.lib.vct_attn_bwd if bwd else self.lib.vct_attn_fwd, C.byref(a))
+
+    # ------------------------------------------------------------------------------------------
+    # workspaces
+    # ------------------------------------------------------------------------------------------
+    def _buf(self, ws, name, shape, dtype):
+        t = torch.empty(shape, dtype=dtype, device=self.device)
+        setattr(ws, name, t)
+        return t
+
+    def workspace(self, B: int, T: int, S: int, training: bool) -> SimpleNamespace:
+        key = (B, T, S, training)
+        if key in self._ws:
+            return self._ws[key]
+        D = self.dims
+        ws = SimpleNamespace(B=B, T=T, S=S, M=T + 1, training=training)
+        d, M = D.d, T + 1
+        Re, Rd = B * M, B * S
+        cdt = _TDT[self.cdt]
+        f32 = torch.float32
+        two = self.cdt == BF16      # separate compute-dtype copies of fp32 activations?
+        ws.Vp = (D.V + 7) // 8 * 8
+
+        def act(name, rows, cols):
+            """fp32 activation + (in bf16 mode) its bf16 twin; returns (fp32 tensor, compute-dtype ptr)."""
+            t = self._buf(ws, name, (rows, cols), f32)
+            c = self._buf(ws, name + "_c", (rows, cols), cdt) if two else t
+            setattr(ws, name + "_c", c)
+            return t
+
+        # inputs (device-resident staging so that plans have static pointers)
+        self._buf(ws, "feats", (B, T, D.Din), f32)
+        self._buf(ws, "vid_pad", (B, M), torch.uint8)
+        self._buf(ws, "ids", (B, S + 1), torch.int64)
+        self._buf(ws, "tok_pad", (B, S), torch.uint8)
+        # encoder
+        self._buf(ws, "a0", (Re, D.Din), cdt)
+        act("x0", Re, d)
+        ws.enc = []
+        for l in range(D.L_enc):
+            e = SimpleNamespace()
+            e.qkv = torch.empty((Re, 3 * d), dtype=cdt, device=self.device)
+            e.ao = torch.empty((Re, d), dtype=cdt, device=self.device)
+            e.s1 = torch.empty((Re, d), dtype=f32, device=self.device)
+            e.x1 = torch.empty((Re, d), dtype=f32, device=self.device)
+            e.x1_c = torch.empty((Re, d), dtype=cdt, device=self.device) if two else e.x1
+            e.z = torch.empty((Re, D.F_enc), dtype=cdt, device=self.device)
+            e.h = torch.empty((Re, D.F_enc), dtype=cdt, device=self.device)
+            e.s2 = torch.empty((Re, d), dtype=f32, device=self.device)
+            e.x2 = torch.empty((Re, d), dtype=f32, device=self.device)
+            e.x2_c = torch.empty((Re, d), dtype=cdt, device=self.device) if two else e.x2
+            e.stats = torch.empty((4, Re), dtype=f32, device=self.device)   # mean1 rstd1 mean2 rstd2
+            ws.enc.append(e)
+        act("mem", Re, d)
+        self._buf(ws, "mem_stats", (2, Re), f32)
+        # decoder
+        act("e0", Rd, d)
+        ws.dec = []
+        for l in range(D.L_dec):
+            e = SimpleNamespace()
+            e.qkv = torch.empty((Rd, 3 * d), dtype=cdt, device=self.device)
+            e.ao = torch.empty((Rd, d), dtype=cdt, device=self.device)
+            e.s1 = torch.empty((Rd, d), dtype=f32, device=self.device)
+            e.x1 = torch.empty((Rd, d), dtype=f32, device=self.device)
+            e.x1_c = torch.empty((Rd, d), dtype=cdt, device=self.device) if two else e.x1
+            e.q = torch.empty((Rd, d), dtype=cdt, device=self.device)
+            e.kv = torch.empty((Re, 2 * d), dtype=cdt, device=self.device)
+            e.ao2 = torch.empty((Rd, d), dtype=cdt, device=self.device)
+            e.s2 = torch.empty((Rd, d), dtype=f32, device=self.device)
+            e.x2 = torch.empty((Rd, d), dtype=f32, device=self.device)
+            e.x2_c = torch.empty((Rd, d), dtype=cdt, device=self.device) if two else e.x2
+            e.z = torch.empty((Rd, D.F_dec), dtype=cdt, device=self.device)
+            e.h = torch.empty((Rd, D.F_dec), dtype=cdt, device=self.device)
+            e.s3 = torch.empty((Rd, d), dtype=f32, device=self.device)
+            e.x3 = torch.empty((Rd, d), dtype=f32, device=self.device)
+            e.x3_c = torch.empty((Rd, d), dtype=cdt, device=self.device) if two else e.x3
+            e.stats = torch.empty((6, Rd), dtype=f32, device=self.device)
+            ws.dec.append(e)
+        act("hfin", Rd, d)
+        self._buf(ws, "hfin_stats", (2, Rd), f32)
+        self._buf(ws, "logits", (Rd, ws.Vp), f32)
+        self._buf(ws, "loss", (1,), f32)
+        self._buf(ws, "row_parts", (Rd, 2), f32)
+        if training:
+            # zero-filled once: columns V..Vp-1 stay zero, they are K-padding of the generator dgrad
+            ws.dlogits = torch.zeros((Rd, ws.Vp), dtype=cdt, device=self.device)
+            Fm = max(D.F_enc, D.F_dec)
+            rmax = max(Re, Rd)
+            self._buf(ws, "g_a", (rmax, d), f32)          # fp32 activation-gradient ping/pong
+            self._buf(ws, "g_b", (rmax, d), f32)
+            self._buf(ws, "g_s", (rmax, d), f32)          # ds of the LN being processed
+            self._buf(ws, "g_r_c", (rmax, d), cdt)        # dr (branch gradient), compute dtype
+            self._buf(ws, "g_o_c", (rmax, d), cdt)        # gradient wrt attention output
+            self._buf(ws, "g_z_c", (rmax, Fm), cdt)       # gradient wrt FFN pre-activation
+            self._buf(ws, "g_qkv_c", (rmax, 3 * d), cdt)
+            self._buf(ws, "g_q_c", (Rd, d), cdt)
+            self._buf(ws, "g_kv_c", (Re, 2 * d), cdt)
+            self._buf(ws, "g_mem", (Re, d), f32)
+            self._buf(ws, "g_x0_c", (Re, d), cdt)
+            nws = max(int(self.lib.vct_ln_bwd_workspace_floats(rmax, d)),
+                      int(self.lib.vct_colsum_workspace_floats(rmax, max(3 * d, Fm))),
+                      int(self.lib.vct_colsum_workspace_floats(Rd, D.V)))
+            self._buf(ws, "partials", (nws,), f32)
+        ws.plans = {}
+        self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------------------------------
+    # forward plan
+    # ------------------------------------------------------------------------------------------
+    def _build_encoder(self, plan: Plan, ws, p_drop: float):
+        D, lib = self.dims, self.lib
+        d, B, T, M = D.d, ws.B, ws.T, ws.M
+        Re = B * M
+        cd = self.cdt
+        plan.add("vct_prep_frames", lib.vct_prep_frames, ws.feats.data_ptr(), ws.a0.data_ptr(), cd, B, T, D.Din)
+        tempo = self.tempo_table(T)
+        plan.keep.append(tempo)
+        self._gemm(plan, "unify", Re, d, D.Din, ws.a0.data_ptr(), D.Din, 0, self._w("video_encoder.unify.0.weight"),
+                   D.Din, 0, ws.x0.data_ptr(), F32, d, bias=self._p("video_encoder.unify.0.bias"),
+                   C2=ws.x0_c.data_ptr() if cd == BF16 else None, c2_dtype=cd, ldc2=d,
+                   row_table=tempo.data_ptr(), row_period=M)
+        x, x_c = ws.x0, ws.x0_c
+        for l, e in enumerate(ws.enc):
+            pre = f"video_encoder.transformer_encoder.layers.{l}."
+            m = L.MhaArgs()
+            m.B, m.L, m.Lk, m.d, m.H, m.dtype = B, M, M, d, D.H_enc, cd
+            m.x, m.w_in, m.b_in = x_c.data_ptr(), self._w(pre + "self_attn.in_proj_weight"), self._p(pre + "self_attn.in_proj_bias")
+            m.qkv, m.o, m.key_pad = e.qkv.data_ptr(), e.ao.data_ptr(), ws.vid_pad.data_ptr()
+            m.drop_p, m.rng_state, m.site = p_drop, self.rng_state.data_ptr(), _enc_site(l, 0)
+            m.gemm_impl = self.gemm_impl
+            plan.keep.append(m)
+            plan.add(f"vct_attn_enc_self_fwd:{l}", lib.vct_attn_enc_self_fwd, C.byref(m))
+            self._gemm(plan, f"enc{l}.out_proj", Re, d, d, e.ao.data_ptr(), d, 0, self._w(pre + "self_attn.out_proj.weight"),
+                       d, 0, e.s1.data_ptr(), F32, d, bias=self._p(pre + "self_attn.out_proj.bias"))
+            self._ln_fwd(plan, f"enc{l}.norm1", x.data_ptr(), e.s1.data_ptr(), pre + "norm1.weight", pre + "norm1.bias",
+                         e.x1.data_ptr(), e.x1_c.data_ptr() if cd == BF16 else None, e.s1.data_ptr(),
+                         e.stats[0].data_ptr(), e.stats[1].data_ptr(), Re, p_drop, _enc_site(l, 1))
+            self._gemm(plan, f"enc{l}.linear1", Re, D.F_enc, d, e.x1_c.data_ptr(), d, 0, self._w(pre + "linear1.weight"), d, 0,
+                       e.z.data_ptr(), cd, D.F_enc, bias=self._p(pre + "linear1.bias"), C2=e.h.data_ptr(), c2_dtype=cd,
+                       ldc2=D.F_enc, act=L.ACT_GELU_FWD, drop_p=p_drop, site=_enc_site(l, 2))
+            self._gemm(plan, f"enc{l}.linear2", Re, d, D.F_enc, e.h.data_ptr(), D.F_enc, 0, self._w(pre + "linear2.weight"),
+                       D.F_enc, 0, e.s2.data_ptr(), F32, d, bias=self._p(pre + "linear2.bias"))
+            self._ln_fwd(plan, f"enc{l}.norm2", e.x1.data_ptr(), e.s2.data_ptr(), pre + "norm2.weight", pre + "norm2.bias",
+                         e.x2.data_ptr(), e.x2_c.data_ptr() if cd == BF16 else None, e.s2.data_ptr(),
+                         e.stats[2].data_ptr(), e.stats[3].data_ptr(), Re, p_drop, _enc_site(l, 3))
+            x, x_c = e.x2, e.x2_c
+        ws.enc_out = x
+        self._ln_fwd(plan, "enc.norm", None, x.data_ptr(), "video_encoder.transformer_encoder.norm.weight",
+                     "video_encoder.transformer_encoder.norm.bias", ws.mem.data_ptr(),
+                     ws.mem_c.data_ptr() if cd == BF16 else None, None, ws.mem_stats[0].data_ptr(),
+                     ws.mem_stats[1].data_ptr(), Re, 0.0, 0)
+
+    def _build_decoder(self, plan: Plan, ws, p_drop: float, with_loss: bool, with_grad: bool):
+        D, lib = self.dims, self.lib
+        d, B, S, M = D.d, ws.B, ws.S, ws.M
+        Re, Rd = B * M, B * S
+        cd = self.cdt
+        plan.add("vct_embed_fwd", lib.vct_embed_fwd, ws.ids.data_ptr(), S + 1, self._p("cap_decoder.tgt_to_emb.weight"),
+                 self.pos.data_ptr(), ws.e0.data_ptr(), ws.e0_c.data_ptr() if cd == BF16 else None, cd, B, S, d, D.V, 0,
+                 p_drop, self.rng_state.data_ptr(), SITE_EMBED)
+        x, x_c = ws.e0, ws.e0_c
+        for l, e in enumerate(ws.dec):
+            pre = f"cap_decoder.decoder.layers.{l}."
+            m = L.MhaArgs()
+            m.B, m.L, m.Lk, m.d, m.H, m.dtype = B, S, S, d, D.H_dec, cd
+            m.x, m.w_in, m.b_in = x_c.data_ptr(), self._w(pre + "self_attn.in_proj_weight"), self._p(pre + "self_attn.in_proj_bias")
+            m.qkv, m.o, m.key_pad = e.qkv.data_ptr(), e.ao.data_ptr(), ws.tok_pad.data_ptr()
+            m.drop_p, m.rng_state, m.site = p_drop, self.rng_state.data_ptr(), _dec_site(l, 0)
+            m.gemm_impl = self.gemm_impl
+            plan.keep.append(m)
+            plan.add(f"vct_attn_dec_self_fwd:{l}", lib.vct_attn_dec_self_fwd, C.byref(m))
+            self._gemm(plan, f"dec{l}.self.out_proj", Rd, d, d, e.ao.data_ptr(), d, 0, self._w(pre + "self_attn.out_proj.weight"),
+                       d, 0, e.s1.data_ptr(), F32, d, bias=self._p(pre + "self_attn.out_proj.bias"))
+            self._ln_fwd(plan, f"dec{l}.norm1", x.data_ptr(), e.s1.data_ptr(), pre + "norm1.weight", pre + "norm1.bias",
+                         e.x1.data_ptr(), e.x1_c.data_ptr() if cd == BF16 else None, e.s1.data_ptr(),
+                         e.stats[0].data_ptr(), e.stats[1].data_ptr(), Rd, p_drop, _dec_site(l, 1))
+            c = L.MhaArgs()
+            c.B, c.L, c.Lk, c.d, c.H, c.dtype = B, S, M, d, D.H_dec, cd
+            c.x, c.mem = e.x1_c.data_ptr(), ws.mem_c.data_ptr()
+            c.w_in, c.b_in = self._w(pre + "multihead_attn.in_proj_weight"), self._p(pre + "multihead_attn.in_proj_bias")
+            c.qkv, c.kv, c.kv_ready, c.o = e.q.data_ptr(), e.kv.data_ptr(), 0, e.ao2.data_ptr()
+            c.drop_p, c.rng_state, c.site = p_drop, self.rng_state.data_ptr(), _dec_site(l, 2)
+            c.gemm_impl = self.gemm_impl
+            plan.keep.append(c)
+            plan.add(f"vct_attn_dec_cross_fwd:{l}", lib.vct_attn_dec_cross_fwd, C.byref(c))
+            self._gemm(plan, f"dec{l}.cross.out_proj", Rd, d, d, e.ao2.data_ptr(), d, 0,
+                       self._w(pre + "multihead_attn.out_proj.weight"), d, 0, e.s2.data_ptr(), F32, d,
+                       bias=self._p(pre + "multihead_attn.out_proj.bias"))
+            self._ln_fwd(plan, f"dec{l}.norm2", e.x1.data_ptr(), e.s2.data_ptr(), pre + "norm2.weight", pre + "norm2.bias",
+                         e.x2.data_ptr(), e.x2_c.data_ptr() if cd == BF16 else None, e.s2.data_ptr(),
+                         e.stats[2].data_ptr(), e.stats[3].data_ptr(), Rd, p_drop, _dec_site(l, 3))
+            self._gemm(plan, f"dec{l}.linear1", Rd, D.F_dec, d, e.x2_c.data_ptr(), d, 0, self._w(pre + "linear1.weight"), d, 0,
+                       e.z.data_ptr(), cd, D.F_dec, bias=self._p(pre + "linear1.bias"), C2=e.h.data_ptr(), c2_dtype=cd,
+                       ldc2=D.F_dec, act=L.ACT_GELU_FWD, drop_p=p_drop, site=_dec_site(l, 4))
+            self._gemm(plan, f"dec{l}.linear2", Rd, d, D.F_dec, e.h.data_ptr(), D.F_dec, 0, self._w(pre + "linear2.weight"),
+                       D.F_dec, 0, e.s3.data_ptr(), F32, d, bias=self._p(pre + "linear2.bias"))
+            self._ln_fwd(plan, f"dec{l}.norm3", e.x2.data_ptr(), e.s3.data_ptr(), pre + "norm3.weight", pre + "norm3.bias",
+                         e.x3.data_ptr(), e.x3_c.data_ptr() if cd == BF16 else None, e.s3.data_ptr(),
+                         e.stats[4].data_ptr(), e.stats[5].data_ptr(), Rd, p_drop, _dec_site(l, 5))
+            x, x_c = e.x3, e.x3_c
+        ws.dec_out = x
+        self._ln_fwd(plan, "dec.norm", None, x.data_ptr(), "cap_decoder.decoder.norm.weight", "cap_decoder.decoder.norm.bias",
+                     ws.hfin.data_ptr(), ws.hfin_c.data_ptr() if cd == BF16 else None, None, ws.hfin_stats[0].data_ptr(),
+                     ws.hfin_stats[1].data_ptr(), Rd, 0.0, 0)
+        self._gemm(plan, "generator", Rd, D.V, d, ws.hfin_c.data_ptr(), d, 0, self._w("cap_decoder.generator.weight"), d, 0,
+                   ws.logits.data_ptr(), F32, ws.Vp, bias=self._p("cap_decoder.generator.bias"))
+        if with_loss or with_grad:
+            self._sce(plan, ws, with_loss, with_grad)
+
+    def _sce(self, plan: Plan, ws, with_loss: bool, with_grad: bool):
+        D = self.dims
+        plan.add("vct_sce", self.lib.vct_sce, ws.logits.data_ptr(), ws.Vp, ws.ids.data_ptr(), ws.S + 1, ws.B, ws.S, D.V,
+                 float(D.alpha), float(1.0 - D.alpha), D.pad_id,
+                 ws.loss.data_ptr() if with_loss else None, ws.row_parts.data_ptr(), self.counters.data_ptr() + 4 * 4,
+                 ws.dlogits.data_ptr() if with_grad else None, self.cdt, ws.Vp, self.upstream.data_ptr())
+
+    def plan_forward(self, ws, *, fused_grad: bool, part: str = "all", with_loss: bool = True) -> Plan:
+        """part 'all': encoder + decoder + generator + SCE loss; 'dec': decoder side only (memory already
+        in ws.mem / ws.mem_c).  fused_grad: the SCE kernel also writes d loss / d logits in the same pass
+        (native trainer); otherwise vct_sce runs again in backward with the upstream gradient (autograd)."""
+        key = ("fwd", fused_grad, part, with_loss)
+        if key not in ws.plans:
+            p = Plan()
+            pd = float(self.dims.dropout) if ws.training else 0.0
+            if part == "all":
+                self._build_encoder(p, ws, pd)
+            self._build_decoder(p, ws, pd, with_loss=with_loss, with_grad=fused_grad)
+            ws.plans[key] = p
+        return ws.plans[key]
+
+    def plan_encode(self, ws) -> Plan:
+        if "encode" not in ws.plans:
+            p = Plan()
+            self._build_encoder(p, ws, float(self.dims.dropout) if ws.training else 0.0)
+            ws.plans["encode"] = p
+        return ws.plans["encode"]
+
+    # ------------------------------------------------------------------------------------------
+    # backward plan
+    # ------------------------------------------------------------------------------------------
+    def plan_backward(self, ws, *, sce_first: bool, part: str = "all") -> Plan:
+        """part: 'all' (loss -> every gradient), 'dec' (loss -> decoder grads + d memory in ws.g_mem),
+        'enc' (ws.g_mem -> encoder grads)."""
+        key = ("bwd", sce_first, part)
+        if key in ws.plans:
+            return ws.plans[key]
+        if not ws.training:
+            raise RuntimeError("backward needs a training workspace")
+        p = Plan()
+        if part in ("all", "dec"):
+            self._build_decoder_bwd(p, ws, sce_first)
+        if part in ("all", "enc"):
+            self._build_encoder_bwd(p, ws)
+        ws.plans[key] = p
+        return p
+
+    def _build_decoder_bwd(self, p: Plan, ws, sce_first: bool):
+        D, lib = self.dims, self.lib
+        d, B, S, M = D.d, ws.B, ws.S, ws.M
+        Re, Rd = B * M, B * S
+        cd = self.cdt
+        pd = float(D.dropout)
+        if sce_first:
+            self._sce(p, ws, with_loss=False, with_grad=True)
+        dl = ws.dlogits.data_ptr()
+        # ---- generator -------------------------------------------------------------------------
+        self._gemm(p, "generator.wgrad", D.V, d, Rd, dl, ws.Vp, 1, ws.hfin_c.data_ptr(), d, 1,
+                   self._g("cap_decoder.generator.weight"), F32, d)
+        self._colsum(p, "generator.bias", dl, ws.Vp, Rd, D.V, self._g("cap_decoder.generator.bias"), ws)
+        self._gemm(p, "generator.dgrad", Rd, d, D.V, dl, ws.Vp, 0, self._w("cap_decoder.generator.weight"), d, 1,
+                   ws.g_a.data_ptr(), F32, d)
+        self._ln_bwd(p, "dec.norm", ws.g_a.data_ptr(), ws.dec_out.data_ptr(), ws.hfin_stats[0].data_ptr(),
+                     ws.hfin_stats[1].data_ptr(), "cap_decoder.decoder.norm.weight", "cap_decoder.decoder.norm.bias",
+                     ws.g_b.data_ptr(), None, None, Rd, 0.0, 0, ws)
+        dx, other = ws.g_b, ws.g_a          # dx: gradient wrt the current layer's output
+        first_mem = True
+        for l in reversed(range(D.L_dec)):
+            e = ws.dec[l]
+            pre = f"cap_decoder.decoder.layers.{l}."
+            xin_c = (ws.dec[l - 1].x3_c if l > 0 else ws.e0_c)
+            # norm3 / FFN
+            self._ln_bwd(p, f"dec{l}.norm3", dx.data_ptr(), e.s3.data_ptr(), e.stats[4].data_ptr(), e.stats[5].data_ptr(),
+                         pre + "norm3.weight", pre + "norm3.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         self._g(pre + "linear2.bias"), Rd, pd, _dec_site(l, 5), ws)
+            self._gemm(p, f"dec{l}.linear2.wgrad", d, D.F_dec, Rd, ws.g_r_c.data_ptr(), d, 1, e.h.data_ptr(), D.F_dec, 1,
+                       self._g(pre + "linear2.weight"), F32, D.F_dec)
+            self._gemm(p, f"dec{l}.linear2.dgrad", Rd, D.F_dec, d, ws.g_r_c.data_ptr(), d, 0, self._w(pre + "linear2.weight"),
+                       D.F_dec, 1, ws.g_z_c.data_ptr(), cd, D.F_dec, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_dec,
+                       drop_p=pd, site=_dec_site(l, 4))
+            self._gemm(p, f"dec{l}.linear1.wgrad", D.F_dec, d, Rd, ws.g_z_c.data_ptr(), D.F_dec, 1, e.x2_c.data_ptr(), d, 1,
+                       self._g(pre + "linear1.weight"), F32, d)
+            self._colsum(p, f"dec{l}.linear1.bias", ws.g_z_c.data_ptr(), D.F_dec, Rd, D.F_dec, self._g(pre + "linear1.bias"), ws)
+            self._gemm(p, f"dec{l}.linear1.dgrad", Rd, d, D.F_dec, ws.g_z_c.data_ptr(), D.F_dec, 0, self._w(pre + "linear1.weight"),
+                       d, 1, other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
+            dx, other = other, dx           # dx = grad wrt x2
+            # norm2 / cross attention
+            self._ln_bwd(p, f"dec{l}.norm2", dx.data_ptr(), e.s2.data_ptr(), e.stats[2].data_ptr(), e.stats[3].data_ptr(),
+                         pre + "norm2.weight", pre + "norm2.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         self._g(pre + "multihead_attn.out_proj.bias"), Rd, pd, _dec_site(l, 3), ws)
+            self._gemm(p, f"dec{l}.cross.out_proj.wgrad", d, d, Rd, ws.g_r_c.data_ptr(), d, 1, e.ao2.data_ptr(), d, 1,
+                       self._g(pre + "multihead_attn.out_proj.weight"), F32, d)
+            self._gemm(p, f"dec{l}.cross.out_proj.dgrad", Rd, d, d, ws.g_r_c.data_ptr(), d, 0,
+                       self._w(pre + "multihead_attn.out_proj.weight"), d, 1, ws.g_o_c.data_ptr(), cd, d)
+            es = _ESIZE[cd]
+            self._attn(p, f"dec{l}.cross", True, B=B, H=D.H_dec, Lq=S, Lk=M, q=e.q.data_ptr(), q_ld=d,
+                       k=e.kv.data_ptr(), k_ld=2 * d, v=e.kv.data_ptr() + d * es, v_ld=2 * d, o=None, o_ld=d,
+                       p=pd, site=_dec_site(l, 2), d_o=ws.g_o_c.data_ptr(), do_ld=d, dq=ws.g_q_c.data_ptr(), dq_ld=d,
+                       dk=ws.g_kv_c.data_ptr(), dk_ld=2 * d, dv=ws.g_kv_c.data_ptr() + d * es, dv_ld=2 * d)
+            wname, bname = pre + "multihead_attn.in_proj_weight", pre + "multihead_attn.in_proj_bias"
+            self._gemm(p, f"dec{l}.cross.q.wgrad", d, d, Rd, ws.g_q_c.data_ptr(), d, 1, e.x1_c.data_ptr(), d, 1,
+                       self._g(wname), F32, d)
+            self._colsum(p, f"dec{l}.cross.q.bias", ws.g_q_c.data_ptr(), d, Rd, d, self._g(bname), ws)
+            self._gemm(p, f"dec{l}.cross.kv.wgrad", 2 * d, d, Re, ws.g_kv_c.data_ptr(), 2 * d, 1, ws.mem_c.data_ptr(), d, 1,
+                       self._g(wname, d * d), F32, d)
+            self._colsum(p, f"dec{l}.cross.kv.bias", ws.g_kv_c.data_ptr(), 2 * d, Re, 2 * d, self._g(bname, d), ws)
+            self._gemm(p, f"dec{l}.cross.q.dgrad", Rd, d, d, ws.g_q_c.data_ptr(), d, 0, self._w(wname), d, 1,
+                       other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
+            self._gemm(p, f"dec{l}.cross.kv.dgrad", Re, d, 2 * d, ws.g_kv_c.data_ptr(), 2 * d, 0, self._w(wname, d), d, 1,
+                       ws.g_mem.data_ptr(), F32, d, addend=None if first_mem else ws.g_mem.data_ptr(), ld_addend=d)
+            first_mem = False
+            dx, other = other, dx           # dx = grad wrt x1
+            # norm1 / self attention
+            self._ln_bwd(p, f"dec{l}.norm1", dx.data_ptr(), e.s1.data_ptr(), e.stats[0].data_ptr(), e.stats[1].data_ptr(),
+                         pre + "norm1.weight", pre + "norm1.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         self._g(pre + "self_attn.out_proj.bias"), Rd, pd, _dec_site(l, 1), ws)
+            self._gemm(p, f"dec{l}.self.out_proj.wgrad", d, d, Rd, ws.g_r_c.data_ptr(), d, 1, e.ao.data_ptr(), d, 1,
+                       self._g(pre + "self_attn.out_proj.weight"), F32, d)
+            self._gemm(p, f"dec{l}.self.out_proj.dgrad", Rd, d, d, ws.g_r_c.data_ptr(), d, 0,
+                       self._w(pre + "self_attn.out_proj.weight"), d, 1, ws.g_o_c.data_ptr(), cd, d)
+            qkv, gq = e.qkv.data_ptr(), ws.g_qkv_c.data_ptr()
+            self._attn(p, f"dec{l}.self", True, B=B, H=D.H_dec, Lq=S, Lk=S, q=qkv, q_ld=3 * d, k=qkv + d * es, k_ld=3 * d,
+                       v=qkv + 2 * d * es, v_ld=3 * d, o=None, o_ld=d, key_pad=ws.tok_pad.data_ptr(), causal=1, p=pd,
+                       site=_dec_site(l, 0), d_o=ws.g_o_c.data_ptr(), do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
+                       dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d)
+            wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
+            self._gemm(p, f"dec{l}.self.in_proj.wgrad", 3 * d, d, Rd, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d)
+            self._colsum(p, f"dec{l}.self.in_proj.bias", gq, 3 * d, Rd, 3 * d, self._g(bname), ws)
+            self._gemm(p, f"dec{l}.self.in_proj.dgrad", Rd, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
+                       addend=ws.g_s.data_ptr(), ld_addend=d)
+            dx, other = other, dx           # dx = grad wrt the layer input
+        # ---- embedding ---------------------------------------------------------------------------
+        p.add("vct_embed_bwd", lib.vct_embed_bwd, ws.ids.data_ptr(), S + 1, dx.data_ptr(),
+              self._g("cap_decoder.tgt_to_emb.weight"), B, S, d, D.V, D.pad_id, pd, self.rng_state.data_ptr(), SITE_EMBED)
+
+    def _build_encoder_bwd(self, p: Plan, ws):
+        D, lib = self.dims, self.lib
+        d, B, M = D.d, ws.B, ws.M
+        Re = B * M
+        cd = self.cdt
+        pd = float(D.dropout)
+        self._ln_bwd(p, "enc.norm", ws.g_mem.data_ptr(), ws.enc_out.data_ptr(), ws.mem_stats[0].data_ptr(),
+                     ws.mem_stats[1].data_ptr(), "video_encoder.transformer_encoder.norm.weight",
+                     "video_encoder.transformer_encoder.norm.bias", ws.g_a.data_ptr(), None, None, Re, 0.0, 0, ws)
+        dx, other = ws.g_a, ws.g_b
+        es = _ESIZE[cd]
+        for l in reversed(range(D.L_enc)):
+            e = ws.enc[l]
+            pre = f"video_encoder.transformer_encoder.layers.{l}."
+            xin_c = (ws.enc[l - 1].x2_c if l > 0 else ws.x0_c)
+            self._ln_bwd(p, f"enc{l}.norm2", dx.data_ptr(), e.s2.data_ptr(), e.stats[2].data_ptr(), e.stats[3].data_ptr(),
+                         pre + "norm2.weight", pre + "norm2.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         self._g(pre + "linear2.bias"), Re, pd, _enc_site(l, 3), ws)
+            self._gemm(p, f"enc{l}.linear2.wgrad", d, D.F_enc, Re, ws.g_r_c.data_ptr(), d, 1, e.h.data_ptr(), D.F_enc, 1,
+                       self._g(pre + "linear2.weight"), F32, D.F_enc)
+            self._gemm(p, f"enc{l}.linear2.dgrad", Re, D.F_enc, d, ws.g_r_c.data_ptr(), d, 0, self._w(pre + "linear2.weight"),
+                       D.F_enc, 1, ws.g_z_c.data_ptr(), cd, D.F_enc, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_enc,
+                       drop_p=pd, site=_enc_site(l, 2))
+            self._gemm(p, f"enc{l}.linear1.wgrad", D.F_enc, d, Re, ws.g_z_c.data_ptr(), D.F_enc, 1, e.x1_c.data_ptr(), d, 1,
+                       self._g(pre + "linear1.weight"), F32, d)
+            self._colsum(p, f"enc{l}.linear1.bias", ws.g_z_c.data_ptr(), D.F_enc, Re, D.F_enc, self._g(pre + "linear1.bias"), ws)
+            self._gemm(p, f"enc{l}.linear1.dgrad", Re, d, D.F_enc, ws.g_z_c.data_ptr(), D.F_enc, 0, self._w(pre + "linear1.weight"),
+                       d, 1, other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
+            dx, other = other, dx
+            self._ln_bwd(p, f"enc{l}.norm1", dx.data_ptr(), e.s1.data_ptr(), e.stats[0].data_ptr(), e.stats[1].data_ptr(),
+                         pre + "norm1.weight", pre + "norm1.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         self._g(pre + "self_attn.out_proj.bias"), Re, pd, _enc_site(l, 1), ws)
+            self._gemm(p, f"enc{l}.out_proj.wgrad", d, d, Re, ws.g_r_c.data_ptr(), d, 1, e.ao.data_ptr(), d, 1,
+                       self._g(pre + "self_attn.out_proj.weight"), F32, d)
+            self._gemm(p, f"enc{l}.out_proj.dgrad", Re, d, d, ws.g_r_c.data_ptr(), d, 0, self._w(pre + "self_attn.out_proj.weight"),
+                       d, 1, ws.g_o_c.data_ptr(), cd, d)
+            qkv, gq = e.qkv.data_ptr(), ws.g_qkv_c.data_ptr()
+            self._attn(p, f"enc{l}.self", True, B=B, H=D.H_enc, Lq=M, Lk=M, q=qkv, q_ld=3 * d, k=qkv + d * es, k_ld=3 * d,
+                       v=qkv + 2 * d * es, v_ld=3 * d, o=None, o_ld=d, key_pad=ws.vid_pad.data_ptr(), causal=0, p=pd,
+                       site=_enc_site(l, 0), d_o=ws.g_o_c.data_ptr(), do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
+                       dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d)
+            wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
+            self._gemm(p, f"enc{l}.in_proj.wgrad", 3 * d, d, Re, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d)
+            self._colsum(p, f"enc{l}.in_proj.bias", gq, 3 * d, Re, 3 * d, self._g(bname), ws)
+            last = l == 0
+            self._gemm(p, f"enc{l}.in_proj.dgrad", Re, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
+                       addend=ws.g_s.data_ptr(), ld_addend=d,
+                       C2=ws.g_x0_c.data_ptr() if (last and cd == BF16) else None, c2_dtype=cd, ldc2=d)
+            dx, other = other, dx
+        g_x0_c = ws.g_x0_c.data_ptr() if cd == BF16 else dx.data_ptr()
+        self._gemm(p, "unify.wgrad", d, D.Din, Re, g_x0_c, d, 1, ws.a0.data_ptr(), D.Din, 1,
+                   self._g("video_encoder.unify.0.weight"), F32, D.Din)
+        self._colsum(p, "unify.bias", g_x0_c, d, Re, d, self._g("video_encoder.unify.0.bias"), ws)
+
+    # ------------------------------------------------------------------------------------------
+    # running
+    # ------------------------------------------------------------------------------------------
+    def stage_inputs(self, ws, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: Optional[torch.Tensor]):
+        """Copy the step's inputs into the workspace (host or device sources; async on the current stream)."""
+        ws.feats.copy_(feats.reshape(ws.feats.shape), non_blocking=True)
+        ws.vid_pad[:, 0] = 0
+        if vid_pad is None:
+            ws.vid_pad[:, 1:] = 0
+        else:
+            ws.vid_pad[:, 1:].copy_(vid_pad, non_blocking=True)
+        if ids is not None:
+            ws.ids.copy_(ids, non_blocking=True)
+            torch.eq(ws.ids[:, :-1], self.dims.pad_id, out=ws.tok_pad.view(torch.bool))
+
+    def run(self, plan: Plan) -> None:
+        self.launches += plan.run(self._stream())
+
+    def zero_scatter_grads(self) -> None:
+        """Only the embedding gradient is accumulated with atomics; every other gradient is overwritten."""
+        self.arena.grad_view("cap_decoder.tgt_to_emb.weight").zero_()
+
+    # ---- Adam ------------------------------------------------------------------------------------
+    def set_adam(self, lr: float, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0) -> None:
+        self.arena.ensure_optimizer_state()
+        h = self.hyper.tolist()
+        h[0:5] = [lr, betas[0], betas[1], eps, weight_decay]
+        self.hyper.copy_(torch.tensor(h, dtype=torch.float32))
+
+    def set_lr(self, lr: float) -> None:
+        self.hyper[0:1].fill_(lr)
+
+    def tick(self) -> None:
+        L.check(self.lib.vct_step_tick(self.rng_state.data_ptr(), self.hyper.data_ptr(), self._stream()), "vct_step_tick")
+        self.launches += 1
+
+    def adam(self, grad_scale: float = 1.0) -> None:
+        a = self.arena
+        shadow = a.ensure_shadow().data_ptr() if self.cdt == BF16 else None
+        L.check(self.lib.vct_adam(a.p32.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(), shadow,
+                                  a.numel, self.hyper.data_ptr(), grad_scale, self._stream()), "vct_adam")
+        self.launches += 1
+
+    # ------------------------------------------------------------------------------------------
+    # greedy decoding with a K/V cache (model/MMT4Caption.py:146-172, model/CapDecoder.py:62-79)
+    # ------------------------------------------------------------------------------------------
+    def decode_workspace(self, B: int, T: int, max_len: int) -> SimpleNamespace:
+        key = ("decode", B, T, max_len)
+        if key in self._ws:
+            return self._ws[key]
+        D = self.dims
+        d, M = D.d, T + 1
+        cdt, f32 = _TDT[self.cdt], torch.float32
+        two = self.cdt == BF16
+        dev = self.device
+        ws = SimpleNamespace(B=B, T=T, M=M, max_len=max_len, Vp=(D.V + 7) // 8 * 8)
+        ws.ys = torch.zeros((B, max_len), dtype=torch.int64, device=dev)
+        ws.ended = torch.zeros(B, dtype=torch.int32, device=dev)
+        ws.n_ended = torch.zeros(1, dtype=torch.int32, device=dev)
+
+        def pair(rows, cols):
+            t = torch.empty((rows, cols), dtype=f32, device=dev)
+            return t, (torch.empty((rows, cols), dtype=cdt, device=dev) if two else t)
+
+        ws.x, ws.x_c = pair(B, d)
+        ws.layers = []
+        for _ in range(D.L_dec):
+            e = SimpleNamespace()
+            e.cache = torch.zeros((B, max_len, 3 * d), dtype=cdt, device=dev)    # q,k,v of every position so far
+            e.ao = torch.empty((B, d), dtype=cdt, device=dev)
+            e.s1 = torch.empty((B, d), dtype=f32, device=dev)
+            e.x1, e.x1_c = pair(B, d)
+            e.q = torch.empty((B, d), dtype=cdt, device=dev)
+            e.kv = torch.empty((B * M, 2 * d), dtype=cdt, device=dev)            # cross K/V: projected once
+            e.ao2 = torch.empty((B, d), dtype=cdt, device=dev)
+            e.s2 = torch.empty((B, d), dtype=f32, device=dev)
+            e.x2, e.x2_c = pair(B, d)
+            e.z = torch.empty((B, D.F_dec), dtype=cdt, device=dev)
+            e.h = torch.empty((B, D.F_dec), dtype=cdt, device=dev)
+            e.s3 = torch.empty((B, d), dtype=f32, device=dev)
+            e.x3, e.x3_c = pair(B, d)
+            e.probs = None
+            ws.layers.append(e)
+        ws.hfin, ws.hfin_c = pair(B, d)
+        ws.logits = torch.empty((B, ws.Vp), dtype=f32, device=dev)
+        ws.plans = {}
+        self._ws[key] = ws
+        return ws
+
+    def plan_decode_init(self, dws, enc_ws) -> Plan:
+        """cross-attention K/V of every decoder layer from the encoder memory (once per batch)."""
+        key = ("init", id(enc_ws))
+        if key not in dws.plans:
+            D = self.dims
+            d = D.d
+            p = Plan()
+            for l, e in enumerate(dws.layers):
+                pre = f"cap_decoder.decoder.layers.{l}.multihead_attn."
+                self._gemm(p, f"dec{l}.cross.kv", dws.B * dws.M, 2 * d, d, enc_ws.mem_c.data_ptr(), d, 0,
+                           self._w(pre + "in_proj_weight", d), d, 0, e.kv.data_ptr(), self.cdt, 2 * d,
+                           bias=self._p(pre + "in_proj_bias", d))
+            dws.plans[key] = p
+        return dws.plans[key]
+
+    def plan_decode_step(self, dws, t: int, want_probs: bool = False) -> Plan:
+        """Feed token column t (ys[:, t]) and append ys[:, t+1] = argmax of the next-word logits."""
+        key = ("step", t, want_probs)
+        if key in dws.plans:
+            return dws.plans[key]
+        D, lib = self.dims, self.lib
+        d, B, M, Lmax = D.d, dws.B, dws.M, dws.max_len
+        cd, es = self.cdt, _ESIZE[self.cdt]
+        p = Plan()
+        p.add("vct_embed_fwd", lib.vct_embed_fwd, dws.ys.data_ptr() + 8 * t, Lmax, self._p("cap_decoder.tgt_to_emb.weight"),
+              self.pos.data_ptr(), dws.x.data_ptr(), dws.x_c.data_ptr() if cd == BF16 else None, cd, B, 1, d, D.V, t,
+              0.0, self.rng_state.data_ptr(), SITE_EMBED)
+        x, x_c = dws.x, dws.x_c
+        for l, e in enumerate(dws.layers):
+            pre = f"cap_decoder.decoder.layers.{l}."
+            cache = e.cache.data_ptr()
+            row = cache + t * 3 * d * es
+            self._gemm(p, f"dec{l}.self.in_proj", B, 3 * d, d, x_c.data_ptr(), d, 0, self._w(pre + "self_attn.in_proj_weight"),
+                       d, 0, row, cd, Lmax * 3 * d, bias=self._p(pre + "self_attn.in_proj_bias"))
+            self._attn(p, f"dec{l}.self", False, B=B, H=D.H_dec, Lq=1, Lk=t + 1, q=row, q_ld=3 * d, q_bs=Lmax * 3 * d,
+                       k=cache + d * es, k_ld=3 * d, k_bs=Lmax * 3 * d, v=cache + 2 * d * es, v_ld=3 * d, v_bs=Lmax * 3 * d,
+                       o=e.ao.data_ptr(), o_ld=d, o_bs=d)
+            self._gemm(p, f"dec{l}.self.out_proj", B, d, d, e.ao.data_ptr(), d, 0, self._w(pre + "self_attn.out_proj.weight"),
+                       d, 0, e.s1.data_ptr(), F32, d, bias=self._p(pre + "self_attn.out_proj.bias"))
+            self._ln_fwd(p, f"dec{l}.norm1", x.data_ptr(), e.s1.data_ptr(), pre + "norm1.weight", pre + "norm1.bias",
+                         e.x1.data_ptr(), e.x1_c.data_ptr() if cd == BF16 else None, None, None, None, B, 0.0, 0)
+            self._gemm(p, f"dec{l}.cross.q", B, d, d, e.x1_c.data_ptr(), d, 0, self._w(pre + "multihead_attn.in_proj_weight"),
+                       d, 0, e.q.data_ptr(), cd, d, bias=self._p(pre + "multihead_attn.in_proj_bias"))
+            if want_probs and e.probs is None:
+                e.probs = torch.zeros((B, D.H_dec, 1, M), dtype=torch.float32, device=self.device)
+            self._attn(p, f"dec{l}.cross", False, B=B, H=D.H_dec, Lq=1, Lk=M, q=e.q.data_ptr(), q_ld=d, q_bs=d,
+                       k=e.kv.data_ptr(), k_ld=2 * d, v=e.kv.data_ptr() + d * es, v_ld=2 * d, o=e.ao2.data_ptr(), o_ld=d,
+                       o_bs=d, probs=e.probs.data_ptr() if want_probs else None)
+            self._gemm(p, f"dec{l}.cross.out_proj", B, d, d, e.ao2.data_ptr(), d, 0,
+                       self._w(pre + "multihead_attn.out_proj.weight"), d, 0, e.s2.data_ptr(), F32, d,
+                       bias=self._p(pre + "multihead_attn.out_proj.bias"))
+            self._ln_fwd(p, f"dec{l}.norm2", e.x1.data_ptr(), e.s2.data_ptr(), pre + "norm2.weight", pre + "norm2.bias",
+                         e.x2.data_ptr(), e.x2_c.data_ptr() if cd == BF16 else None, None, None, None, B, 0.0, 0)
+            self._gemm(p, f"dec{l}.linear1", B, D.F_dec, d, e.x2_c.data_ptr(), d, 0, self._w(pre + "linear1.weight"), d, 0,
+                       e.z.data_ptr(), cd, D.F_dec, bias=self._p(pre + "linear1.bias"), C2=e.h.data_ptr(), c2_dtype=cd,
+                       ldc2=D.F_dec, act=L.ACT_GELU_FWD)
+            self._gemm(p, f"dec{l}.linear2", B, d, D.F_dec, e.h.data_ptr(), D.F_dec, 0, self._w(pre + "linear2.weight"),
+                       D.F_dec, 0, e.s3.data_ptr(), F32, d, bias=self._p(pre + "linear2.bias"))
+            self._ln_fwd(p, f"dec{l}.norm3", e.x2.data_ptr(), e.s3.data_ptr(), pre + "norm3.weight", pre + "norm3.bias",
+                         e.x3.data_ptr(), e.x3_c.data_ptr() if cd == BF16 else None, None, None, None, B, 0.0, 0)
+            x, x_c = e.x3, e.x3_c
+        self._ln_fwd(p, "dec.norm", None, x.data_ptr(), "cap_decoder.decoder.norm.weight", "cap_decoder.decoder.norm.bias",
+                     dws.hfin.data_ptr(), dws.hfin_c.data_ptr() if cd == BF16 else None, None, None, None, B, 0.0, 0)
+        self._gemm(p, "generator", B, D.V, d, dws.hfin_c.data_ptr(), d, 0, self._w("cap_decoder.generator.weight"), d, 0,
+                   dws.logits.data_ptr(), F32, dws.Vp, bias=self._p("cap_decoder.generator.bias"))
+        p.add("vct_argmax_append", lib.vct_argmax_append, dws.logits.data_ptr(), dws.Vp, B, D.V, dws.ys.data_ptr(), Lmax,
+              t + 1, self.end_id, dws.ended.data_ptr(), dws.n_ended.data_ptr())
+        dws.plans[key] = p
+        return p
+
+    end_id = 102
+
+    @torch.no_grad()
+    def greedy_decode(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], max_len: int, start_id: int,
+                      end_id: int, sync_every: int = 1, want_probs: bool = False):
+        """Returns ys [B, n] (device int64, incl. the start token).  Same stopping rule as the reference:
+        stop once every row has produced end_id (checked every ``sync_every`` tokens; the reference checks
+        every token through ``.tolist()``, model/MMT4Caption.py:168-172).  Checking less often only appends
+        tokens after a row's first [SEP], which the caption cut discards."""
+        self.check_arena()
+        self.refresh_shadow()
+        self.end_id = end_id
+        B, T, _ = feats.shape
+        enc_ws = self.workspace(B, T, 1, False)
+        self.stage_inputs(enc_ws, feats, vid_pad, None)
+        self.run(self.plan_encode(enc_ws))
+        dws = self.decode_workspace(B, T, max_len)
+        dws.ys.zero_()
+        dws.ys[:, 0] = start_id
+        dws.ended.zero_()
+        dws.n_ended.zero_()
+        self.run(self.plan_decode_init(dws, enc_ws))
+        n = 1
+        probs = [[] for _ in dws.layers] if want_probs else None
+        for t in range(max_len - 1):
+            self.run(self.plan_decode_step(dws, t, want_probs))
+            n = t + 2
+            if want_probs:
+                for l, e in enumerate(dws.layers):
+                    probs[l].append(e.probs.mean(dim=1).clone())      # head average [B, 1, M]
+            if (t + 1) % sync_every == 0 or t == max_len - 2:
+                if int(dws.n_ended.item()) >= B:
+                    break
+        ys = dws.ys[:, :n].clone()
+        if want_probs:
+            return ys, [torch.cat(pl, dim=1) for pl in probs]
+        return ys

@@ -1,0 +1,125 @@
+"""Native training step: the loop body of the reference's ``train_epoch`` (train.py:119-131 --
+forward, zero_grad, backward, optimizer.step, loss all-reduce) as ONE launch sequence over the flat
+arenas, optionally captured in a CUDA graph.
+
+    per step:  H2D stage inputs -> [tick | zero dE | forward plan (fused SCE grad) | backward plan |
+               gradient all-reduce (NCCL, bucketed, overlapped with backward) | vct_adam] -> loss
+
+Data parallelism is the reference's: one process per GPU, batch sharded by the caller
+(DistributedSampler, dataloader.py:524), gradients averaged across ranks (DDP, train.py:218).  Here the
+"bucket" is a slice of the flat gradient arena, so no flatten/copy is needed; slices are all-reduced
+(SUM) on a side stream as soon as the backward plan has produced them and the 1/world_size factor is
+folded into the Adam kernel.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Tuple
+
+import torch
+
+
+def gradient_buckets(arena, order: List[str], max_bytes: int = 64 << 20) -> List[Tuple[int, int]]:
+    """Partition the arena into contiguous [start, end) element ranges, in the order the backward plan
+    finishes them (``order`` = parameter-name prefixes, last-finished last).  Every element of the arena
+    belongs to exactly one bucket."""
+    names = arena.names
+    spans = []
+    for pre in order:
+        idx = [i for i, n in enumerate(names) if n.startswith(pre)]
+        if not idx:
+            continue
+        lo = arena.offset[names[idx[0]]]
+        last = names[idx[-1]]
+        hi = arena.offset[names[idx[-1] + 1]] if idx[-1] + 1 < len(names) else arena.numel
+        spans.append((lo, hi))
+    covered = sorted(spans)
+    pos = 0
+    for lo, hi in covered:
+        if lo != pos:
+            raise ValueError(f"bucket order leaves a gap or overlap at element {pos} (next span starts at {lo})")
+        pos = hi
+    if pos != arena.numel:
+        raise ValueError("bucket order does not cover the arena")
+    out = []
+    max_el = max_bytes // 4
+    for lo, hi in spans:
+        while hi - lo > max_el:
+            out.append((lo, lo + max_el))
+            lo += max_el
+        out.append((lo, hi))
+    return out
+
+
+def all_reduce_flat(flat: torch.Tensor, buckets: List[Tuple[int, int]], group=None) -> None:
+    """SUM all-reduce of each bucket slice (any backend: nccl on GPU, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    for lo, hi in buckets:
+        dist.all_reduce(flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+
+
+class CaptionTrainer:
+    def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
+                 use_graph: bool = True, process_group=None, world_size: Optional[int] = None):
+        import torch.distributed as dist
+        self.model = model
+        self.engine = model._engine()
+        if model.f_type != "caption":
+            raise ValueError("CaptionTrainer drives the caption task: call model.mode('caption') first")
+        self.engine.set_adam(lr, betas, eps, weight_decay)
+        self.engine.refresh_shadow(force=True)
+        self.use_graph = use_graph
+        self.group = process_group
+        self.world = world_size if world_size is not None else (dist.get_world_size(process_group)
+                                                                 if dist.is_available() and dist.is_initialized() else 1)
+        self._graphs = {}
+        self._warm = {}
+        self.buckets = None
+        if self.world > 1:
+            # backward finishes the decoder (generator first, embedding last) before the encoder
+            self.buckets = gradient_buckets(self.engine.arena, ["video_encoder.", "cap_decoder."])
+            self.comm_stream = torch.cuda.Stream(device=self.engine.device)
+
+    def set_lr(self, lr: float) -> None:
+        self.engine.set_lr(lr)
+
+    # ---- one step -----------------------------------------------------------------------------------
+    def _body(self, ws) -> None:
+        eng = self.engine
+        eng.tick()
+        eng.zero_scatter_grads()
+        eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
+        eng.run(eng.plan_backward(ws, sce_first=False, part="all"))
+        if self.world > 1:
+            all_reduce_flat(eng.arena.grad, self.buckets, self.group)
+        eng.adam(grad_scale=1.0 / self.world)
+
+    def step(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: torch.Tensor) -> torch.Tensor:
+        """feats fp32 [B,T,Din], vid_pad bool [B,T] | None, ids int64 [B,S+1] (host -- ideally pinned -- or
+        device tensors).  Returns the step's loss as a device scalar (no host sync)."""
+        eng = self.engine
+        B, T, _ = feats.shape
+        S = ids.shape[1] - 1
+        ws = eng.workspace(B, T, S, True)
+        eng.check_arena()
+        eng.refresh_shadow()               # no-op unless the masters were edited outside vct_adam
+        eng.stage_inputs(ws, feats, vid_pad, ids)
+        key = (B, T, S)
+        if not self.use_graph:
+            self._body(ws)
+            return ws.loss[0]
+        if key not in self._graphs:
+            if self._warm.get(key, 0) < 2:
+                # eager warm-up: builds plans, sets kernel attributes, lets NCCL set up its channels
+                self._warm[key] = self._warm.get(key, 0) + 1
+                self._body(ws)
+                return ws.loss[0]
+            g = torch.cuda.CUDAGraph()
+            before = eng.launches
+            with torch.cuda.graph(g):
+                self._body(ws)
+            self._graphs[key] = (g, eng.launches - before)
+            eng.launches = before          # capture issued nothing; the replay below is this step
+        g, n = self._graphs[key]
+        g.replay()
+        eng.launches += n
+        return ws.loss[0]
