@@ -1,9 +1,316 @@
-// tcgen05 GEMM -- placeholder until the TMA/tcgen05 kernel lands.
+// tcgen05 GEMM for sm_100a: bf16 operands staged by TMA (cp.async.bulk.tensor, 128-byte swizzle) into a
+// multi-stage shared-memory ring, tcgen05.mma (cta_group::1, M = 128, N = 64/128/256, K = 16 per
+// instruction) issued by one elected thread, fp32 accumulators in TMEM, epilogue warps read TMEM with
+// tcgen05.ld and apply the fused epilogue (gemm_epilogue.cuh).
+//
+//   warp 0 : TMA producer (one elected lane)
+//   warp 1 : TMEM allocation + MMA issuer (one elected lane)
+//   warps 2-5 : epilogue, one thread per accumulator row (TMEM lane)
+//
+// Operand layouts (vct_gemm): "trans = 0" operands are K-major (rows x K, K contiguous) and are loaded
+// as one [rows x 64] box per stage; "trans = 1" operands are MN-major (K x rows, rows contiguous) and are
+// loaded as rows/64 boxes of [64 K-rows x 64] per stage.  Both land in the canonical UMMA SWIZZLE_128B
+// layouts, so forward (x W^T), dgrad (dY W) and wgrad (dY^T X) all run on the same kernel without any
+// transposed copies.  Out-of-bounds rows / K tails are zero-filled by TMA.
+#include <cuda.h>
+
+#include <mutex>
+#include <unordered_map>
+
 #include "gemm_epilogue.cuh"
-namespace vct {
-int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
-    (void)a; (void)st;
-    set_error("vct_gemm: VCT_GEMM_TCGEN05 not built in this library");
-    return VCT_ERR_INVALID;
+
+using namespace vct;
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;                 // 64 bf16 = 128 bytes = one swizzle span
+constexpr int UMMA_K = 16;
+constexpr int kThreads = 192;
+constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;
+constexpr int kSmemBudget = 200 * 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    uint32_t done = 0;
+    while (true) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a protocol bug must not hang the GPU
+    }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+
+// UMMA shared-memory descriptor, SWIZZLE_128B, sm_100 version bits (cute::UMMA::SmemDescriptor)
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
+           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, Epilogue epi) {
+    constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
+    constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) unsigned long long full_bar[STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[STAGES];
+    __shared__ __align__(8) unsigned long long tmem_full_bar;
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        mbar_init(smem_u32(&tmem_full_bar), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"((uint32_t)BLOCK_N)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===== TMA producer =====
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                const uint32_t full = smem_u32(&full_bar[s]);
+                mbar_expect_tx(full, kStageBytes);
+                const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
+                const int k0 = kb * BLOCK_K;
+                if (!A_MN) {
+                    tma_load_2d(sa, &tmA, k0, m0, full);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, k0, full);
+                }
+                if (!B_MN) {
+                    tma_load_2d(sb, &tmB, k0, n0, full);
+                } else {
+#pragma unroll
+                    for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, k0, full);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ===== MMA issuer =====
+            // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, majors, N>>3, M>>4
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % STAGES;
+                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
+                mbar_wait(smem_u32(&full_bar[s]), ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
+                // K-major: 8-row groups 1024 B apart, one MMA K-step = 32 B along the row
+                // MN-major: 64-wide MN chunks 8192 B apart (LBO), 8-K-row groups 1024 B apart (SBO), K-step = 2048 B
+                const uint64_t adesc = A_MN ? make_desc(sa, 8192, 1024) : make_desc(sa, 16, 1024);
+                const uint64_t bdesc = B_MN ? make_desc(sb, 8192, 1024) : make_desc(sb, 16, 1024);
+#pragma unroll
+                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                    const uint64_t ak = adesc + (uint64_t)((A_MN ? 2048u : 32u) * k >> 4);
+                    const uint64_t bk = bdesc + (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
+                    umma_bf16(tmem_base, ak, bk, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(smem_u32(&empty_bar[s]));      // frees the smem slot when these MMAs retire
+            }
+            umma_commit(smem_u32(&tmem_full_bar));          // accumulator complete
+        }
+    } else {
+        // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+        const int q = warp & 3;
+        const int m = m0 + q * 32 + lane;
+        mbar_wait(smem_u32(&tmem_full_bar), 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const Rng rng = make_rng(epi.rng_state, epi.act != VCT_ACT_NONE ? epi.drop_p : 0.f);
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                : "r"(taddr)
+                : "memory");
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const int nb = n0 + c * 32;
+            if (m < epi.M && nb < epi.N) {
+#pragma unroll
+                for (int g = 0; g < 8; ++g) {
+                    float v[4] = {__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                  __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])};
+                    epilogue_store4(epi, rng, m, nb + g * 4, v);
+                }
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host: tensor maps (cached) and dispatch
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; long long inner, outer, ld; int box_inner, box_outer;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+               box_outer == o.box_outer;
+    }
+};
+struct MapHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        auto mix = [&h](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+        return h;
+    }
+};
+
+// 2-D bf16 tensor: `inner` contiguous elements, `outer` rows `ld` elements apart; box [box_inner x box_outer]
+int get_map(const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, CUtensorMap* out) {
+    static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+    static std::mutex mu;
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = get_encode();
+    VCT_REQUIRE(enc != nullptr, "vct_gemm(tcgen05): cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VCT_REQUIRE(r == CUDA_SUCCESS, "vct_gemm(tcgen05): cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%lld outer=%lld ld=%lld",
+                (int)r, ptr, inner, outer, ld);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN>
+int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+    constexpr int kStage = kABytes + BLOCK_N * BLOCK_K * 2;
+    constexpr int STAGES = kSmemBudget / kStage > 8 ? 8 : kSmemBudget / kStage;
+    constexpr int smem = STAGES * kStage + 1024;
+    auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
+    static bool once = false;
+    if (!once) {
+        VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        once = true;
+    }
+    dim3 grid((a->N + BLOCK_N - 1) / BLOCK_N, (a->M + BLOCK_M - 1) / BLOCK_M);
+    kern<<<grid, kThreads, smem, st>>>(tmA, tmB, a->K, make_epilogue(a));
+    return check_launch("vct_gemm(tcgen05)");
+}
+
+template <int BLOCK_N>
+int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+    if (!a->a_trans && !a->b_trans) return launch<BLOCK_N, false, false>(a, tmA, tmB, st);
+    if (!a->a_trans && a->b_trans) return launch<BLOCK_N, false, true>(a, tmA, tmB, st);
+    if (a->a_trans && !a->b_trans) return launch<BLOCK_N, true, false>(a, tmA, tmB, st);
+    return launch<BLOCK_N, true, true>(a, tmA, tmB, st);
+}
+
+}  // namespace
+
+namespace vct {
+
+int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
+    VCT_REQUIRE(a->a_dtype == VCT_BF16, "vct_gemm(tcgen05): operands must be bf16");
+    VCT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "vct_gemm(tcgen05): lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
+    VCT_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
+                "vct_gemm(tcgen05): operands must be 16-byte aligned");
+    // tile width: the widest N tile that still yields about one wave of CTAs
+    const long long tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M;
+    int bn = 256;
+    while (bn > 64 && tiles_m * ((a->N + bn - 1) / bn) < kNumSMs) bn >>= 1;
+    CUtensorMap tmA, tmB;
+    if (!a->a_trans) { if (int e = get_map(a->A, a->K, a->M, a->lda, BLOCK_K, BLOCK_M, &tmA)) return e; }
+    else             { if (int e = get_map(a->A, a->M, a->K, a->lda, 64, BLOCK_K, &tmA)) return e; }
+    if (!a->b_trans) { if (int e = get_map(a->B, a->K, a->N, a->ldb, BLOCK_K, bn, &tmB)) return e; }
+    else             { if (int e = get_map(a->B, a->N, a->K, a->ldb, 64, BLOCK_K, &tmB)) return e; }
+    if (bn == 256) return dispatch_major<256>(a, tmA, tmB, st);
+    if (bn == 128) return dispatch_major<128>(a, tmA, tmB, st);
+    return dispatch_major<64>(a, tmA, tmB, st);
+}
+
 }  // namespace vct
