@@ -390,3 +390,59 @@ def test_argmax_append_ties_and_end_flags(lib):
     assert ys[1:, 2].tolist() == logits[1:, :V].argmax(1).tolist()
     assert ys[0, 2].item() == 77 and ys[1, 2].item() == 102
     assert ended.tolist() == [0, 1, 0, 0] and n_ended.item() == 1
+
+
+# ---- tcgen05 GEMM (TMA + UMMA, bf16 operands, fp32 TMEM accumulators) ---------------------------------
+TC_SHAPES = [(128, 256, 64), (128, 64, 128), (256, 512, 768), (1280, 768, 768), (832, 2304, 768), (200, 136, 72),
+             (64, 96, 40), (1280, 2048, 768), (768, 2048, 1280), (300, 30522, 96), (1280, 768, 30522)]
+
+
+@pytest.mark.parametrize("a_trans,b_trans", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("M,N,K", TC_SHAPES)
+def test_gemm_tcgen05_layouts(lib, a_trans, b_trans, M, N, K):
+    """All four operand-major combinations (forward, dgrad, wgrad), ragged M/N/K tails handled by TMA
+    zero fill, against an fp64 product of the same bf16-rounded operands.  fp32 accumulation: the only
+    error is summation order, ~ sqrt(K) * 2^-24 * |terms|."""
+    if K % 8:
+        K = (K + 7) // 8 * 8
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    A = torch.randn(M, K, generator=g)
+    B = torch.randn(N, K, generator=g)
+    lda = (M + 7) // 8 * 8 if a_trans else K
+    ldb = (N + 7) // 8 * 8 if b_trans else K
+    Ad = torch.zeros((K, lda) if a_trans else (M, lda), dtype=torch.bfloat16, device=DEV)
+    Bd = torch.zeros((K, ldb) if b_trans else (N, ldb), dtype=torch.bfloat16, device=DEV)
+    if a_trans: Ad[:, :M] = A.t().to(DEV)
+    else: Ad[:, :K] = A.to(DEV)
+    if b_trans: Bd[:, :N] = B.t().to(DEV)
+    else: Bd[:, :K] = B.to(DEV)
+    Ar = (Ad[:, :M].t() if a_trans else Ad[:, :K]).double()
+    Br = (Bd[:, :N].t() if b_trans else Bd[:, :K]).double()
+    ldc = (N + 3) // 4 * 4
+    Cc, _ = run_gemm(lib, Ad, Bd, a_trans, b_trans, M, N, K, impl=L.GEMM_TCGEN05, ldc=ldc)
+    want = Ar @ Br.t()
+    got = Cc[:, :N].double()
+    assert torch.isfinite(got).all()
+    torch.testing.assert_close(got, want, rtol=1e-4, atol=5e-4 * math.sqrt(K))
+
+
+def test_gemm_tcgen05_epilogues_match_simt(lib):
+    M, N, K = 300, 2048, 768
+    g = torch.Generator().manual_seed(77)
+    A = torch.randn(M, K, generator=g).to(DEV, torch.bfloat16)
+    B = (torch.randn(N, K, generator=g) * 0.05).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    addend = torch.randn(M, N, generator=g).to(DEV)
+    table = torch.randn(13, N, generator=g).to(DEV)
+    rng = torch.tensor([9, 4], dtype=torch.int64, device=DEV)
+    for kw in (dict(bias=bias, addend=addend, row_table=table, row_period=13, c2_dtype=L.BF16),
+               dict(bias=bias, act=L.ACT_GELU_FWD, c2_dtype=L.BF16, drop_p=0.3, rng_state=rng, site=5, c_dtype=L.BF16),
+               dict(act=L.ACT_GELU_BWD, aux=torch.randn(M, N, generator=g).to(DEV, torch.bfloat16), drop_p=0.3,
+                    rng_state=rng, site=5, c_dtype=L.BF16)):
+        cd = kw.pop("c_dtype", L.F32)
+        c_s, c2_s = run_gemm(lib, A, B, 0, 0, M, N, K, c_dtype=cd, impl=L.GEMM_SIMT, **kw)
+        c_t, c2_t = run_gemm(lib, A, B, 0, 0, M, N, K, c_dtype=cd, impl=L.GEMM_TCGEN05, **kw)
+        tol = dict(rtol=2e-2, atol=2e-2) if cd == L.BF16 else dict(rtol=1e-4, atol=1e-3)
+        torch.testing.assert_close(c_t.float(), c_s.float(), **tol)
+        if c2_s is not None:
+            torch.testing.assert_close(c2_t.float(), c2_s.float(), rtol=2e-2, atol=2e-2)
