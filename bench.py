@@ -168,6 +168,9 @@ def profile_calls(engine, plans):
     stream, eager).  Returns [(name, ms, call)] in issue order."""
     stream = torch.cuda.current_stream()
     out = []
+    # keep the GPU busy while the host queues every launch + event, so the event deltas are device time
+    # (kernel + its dependency gap), not host submission latency
+    torch.cuda._sleep(int(4e7))
     for plan in plans:
         for name, fn, a in plan.calls:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

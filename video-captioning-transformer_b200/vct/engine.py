@@ -71,7 +71,8 @@ class CaptionEngine:
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.precision = precision
         self.cdt = BF16 if precision == "bf16" else F32
-        impl = gemm_impl or os.environ.get("VCT_GEMM", "tcgen05" if precision == "bf16" else "simt")
+        # VCT_GEMM only selects between the two bf16 implementations; fp32 storage always runs the SIMT kernel
+        impl = gemm_impl or (os.environ.get("VCT_GEMM", "tcgen05") if precision == "bf16" else "simt")
         if impl not in ("simt", "tcgen05"):
             raise ValueError("gemm_impl must be 'simt' or 'tcgen05'")
         if impl == "tcgen05" and precision != "bf16":
