@@ -172,7 +172,7 @@ def profile_calls(engine, plans):
     # (kernel + its dependency gap), not host submission latency
     torch.cuda._sleep(int(4e7))
     for plan in plans:
-        for name, fn, a in plan.calls:
+        for name, fn, a, _lane in plan.calls:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
             rc = fn(*a, stream.cuda_stream)

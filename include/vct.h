@@ -171,8 +171,8 @@ int vct_ln_residual_fwd(const float* x, const float* r, const float* gamma, cons
  * dr_c (dr_dtype) = ds * dropmask (gradient wrt the branch output r; GEMM operand).
  * Column sums: dgamma += sum dy*xhat, dbeta += sum dy, dbias_r = sum dr (bias gradient of the
  * linear that produced r; NULL to skip).  `partials` is a fp32 workspace of
- * vct_ln_bwd_workspace_floats(R, d) floats, `counter` a zero-initialised uint32 (self-resetting).
- * dgamma/dbeta/dbias_r are OVERWRITTEN (deterministic two-level reduction, no atomics on data). */
+ * vct_ln_bwd_workspace_floats(R, d) floats; `counter` is unused (kept for ABI stability, may be NULL).
+ * dgamma/dbeta/dbias_r are OVERWRITTEN (deterministic two-kernel reduction, no atomics). */
 long long vct_ln_bwd_workspace_floats(int R, int d);
 int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
                         float* ds, void* dr_c, int dr_dtype, float* dgamma, float* dbeta, float* dbias_r,

@@ -1,14 +1,23 @@
 // Attention core: softmax(scale * Q K^T + mask) V, forward and backward.
-// One warp per (batch, head); K/V of the head live in shared memory (fp32), scores and the
-// softmax are spread one key per lane (two when Lk > 32) and reduced with warp shuffles.
-// Sequence lengths on this path are 13..33, so a whole head fits a warp.
+//
+// One CTA (4 warps) per (batch, head).  Sequence lengths on this path are 13..33, so the
+// whole head -- Q, K, V (and dO) -- is staged once in shared memory as fp32; each warp owns a contiguous block
+// of query rows.
+//   scores   : one key per lane; the lane keeps its K row in REGISTERS and the query row is read from shared
+//              memory as broadcast float4 -> FMA-bound, not shared-memory-bound
+//   softmax  : warp-shuffle max / sum over the key lanes; key-padding and causal masks are implicit
+//   P V      : one head-dim column per lane, 4 query rows register-blocked per pass over the keys
+//   backward : recomputes P (same Philox dropout mask), dP with V rows in registers, dS; dQ like P V;
+//              then the keys are split over the warps for dK = dS^T Q and dV = P^T dO (no atomics)
 #include "common.cuh"
 
 using namespace vct;
 
 namespace {
 
-constexpr int kMaxWarps = 4;
+constexpr int kWarps = 4;
+constexpr int kThreads = kWarps * 32;
+constexpr int RB = 4;                      // query rows (or keys) register-blocked per pass
 constexpr size_t kSmemBudget = 200 * 1024;
 
 struct Dims {
@@ -19,25 +28,57 @@ struct Dims {
     float scale;
 };
 
-// scores of query row i against key slots (lane, lane+32); returns probabilities p0,p1 (0 where masked)
-__device__ __forceinline__ void row_softmax(const float* __restrict__ qs, const float* __restrict__ Ks, int dh, int Lk,
-                                            int i, int lane, bool causal, const unsigned char* __restrict__ pad_row,
-                                            float scale, float& p0, float& p1) {
+// rows x dh tile (global, dtype T) -> shared fp32 [rows][stride], zero-padded to DHP columns
+template <typename T, int DHP>
+__device__ __forceinline__ void stage_tile(const T* __restrict__ g, long long ld, int rows, int dh, float* s, int stride) {
+    constexpr int NV = DHP / 4;
+    for (int idx = threadIdx.x; idx < rows * NV; idx += kThreads) {
+        const int r = idx / NV, c = (idx % NV) * 4;
+        float4 v = c < dh ? ld4(g + (long long)r * ld + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        float* d = s + r * stride + c;
+        d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+    }
+}
+
+// out[i][j] = sum_c rows[i][c] * keys[j][c] for this warp's rows [r0, r1) and every key j (lane = key).
+// The lane's key row lives in registers; rows are read as broadcast float4.
+template <int DHP>
+__device__ __forceinline__ void rows_dot_keys(const float* __restrict__ rows, const float* __restrict__ keys, int KS,
+                                              int Lk, int LkP, int r0, int r1, int lane, float* __restrict__ out) {
+    for (int slot = 0; slot * 32 < Lk; ++slot) {
+        const int j = lane + 32 * slot;
+        float kreg[DHP];
+#pragma unroll
+        for (int c = 0; c < DHP; ++c) kreg[c] = j < Lk ? keys[j * KS + c] : 0.f;
+#pragma unroll 1
+        for (int i = r0; i < r1; ++i) {
+            const float4* qrow = reinterpret_cast<const float4*>(rows + i * DHP);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < DHP / 4; ++c4) {
+                const float4 qv = qrow[c4];
+                a0 = fmaf(qv.x, kreg[4 * c4 + 0], a0);
+                a1 = fmaf(qv.y, kreg[4 * c4 + 1], a1);
+                a2 = fmaf(qv.z, kreg[4 * c4 + 2], a2);
+                a3 = fmaf(qv.w, kreg[4 * c4 + 3], a3);
+            }
+            if (j < Lk) out[i * LkP + j] = (a0 + a1) + (a2 + a3);
+        }
+    }
+}
+
+// masked softmax of one score row held as (lane, lane + 32); returns probabilities (0 where masked)
+__device__ __forceinline__ void softmax_row(const float* __restrict__ srow, int Lk, int i, int lane, bool causal,
+                                            const unsigned char* __restrict__ pad_row, float scale, float& p0, float& p1) {
     float s[2];
 #pragma unroll
     for (int t = 0; t < 2; ++t) {
         const int j = lane + 32 * t;
-        float a = -INFINITY;
-        if (j < Lk && !(causal && j > i) && !(pad_row != nullptr && pad_row[j])) {
-            const float* kr = Ks + j * (dh + 1);
-            a = 0.f;
-            for (int c = 0; c < dh; ++c) a += qs[c] * kr[c];
-            a *= scale;
-        }
-        s[t] = a;
+        const bool ok = j < Lk && !(causal && j > i) && !(pad_row != nullptr && pad_row[j]);
+        s[t] = ok ? srow[j] * scale : -INFINITY;
     }
     const float m = warp_max(fmaxf(s[0], s[1]));
-    if (m == -INFINITY) { p0 = p1 = 0.f; return; }   // fully masked row (cannot happen on this path, Q8)
+    if (m == -INFINITY) { p0 = p1 = 0.f; return; }    // fully masked row (cannot happen on this path, Q8)
     const float e0 = s[0] == -INFINITY ? 0.f : expf(s[0] - m);
     const float e1 = s[1] == -INFINITY ? 0.f : expf(s[1] - m);
     const float inv = 1.f / warp_sum(e0 + e1);
@@ -45,41 +86,59 @@ __device__ __forceinline__ void row_softmax(const float* __restrict__ qs, const 
     p1 = e1 * inv;
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kMaxWarps * 32)
+// acc[k][cc] = sum_j wt[j][ib + k] * mat[j][lane + 32 cc]  for k < RB   (wt transposed: [Lk][LqP])
+template <int DHP>
+__device__ __forceinline__ void weighted_rows(const float* __restrict__ wt, int LqP, const float* __restrict__ mat,
+                                              int MS, int Lk, int ib, int nrows, int lane, float (&acc)[RB][DHP / 32]) {
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+#pragma unroll
+        for (int cc = 0; cc < DHP / 32; ++cc) acc[k][cc] = 0.f;
+    for (int j = 0; j < Lk; ++j) {
+        float w[RB];
+#pragma unroll
+        for (int k = 0; k < RB; ++k) w[k] = k < nrows ? wt[j * LqP + ib + k] : 0.f;
+#pragma unroll
+        for (int cc = 0; cc < DHP / 32; ++cc) {
+            const float v = mat[j * MS + lane + 32 * cc];
+#pragma unroll
+            for (int k = 0; k < RB; ++k) acc[k][cc] = fmaf(w[k], v, acc[k][cc]);
+        }
+    }
+}
+
+template <typename T, int DHP>
+__global__ void __launch_bounds__(kThreads)
 attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
                 const unsigned char* __restrict__ key_pad, float* __restrict__ probs, Dims D, float drop_p,
-                const unsigned long long* __restrict__ rng_state, unsigned int site, int per_warp_floats) {
-    extern __shared__ float smem[];
+                const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (bh >= D.B * D.H) return;
-    const int b = bh / D.H, h = bh % D.H;
-    const int dh = D.dh, Lk = D.Lk, Lq = D.Lq, nv = dh >> 2;
-    float* Ks = smem + (size_t)warp * per_warp_floats;   // [Lk][dh+1]
-    float* Vs = Ks + Lk * (dh + 1);                      // [Lk][dh]
-    float* qs = Vs + Lk * dh;                            // [dh]
+    const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
+    const int dh = D.dh, Lk = D.Lk, Lq = D.Lq;
+    constexpr int KS = DHP + 1;
+    const int LkP = (Lk + 3) & ~3, LqP = (Lq + 3) & ~3;
+    float* Qs = sm;                       // [Lq][DHP]
+    float* Ks = Qs + Lq * DHP;            // [Lk][KS]
+    float* Vs = Ks + Lk * KS;             // [Lk][KS]
+    float* Ss = Vs + Lk * KS;             // [Lq][LkP]   raw scores
+    float* Pt = Ss + Lq * LkP;            // [Lk][LqP]   (dropped) probabilities, transposed
     const Rng rng = make_rng(rng_state, drop_p);
 
-    for (int idx = lane; idx < Lk * nv; idx += 32) {
-        const int j = idx / nv, c = (idx % nv) * 4;
-        float4 kv = ld4(k + (long long)b * D.k_bs + (long long)j * D.k_ld + h * dh + c);
-        float4 vv = ld4(v + (long long)b * D.v_bs + (long long)j * D.v_ld + h * dh + c);
-        float* kd = Ks + j * (dh + 1) + c;
-        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
-        float* vd = Vs + j * dh + c;
-        vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
-    }
+    stage_tile<T, DHP>(q + (long long)b * D.q_bs + h * dh, D.q_ld, Lq, dh, Qs, DHP);
+    stage_tile<T, DHP>(k + (long long)b * D.k_bs + h * dh, D.k_ld, Lk, dh, Ks, KS);
+    stage_tile<T, DHP>(v + (long long)b * D.v_bs + h * dh, D.v_ld, Lk, dh, Vs, KS);
+    __syncthreads();
+
+    const int R = (Lq + kWarps - 1) / kWarps;
+    const int r0 = warp * R, r1 = min(Lq, r0 + R);
+    if (r0 >= r1) return;
+    rows_dot_keys<DHP>(Qs, Ks, KS, Lk, LkP, r0, r1, lane, Ss);
+    __syncwarp();
     const unsigned char* pad_row = key_pad ? key_pad + (long long)b * Lk : nullptr;
-    for (int i = 0; i < Lq; ++i) {
-        __syncwarp();
-        if (lane < nv) {
-            float4 qv = ld4(q + (long long)b * D.q_bs + (long long)i * D.q_ld + h * dh + lane * 4);
-            qs[lane * 4 + 0] = qv.x; qs[lane * 4 + 1] = qv.y; qs[lane * 4 + 2] = qv.z; qs[lane * 4 + 3] = qv.w;
-        }
-        __syncwarp();
+    for (int i = r0; i < r1; ++i) {
         float p0, p1;
-        row_softmax(qs, Ks, dh, Lk, i, lane, D.causal != 0, pad_row, D.scale, p0, p1);
+        softmax_row(Ss + i * LkP, Lk, i, lane, D.causal != 0, pad_row, D.scale, p0, p1);
         const long long pbase = ((long long)bh * Lq + i) * Lk;
         if (probs) {
             if (lane < Lk) probs[pbase + lane] = p0;
@@ -89,121 +148,146 @@ attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
             if (lane < Lk) p0 *= dropout_scale1(rng, site, (unsigned long long)(pbase + lane));
             if (lane + 32 < Lk) p1 *= dropout_scale1(rng, site, (unsigned long long)(pbase + lane + 32));
         }
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int j = 0; j < Lk; ++j) {
-            const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
-            const float* vr = Vs + j * dh;
+        if (lane < Lk) Pt[lane * LqP + i] = p0;
+        if (lane + 32 < Lk) Pt[(lane + 32) * LqP + i] = p1;
+    }
+    __syncwarp();
+    for (int ib = r0; ib < r1; ib += RB) {
+        const int nrows = min(RB, r1 - ib);
+        float acc[RB][DHP / 32];
+        weighted_rows<DHP>(Pt, LqP, Vs, KS, Lk, ib, nrows, lane, acc);
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = lane + 32 * cc;
-                if (c < dh) acc[cc] += pj * vr[c];
+        for (int kk = 0; kk < RB; ++kk) {
+            if (kk < nrows) {
+                T* orow = o + (long long)b * D.o_bs + (long long)(ib + kk) * D.o_ld + h * dh;
+#pragma unroll
+                for (int cc = 0; cc < DHP / 32; ++cc) {
+                    const int c = lane + 32 * cc;
+                    if (c < dh) orow[c] = from_f32<T>(acc[kk][cc]);
+                }
             }
-        }
-        T* orow = o + (long long)b * D.o_bs + (long long)i * D.o_ld + h * dh;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = lane + 32 * cc;
-            if (c < dh) orow[c] = from_f32<T>(acc[cc]);
         }
     }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(kMaxWarps * 32)
+template <typename T, int DHP>
+__global__ void __launch_bounds__(kThreads)
 attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ d_o,
                 T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, const unsigned char* __restrict__ key_pad,
-                Dims D, float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site,
-                int per_warp_floats) {
-    extern __shared__ float smem[];
+                Dims D, float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int bh = blockIdx.x * (blockDim.x >> 5) + warp;
-    if (bh >= D.B * D.H) return;
-    const int b = bh / D.H, h = bh % D.H;
-    const int dh = D.dh, Lk = D.Lk, Lq = D.Lq, nv = dh >> 2;
-    float* Ks = smem + (size_t)warp * per_warp_floats;   // [Lk][dh+1]
-    float* Vs = Ks + Lk * (dh + 1);                      // [Lk][dh+1]
-    float* dKs = Vs + Lk * (dh + 1);                     // [Lk][dh]
-    float* dVs = dKs + Lk * dh;                          // [Lk][dh]
-    float* qs = dVs + Lk * dh;                           // [dh]
-    float* dos = qs + dh;                                // [dh]
+    const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
+    const int dh = D.dh, Lk = D.Lk, Lq = D.Lq;
+    constexpr int KS = DHP + 1;
+    const int LkP = (Lk + 3) & ~3, LqP = (Lq + 3) & ~3;
+    float* Qs = sm;                        // [Lq][DHP]
+    float* dOs = Qs + Lq * DHP;            // [Lq][DHP]
+    float* Ks = dOs + Lq * DHP;            // [Lk][KS]
+    float* Vs = Ks + Lk * KS;              // [Lk][KS]
+    float* Ss = Vs + Lk * KS;              // [Lq][LkP]   raw scores
+    float* dPs = Ss + Lq * LkP;            // [Lq][LkP]   dO . V
+    float* dSt = dPs + Lq * LkP;           // [Lk][LqP]   dS transposed
+    float* Pdt = dSt + Lk * LqP;           // [Lk][LqP]   dropped probabilities transposed
     const Rng rng = make_rng(rng_state, drop_p);
 
-    for (int idx = lane; idx < Lk * nv; idx += 32) {
-        const int j = idx / nv, c = (idx % nv) * 4;
-        float4 kv = ld4(k + (long long)b * D.k_bs + (long long)j * D.k_ld + h * dh + c);
-        float4 vv = ld4(v + (long long)b * D.v_bs + (long long)j * D.v_ld + h * dh + c);
-        float* kd = Ks + j * (dh + 1) + c;
-        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
-        float* vd = Vs + j * (dh + 1) + c;
-        vd[0] = vv.x; vd[1] = vv.y; vd[2] = vv.z; vd[3] = vv.w;
-    }
-    for (int idx = lane; idx < Lk * dh; idx += 32) { dKs[idx] = 0.f; dVs[idx] = 0.f; }
-    const unsigned char* pad_row = key_pad ? key_pad + (long long)b * Lk : nullptr;
+    stage_tile<T, DHP>(q + (long long)b * D.q_bs + h * dh, D.q_ld, Lq, dh, Qs, DHP);
+    stage_tile<T, DHP>(d_o + (long long)b * D.do_bs + h * dh, D.do_ld, Lq, dh, dOs, DHP);
+    stage_tile<T, DHP>(k + (long long)b * D.k_bs + h * dh, D.k_ld, Lk, dh, Ks, KS);
+    stage_tile<T, DHP>(v + (long long)b * D.v_bs + h * dh, D.v_ld, Lk, dh, Vs, KS);
+    __syncthreads();
 
-    for (int i = 0; i < Lq; ++i) {
+    const int R = (Lq + kWarps - 1) / kWarps;
+    const int r0 = warp * R, r1 = min(Lq, r0 + R);
+    if (r0 < r1) {
+        rows_dot_keys<DHP>(Qs, Ks, KS, Lk, LkP, r0, r1, lane, Ss);
+        rows_dot_keys<DHP>(dOs, Vs, KS, Lk, LkP, r0, r1, lane, dPs);
         __syncwarp();
-        if (lane < nv) {
-            float4 qv = ld4(q + (long long)b * D.q_bs + (long long)i * D.q_ld + h * dh + lane * 4);
-            qs[lane * 4 + 0] = qv.x; qs[lane * 4 + 1] = qv.y; qs[lane * 4 + 2] = qv.z; qs[lane * 4 + 3] = qv.w;
-            float4 gv = ld4(d_o + (long long)b * D.do_bs + (long long)i * D.do_ld + h * dh + lane * 4);
-            dos[lane * 4 + 0] = gv.x; dos[lane * 4 + 1] = gv.y; dos[lane * 4 + 2] = gv.z; dos[lane * 4 + 3] = gv.w;
-        }
-        __syncwarp();
-        float p[2];
-        row_softmax(qs, Ks, dh, Lk, i, lane, D.causal != 0, pad_row, D.scale, p[0], p[1]);
-        const long long pbase = ((long long)bh * Lq + i) * Lk;
-        float sc[2] = {1.f, 1.f}, dP[2] = {0.f, 0.f};
-        float dsum = 0.f;
+        const unsigned char* pad_row = key_pad ? key_pad + (long long)b * Lk : nullptr;
+        for (int i = r0; i < r1; ++i) {
+            float p[2];
+            softmax_row(Ss + i * LkP, Lk, i, lane, D.causal != 0, pad_row, D.scale, p[0], p[1]);
+            const long long pbase = ((long long)bh * Lq + i) * Lk;
+            float sc[2] = {1.f, 1.f}, dP[2] = {0.f, 0.f};
+            float dsum = 0.f;
 #pragma unroll
-        for (int t = 0; t < 2; ++t) {
-            const int j = lane + 32 * t;
-            if (j < Lk) {
-                if (rng.p > 0.f) sc[t] = dropout_scale1(rng, site, (unsigned long long)(pbase + j));
-                const float* vr = Vs + j * (dh + 1);
-                float a = 0.f;
-                for (int c = 0; c < dh; ++c) a += dos[c] * vr[c];
-                dP[t] = a * sc[t];
-                dsum += p[t] * dP[t];
+            for (int t = 0; t < 2; ++t) {
+                const int j = lane + 32 * t;
+                if (j < Lk) {
+                    if (rng.p > 0.f) sc[t] = dropout_scale1(rng, site, (unsigned long long)(pbase + j));
+                    dP[t] = dPs[i * LkP + j] * sc[t];
+                    dsum += p[t] * dP[t];
+                }
             }
-        }
-        dsum = warp_sum(dsum);
-        const float dS0 = p[0] * (dP[0] - dsum) * D.scale, dS1 = p[1] * (dP[1] - dsum) * D.scale;
-        const float pd0 = p[0] * sc[0], pd1 = p[1] * sc[1];
-        float qreg[4], doreg[4], dqacc[4] = {0.f, 0.f, 0.f, 0.f};
+            dsum = warp_sum(dsum);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = lane + 32 * cc;
-            qreg[cc] = c < dh ? qs[c] : 0.f;
-            doreg[cc] = c < dh ? dos[c] : 0.f;
-        }
-        for (int j = 0; j < Lk; ++j) {
-            const float dsj = __shfl_sync(0xffffffffu, j < 32 ? dS0 : dS1, j & 31);
-            const float pdj = __shfl_sync(0xffffffffu, j < 32 ? pd0 : pd1, j & 31);
-            const float* kr = Ks + j * (dh + 1);
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                const int c = lane + 32 * cc;
-                if (c < dh) {
-                    dqacc[cc] += dsj * kr[c];
-                    dKs[j * dh + c] += dsj * qreg[cc];
-                    dVs[j * dh + c] += pdj * doreg[cc];
+            for (int t = 0; t < 2; ++t) {
+                const int j = lane + 32 * t;
+                if (j < Lk) {
+                    dSt[j * LqP + i] = p[t] * (dP[t] - dsum) * D.scale;
+                    Pdt[j * LqP + i] = p[t] * sc[t];
                 }
             }
         }
-        T* dqrow = dq + (long long)b * D.dq_bs + (long long)i * D.dq_ld + h * dh;
+        __syncwarp();
+        // dQ[i][c] = sum_j dS[i][j] K[j][c]
+        for (int ib = r0; ib < r1; ib += RB) {
+            const int nrows = min(RB, r1 - ib);
+            float acc[RB][DHP / 32];
+            weighted_rows<DHP>(dSt, LqP, Ks, KS, Lk, ib, nrows, lane, acc);
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int c = lane + 32 * cc;
-            if (c < dh) dqrow[c] = from_f32<T>(dqacc[cc]);
+            for (int kk = 0; kk < RB; ++kk) {
+                if (kk < nrows) {
+                    T* row = dq + (long long)b * D.dq_bs + (long long)(ib + kk) * D.dq_ld + h * dh;
+#pragma unroll
+                    for (int cc = 0; cc < DHP / 32; ++cc) {
+                        const int c = lane + 32 * cc;
+                        if (c < dh) row[c] = from_f32<T>(acc[kk][cc]);
+                    }
+                }
+            }
         }
     }
-    __syncwarp();
-    for (int idx = lane; idx < Lk * nv; idx += 32) {
-        const int j = idx / nv, c = (idx % nv) * 4;
-        const float* a = dKs + j * dh + c;
-        const float* g = dVs + j * dh + c;
-        st4(dk + (long long)b * D.dk_bs + (long long)j * D.dk_ld + h * dh + c, make_float4(a[0], a[1], a[2], a[3]));
-        st4(dv + (long long)b * D.dv_bs + (long long)j * D.dv_ld + h * dh + c, make_float4(g[0], g[1], g[2], g[3]));
+    __syncthreads();
+    // keys split over the warps: dK[j][c] = sum_i dS[i][j] Q[i][c],  dV[j][c] = sum_i Pd[i][j] dO[i][c]
+    const int KR = (Lk + kWarps - 1) / kWarps;
+    const int j0 = warp * KR, j1 = min(Lk, j0 + KR);
+    for (int jb = j0; jb < j1; jb += RB) {
+        const int nk = min(RB, j1 - jb);
+        float ak[RB][DHP / 32], av[RB][DHP / 32];
+#pragma unroll
+        for (int kk = 0; kk < RB; ++kk)
+#pragma unroll
+            for (int cc = 0; cc < DHP / 32; ++cc) ak[kk][cc] = av[kk][cc] = 0.f;
+        for (int i = 0; i < Lq; ++i) {
+            float ws[RB], wp[RB];
+#pragma unroll
+            for (int kk = 0; kk < RB; ++kk) {
+                ws[kk] = kk < nk ? dSt[(jb + kk) * LqP + i] : 0.f;
+                wp[kk] = kk < nk ? Pdt[(jb + kk) * LqP + i] : 0.f;
+            }
+#pragma unroll
+            for (int cc = 0; cc < DHP / 32; ++cc) {
+                const float qv = Qs[i * DHP + lane + 32 * cc], gv = dOs[i * DHP + lane + 32 * cc];
+#pragma unroll
+                for (int kk = 0; kk < RB; ++kk) {
+                    ak[kk][cc] = fmaf(ws[kk], qv, ak[kk][cc]);
+                    av[kk][cc] = fmaf(wp[kk], gv, av[kk][cc]);
+                }
+            }
+        }
+#pragma unroll
+        for (int kk = 0; kk < RB; ++kk) {
+            if (kk < nk) {
+                T* krow = dk + (long long)b * D.dk_bs + (long long)(jb + kk) * D.dk_ld + h * dh;
+                T* vrow = dv + (long long)b * D.dv_bs + (long long)(jb + kk) * D.dv_ld + h * dh;
+#pragma unroll
+                for (int cc = 0; cc < DHP / 32; ++cc) {
+                    const int c = lane + 32 * cc;
+                    if (c < dh) { krow[c] = from_f32<T>(ak[kk][cc]); vrow[c] = from_f32<T>(av[kk][cc]); }
+                }
+            }
+        }
     }
 }
 
@@ -236,34 +320,48 @@ Dims make_dims(const vct_attn_args* a) {
     return D;
 }
 
+template <typename T, int DHP>
+int launch_fwd(const vct_attn_args* a, cudaStream_t st) {
+    const int LkP = (a->Lk + 3) & ~3, LqP = (a->Lq + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)a->Lq * DHP + 2 * (size_t)a->Lk * (DHP + 1) + (size_t)a->Lq * LkP + (size_t)a->Lk * LqP);
+    VCT_REQUIRE(smem <= kSmemBudget, "vct_attn_fwd: head does not fit shared memory");
+    auto kern = attn_fwd_kernel<T, DHP>;
+    static bool once = false;
+    if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
+    kern<<<a->B * a->H, kThreads, smem, st>>>((const T*)a->q, (const T*)a->k, (const T*)a->v, (T*)a->o, a->key_pad, a->probs,
+                                              make_dims(a), a->drop_p, a->rng_state, a->site);
+    return check_launch("vct_attn_fwd");
+}
+
+template <typename T, int DHP>
+int launch_bwd(const vct_attn_args* a, cudaStream_t st) {
+    const int LkP = (a->Lk + 3) & ~3, LqP = (a->Lq + 3) & ~3;
+    const size_t smem = sizeof(float) * (2 * (size_t)a->Lq * DHP + 2 * (size_t)a->Lk * (DHP + 1) + 2 * (size_t)a->Lq * LkP + 2 * (size_t)a->Lk * LqP);
+    VCT_REQUIRE(smem <= kSmemBudget, "vct_attn_bwd: head does not fit shared memory");
+    auto kern = attn_bwd_kernel<T, DHP>;
+    static bool once = false;
+    if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
+    kern<<<a->B * a->H, kThreads, smem, st>>>((const T*)a->q, (const T*)a->k, (const T*)a->v, (const T*)a->d_o, (T*)a->dq,
+                                              (T*)a->dk, (T*)a->dv, a->key_pad, make_dims(a), a->drop_p, a->rng_state, a->site);
+    return check_launch("vct_attn_bwd");
+}
+
+template <typename T>
+int dispatch(const vct_attn_args* a, cudaStream_t st, bool bwd) {
+    const int dh = a->dh;
+    if (dh <= 32) return bwd ? launch_bwd<T, 32>(a, st) : launch_fwd<T, 32>(a, st);
+    if (dh <= 64) return bwd ? launch_bwd<T, 64>(a, st) : launch_fwd<T, 64>(a, st);
+    if (dh <= 96) return bwd ? launch_bwd<T, 96>(a, st) : launch_fwd<T, 96>(a, st);
+    return bwd ? launch_bwd<T, 128>(a, st) : launch_fwd<T, 128>(a, st);
+}
+
 }  // namespace
 
 extern "C" int vct_attn_fwd(const vct_attn_args* a, vct_stream_t stream) {
     if (int e = validate(a, "vct_attn_fwd")) return e;
     VCT_REQUIRE(a->q && a->k && a->v && a->o, "vct_attn_fwd: null tensor");
-    const int per_warp = a->Lk * (a->dh + 1) + a->Lk * a->dh + a->dh;
-    int warps = (int)(kSmemBudget / ((size_t)per_warp * sizeof(float)));
-    warps = warps > kMaxWarps ? kMaxWarps : warps;
-    VCT_REQUIRE(warps >= 1, "vct_attn_fwd: head does not fit shared memory");
-    const size_t smem = (size_t)warps * per_warp * sizeof(float);
-    const int blocks = (a->B * a->H + warps - 1) / warps;
-    const Dims D = make_dims(a);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (a->dtype == VCT_BF16) {
-        auto kern = attn_fwd_kernel<__nv_bfloat16>;
-        static bool once = false;
-        if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
-        kern<<<blocks, warps * 32, smem, st>>>((const __nv_bfloat16*)a->q, (const __nv_bfloat16*)a->k,
-                                               (const __nv_bfloat16*)a->v, (__nv_bfloat16*)a->o, a->key_pad, a->probs, D,
-                                               a->drop_p, a->rng_state, a->site, per_warp);
-    } else {
-        auto kern = attn_fwd_kernel<float>;
-        static bool once = false;
-        if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
-        kern<<<blocks, warps * 32, smem, st>>>((const float*)a->q, (const float*)a->k, (const float*)a->v, (float*)a->o,
-                                               a->key_pad, a->probs, D, a->drop_p, a->rng_state, a->site, per_warp);
-    }
-    return check_launch("vct_attn_fwd");
+    if (a->dtype == VCT_BF16) return dispatch<__nv_bfloat16>(a, (cudaStream_t)stream, false);
+    return dispatch<float>(a, (cudaStream_t)stream, false);
 }
 
 extern "C" int vct_attn_bwd(const vct_attn_args* a, vct_stream_t stream) {
@@ -271,29 +369,6 @@ extern "C" int vct_attn_bwd(const vct_attn_args* a, vct_stream_t stream) {
     VCT_REQUIRE(a->q && a->k && a->v && a->d_o && a->dq && a->dk && a->dv, "vct_attn_bwd: null tensor");
     VCT_REQUIRE(a->do_ld % 4 == 0 && a->dq_ld % 4 == 0 && a->dk_ld % 4 == 0 && a->dv_ld % 4 == 0,
                 "vct_attn_bwd: gradient row strides must be multiples of 4 elements");
-    const int per_warp = 2 * a->Lk * (a->dh + 1) + 2 * a->Lk * a->dh + 2 * a->dh;
-    int warps = (int)(kSmemBudget / ((size_t)per_warp * sizeof(float)));
-    warps = warps > kMaxWarps ? kMaxWarps : warps;
-    VCT_REQUIRE(warps >= 1, "vct_attn_bwd: head does not fit shared memory");
-    const size_t smem = (size_t)warps * per_warp * sizeof(float);
-    const int blocks = (a->B * a->H + warps - 1) / warps;
-    const Dims D = make_dims(a);
-    cudaStream_t st = (cudaStream_t)stream;
-    if (a->dtype == VCT_BF16) {
-        auto kern = attn_bwd_kernel<__nv_bfloat16>;
-        static bool once = false;
-        if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
-        kern<<<blocks, warps * 32, smem, st>>>((const __nv_bfloat16*)a->q, (const __nv_bfloat16*)a->k,
-                                               (const __nv_bfloat16*)a->v, (const __nv_bfloat16*)a->d_o,
-                                               (__nv_bfloat16*)a->dq, (__nv_bfloat16*)a->dk, (__nv_bfloat16*)a->dv,
-                                               a->key_pad, D, a->drop_p, a->rng_state, a->site, per_warp);
-    } else {
-        auto kern = attn_bwd_kernel<float>;
-        static bool once = false;
-        if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
-        kern<<<blocks, warps * 32, smem, st>>>((const float*)a->q, (const float*)a->k, (const float*)a->v,
-                                               (const float*)a->d_o, (float*)a->dq, (float*)a->dk, (float*)a->dv,
-                                               a->key_pad, D, a->drop_p, a->rng_state, a->site, per_warp);
-    }
-    return check_launch("vct_attn_bwd");
+    if (a->dtype == VCT_BF16) return dispatch<__nv_bfloat16>(a, (cudaStream_t)stream, true);
+    return dispatch<float>(a, (cudaStream_t)stream, true);
 }

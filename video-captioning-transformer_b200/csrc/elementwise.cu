@@ -190,11 +190,13 @@ extern "C" int vct_ln_residual_fwd(const float* x, const float* r, const float* 
 
 // ------------------------------------------------------------------------------------------------
 // residual + dropout + LayerNorm backward
+//   kernel 1: one warp per row (grid ~ 1-2 CTAs per SM), per-CTA column partials [3][d] -> workspace
+//   kernel 2: deterministic reduction of the partials over CTAs -> dgamma, dbeta, dbias
 // ------------------------------------------------------------------------------------------------
 static inline int ln_bwd_rows_per_cta(int R) {
-    int rows = (R + kNumSMs - 1) / kNumSMs;
+    int rows = (R + 2 * kNumSMs - 1) / (2 * kNumSMs);
     rows = ((rows + kLnWarps - 1) / kLnWarps) * kLnWarps;
-    return rows < 4 * kLnWarps ? 4 * kLnWarps : rows;
+    return rows < kLnWarps ? kLnWarps : rows;
 }
 static inline int ln_bwd_blocks(int R) {
     const int rows = ln_bwd_rows_per_cta(R);
@@ -207,11 +209,9 @@ template <int NV, typename TC>
 __global__ void __launch_bounds__(kLnWarps * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ ds,
-              TC* __restrict__ dr_c, float* __restrict__ dgamma, float* __restrict__ dbeta,
-              float* __restrict__ dbias_r, float* __restrict__ partials, unsigned int* counter, int R, int d,
-              int rows_per_cta, float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site) {
+              TC* __restrict__ dr_c, float* __restrict__ partials, int R, int d, int rows_per_cta, float drop_p,
+              const unsigned long long* __restrict__ rng_state, unsigned int site) {
     extern __shared__ float sm[];  // [3][d]
-    __shared__ bool is_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = d >> 2;
     const Rng rng = make_rng(rng_state, drop_p);
@@ -282,45 +282,49 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const f
     }
     float* mine = partials + (long long)blockIdx.x * 3 * d;
     for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) mine[i] = sm[i];
-    __threadfence();
+}
+
+// out[col] = sum_b partials[b][col]; 32 columns x 8 block-groups per CTA, fixed summation order
+__global__ void __launch_bounds__(256)
+ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, float* __restrict__ dbias_r) {
+    __shared__ float red[8][33];
+    const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
+    const int col = blockIdx.x * 32 + cx;
+    float a = 0.f;
+    if (col < 3 * d)
+        for (int b = gy; b < nblocks; b += 8) a += partials[(long long)b * 3 * d + col];
+    red[gy][cx] = a;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned int prev = atomicAdd(counter, 1u);
-        is_last = (prev == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (is_last) {
-        __threadfence();
-        for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
-            float a = 0.f;
-            for (unsigned int b = 0; b < gridDim.x; ++b) a += __ldcg(partials + (long long)b * 3 * d + i);
-            if (i < d) { if (dgamma) dgamma[i] = a; }
-            else if (i < 2 * d) { if (dbeta) dbeta[i - d] = a; }
-            else { if (dbias_r) dbias_r[i - 2 * d] = a; }
-        }
-        if (threadIdx.x == 0) *counter = 0u;
+    if (gy == 0 && col < 3 * d) {
+        float t = 0.f;
+#pragma unroll
+        for (int g = 0; g < 8; ++g) t += red[g][cx];
+        if (col < d) { if (dgamma) dgamma[col] = t; }
+        else if (col < 2 * d) { if (dbeta) dbeta[col - d] = t; }
+        else { if (dbias_r) dbias_r[col - 2 * d] = t; }
     }
 }
 
 template <typename TC>
 static int launch_ln_bwd(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
-                         float* ds, TC* dr_c, float* dgamma, float* dbeta, float* dbias_r, float* partials,
-                         unsigned int* counter, int R, int d, float drop_p, const unsigned long long* rng_state,
-                         unsigned int site, cudaStream_t st) {
+                         float* ds, TC* dr_c, float* dgamma, float* dbeta, float* dbias_r, float* partials, int R, int d,
+                         float drop_p, const unsigned long long* rng_state, unsigned int site, cudaStream_t st) {
     const int rows = ln_bwd_rows_per_cta(R), blocks = ln_bwd_blocks(R);
     const int nvl = (d / 4 + 31) / 32;
     const size_t smem = (size_t)3 * d * sizeof(float);
-#define LN_BWD_CASE(NVV)                                                                                          \
-    ln_bwd_kernel<NVV, TC><<<blocks, kLnWarps * 32, smem, st>>>(dy, s, mean, rstd, gamma, ds, dr_c, dgamma, dbeta, \
-                                                                 dbias_r, partials, counter, R, d, rows, drop_p,  \
-                                                                 rng_state, site)
+#define LN_BWD_CASE(NVV)                                                                                        \
+    ln_bwd_kernel<NVV, TC><<<blocks, kLnWarps * 32, smem, st>>>(dy, s, mean, rstd, gamma, ds, dr_c, partials, R, d, rows, \
+                                                                 drop_p, rng_state, site)
     if (nvl <= 1) LN_BWD_CASE(1);
     else if (nvl <= 2) LN_BWD_CASE(2);
     else if (nvl <= 4) LN_BWD_CASE(4);
     else if (nvl <= 6) LN_BWD_CASE(6);
     else LN_BWD_CASE(8);
 #undef LN_BWD_CASE
-    return check_launch("vct_ln_residual_bwd");
+    if (int e = check_launch("vct_ln_residual_bwd")) return e;
+    ln_bwd_reduce_kernel<<<(3 * d + 31) / 32, 256, 0, st>>>(partials, blocks, d, dgamma, dbeta, dbias_r);
+    return check_launch("vct_ln_residual_bwd(reduce)");
 }
 
 extern "C" int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
@@ -328,13 +332,14 @@ extern "C" int vct_ln_residual_bwd(const float* dy, const float* s, const float*
                                    float* dbeta, float* dbias_r, float* partials, unsigned int* counter, int R, int d,
                                    float drop_p, const unsigned long long* rng_state, unsigned int site,
                                    vct_stream_t stream) {
+    (void)counter;   // kept in the ABI; the two-kernel reduction needs no counter
     VCT_REQUIRE(d % 4 == 0 && d <= 1024 && R > 0, "vct_ln_residual_bwd: need d %% 4 == 0, d <= 1024 (d=%d)", d);
-    VCT_REQUIRE(dy && s && mean && rstd && gamma && partials && counter, "vct_ln_residual_bwd: null input");
+    VCT_REQUIRE(dy && s && mean && rstd && gamma && partials, "vct_ln_residual_bwd: null input");
     if (dr_dtype == VCT_BF16)
         return launch_ln_bwd<__nv_bfloat16>(dy, s, mean, rstd, gamma, ds, (__nv_bfloat16*)dr_c, dgamma, dbeta, dbias_r,
-                                            partials, counter, R, d, drop_p, rng_state, site, (cudaStream_t)stream);
-    return launch_ln_bwd<float>(dy, s, mean, rstd, gamma, ds, (float*)dr_c, dgamma, dbeta, dbias_r, partials, counter,
-                                R, d, drop_p, rng_state, site, (cudaStream_t)stream);
+                                            partials, R, d, drop_p, rng_state, site, (cudaStream_t)stream);
+    return launch_ln_bwd<float>(dy, s, mean, rstd, gamma, ds, (float*)dr_c, dgamma, dbeta, dbias_r, partials, R, d, drop_p,
+                                rng_state, site, (cudaStream_t)stream);
 }
 
 // ------------------------------------------------------------------------------------------------

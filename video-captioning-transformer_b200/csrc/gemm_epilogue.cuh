@@ -1,5 +1,7 @@
 // Fused GEMM epilogue shared by the SIMT and the tcgen05 kernels.
 // Order: + bias[n]; + row_table[m % period, n]; activation; + addend[m, n]; store C (and C2).
+// The activation kind is a template parameter so that the plain epilogue (most launches) carries neither the
+// Philox nor the erf code: instruction-cache footprint matters for the many ~5 us GEMMs of a step.
 #pragma once
 #include "common.cuh"
 
@@ -15,6 +17,7 @@ struct Epilogue {
     int act;
     const void* aux; int aux_dtype; long long ld_aux;
     float drop_p; const unsigned long long* rng_state; unsigned int site;
+    int vec_ok;   // leading dimensions / pointers allow 16-byte loads and stores for full groups of 4 columns
 };
 
 inline Epilogue make_epilogue(const vct_gemm_args* a) {
@@ -28,72 +31,89 @@ inline Epilogue make_epilogue(const vct_gemm_args* a) {
     e.act = a->act;
     e.aux = a->aux; e.aux_dtype = a->aux_dtype; e.ld_aux = a->ld_aux;
     e.drop_p = a->drop_p; e.rng_state = a->rng_state; e.site = a->site;
+    auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    e.vec_ok = (a->ldc % 4 == 0) && (a->C2 == nullptr || a->ldc2 % 4 == 0) &&
+               (a->addend == nullptr || (a->ld_addend % 4 == 0 && al16(a->addend))) &&
+               (a->aux == nullptr || (a->ld_aux % 4 == 0 && al16(a->aux))) && (a->bias == nullptr || al16(a->bias)) &&
+               (a->row_table == nullptr || (al16(a->row_table) && a->N % 4 == 0)) &&
+               (a->act == VCT_ACT_NONE || a->N % 4 == 0);
     return e;
 }
 
-__device__ __forceinline__ void store_vals(void* base, int dtype, long long off, const float* v, int cnt, bool vec) {
-    if (dtype == VCT_BF16) {
-        __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(base) + off;
-        if (vec) st4(p, make_float4(v[0], v[1], v[2], v[3]));
-        else for (int q = 0; q < cnt; ++q) p[q] = __float2bfloat16_rn(v[q]);
-    } else {
-        float* p = reinterpret_cast<float*>(base) + off;
-        if (vec) st4(p, make_float4(v[0], v[1], v[2], v[3]));
-        else for (int q = 0; q < cnt; ++q) p[q] = v[q];
+__device__ __forceinline__ void store4(void* base, int dtype, long long off, float4 v) {
+    if (dtype == VCT_BF16) st4(reinterpret_cast<__nv_bfloat16*>(base) + off, v);
+    else st4(reinterpret_cast<float*>(base) + off, v);
+}
+__device__ __forceinline__ void store1(void* base, int dtype, long long off, float v) {
+    if (dtype == VCT_BF16) reinterpret_cast<__nv_bfloat16*>(base)[off] = __float2bfloat16_rn(v);
+    else reinterpret_cast<float*>(base)[off] = v;
+}
+__device__ __forceinline__ float load1(const void* base, int dtype, long long off) {
+    return dtype == VCT_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(base)[off])
+                             : reinterpret_cast<const float*>(base)[off];
+}
+
+// slow path: ragged N or unaligned strides; one element at a time
+template <int ACT>
+__device__ __noinline__ void epilogue_scalar(const Epilogue& e, const Rng& rng, int m, int n, float4 acc) {
+    const float v4[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll 1
+    for (int q = 0; q < 4; ++q) {
+        const int nn = n + q;
+        if (nn >= e.N) break;
+        float v = v4[q];
+        if (e.bias) v += e.bias[nn];
+        if (e.row_table) v += e.row_table[(long long)(m % e.row_period) * e.N + nn];
+        float sc = 1.f;
+        if (ACT != VCT_ACT_NONE) sc = dropout_scale1(rng, e.site, (unsigned long long)m * (unsigned long long)e.N + nn);
+        if (ACT == VCT_ACT_GELU_FWD) {
+            store1(e.C, e.c_dtype, (long long)m * e.ldc + nn, v);
+            if (e.C2) store1(e.C2, e.c2_dtype, (long long)m * e.ldc2 + nn, gelu_f(v) * sc);
+            continue;
+        }
+        if (ACT == VCT_ACT_GELU_BWD) v *= dgelu_f(load1(e.aux, e.aux_dtype, (long long)m * e.ld_aux + nn)) * sc;
+        if (e.addend) v += e.addend[(long long)m * e.ld_addend + nn];
+        store1(e.C, e.c_dtype, (long long)m * e.ldc + nn, v);
+        if (e.C2) store1(e.C2, e.c2_dtype, (long long)m * e.ldc2 + nn, v);
     }
 }
 
-// v[0..3] = accumulators of row m, columns n..n+3 (n % 4 == 0).  Columns >= N are dropped.
-__device__ __forceinline__ void epilogue_store4(const Epilogue& e, const Rng& rng, int m, int n, float* v) {
+// acc = accumulators of row m, columns n..n+3 (n % 4 == 0).  Rows >= M / columns >= N are dropped.
+template <int ACT>
+__device__ __forceinline__ void epilogue_store4(const Epilogue& e, const Rng& rng, int m, int n, float4 acc) {
     if (m >= e.M || n >= e.N) return;
-    const int cnt = e.N - n < 4 ? e.N - n : 4;
+    if (!e.vec_ok || n + 4 > e.N) { epilogue_scalar<ACT>(e, rng, m, n, acc); return; }
     if (e.bias) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (q < cnt) v[q] += e.bias[n + q];
+        const float4 b = ld4(e.bias + n);
+        acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
     }
     if (e.row_table) {
-        const float* t = e.row_table + (long long)(m % e.row_period) * e.N + n;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (q < cnt) v[q] += t[q];
+        const float4 t = ld4(e.row_table + (long long)(m % e.row_period) * e.N + n);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    float sc[4] = {1.f, 1.f, 1.f, 1.f};
-    if (e.act != VCT_ACT_NONE && rng.p > 0.f) {
-        const unsigned long long idx = (unsigned long long)m * (unsigned long long)e.N + (unsigned long long)n;
-        if ((idx & 3ull) == 0ull) {
-            float4 s4 = dropout_scale4(rng, e.site, idx >> 2);
-            sc[0] = s4.x; sc[1] = s4.y; sc[2] = s4.z; sc[3] = s4.w;
-        } else {
-#pragma unroll
-            for (int q = 0; q < 4; ++q) sc[q] = dropout_scale1(rng, e.site, idx + q);
+    if (ACT != VCT_ACT_NONE) {
+        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
+        if (rng.p > 0.f)    // vec_ok implies N % 4 == 0 for activation epilogues, so (m * N + n) / 4 is exact
+            sc = dropout_scale4(rng, e.site, ((unsigned long long)m * (unsigned long long)e.N + (unsigned long long)n) >> 2);
+        if (ACT == VCT_ACT_GELU_FWD) {
+            store4(e.C, e.c_dtype, (long long)m * e.ldc + n, acc);
+            if (e.C2)
+                store4(e.C2, e.c2_dtype, (long long)m * e.ldc2 + n,
+                       make_float4(gelu_f(acc.x) * sc.x, gelu_f(acc.y) * sc.y, gelu_f(acc.z) * sc.z, gelu_f(acc.w) * sc.w));
+            return;
         }
-    }
-    if (e.act == VCT_ACT_GELU_FWD) {
-        const bool vec1 = cnt == 4 && (e.ldc & 3) == 0;
-        store_vals(e.C, e.c_dtype, (long long)m * e.ldc + n, v, cnt, vec1);
-        float h[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) h[q] = gelu_f(v[q]) * sc[q];
-        if (e.C2) store_vals(e.C2, e.c2_dtype, (long long)m * e.ldc2 + n, h, cnt, cnt == 4 && (e.ldc2 & 3) == 0);
-        return;
-    }
-    if (e.act == VCT_ACT_GELU_BWD) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (q < cnt) {
-                const long long o = (long long)m * e.ld_aux + n + q;
-                const float z = e.aux_dtype == VCT_BF16 ? __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(e.aux)[o])
-                                                        : reinterpret_cast<const float*>(e.aux)[o];
-                v[q] *= dgelu_f(z) * sc[q];
-            }
-        }
+        const long long ao = (long long)m * e.ld_aux + n;
+        const float4 z = e.aux_dtype == VCT_BF16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(e.aux) + ao)
+                                                 : ld4(reinterpret_cast<const float*>(e.aux) + ao);
+        acc.x *= dgelu_f(z.x) * sc.x; acc.y *= dgelu_f(z.y) * sc.y;
+        acc.z *= dgelu_f(z.z) * sc.z; acc.w *= dgelu_f(z.w) * sc.w;
     }
     if (e.addend) {
-        const float* ad = e.addend + (long long)m * e.ld_addend + n;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) if (q < cnt) v[q] += ad[q];
+        const float4 ad = ld4(e.addend + (long long)m * e.ld_addend + n);
+        acc.x += ad.x; acc.y += ad.y; acc.z += ad.z; acc.w += ad.w;
     }
-    store_vals(e.C, e.c_dtype, (long long)m * e.ldc + n, v, cnt, cnt == 4 && (e.ldc & 3) == 0);
-    if (e.C2) store_vals(e.C2, e.c2_dtype, (long long)m * e.ldc2 + n, v, cnt, cnt == 4 && (e.ldc2 & 3) == 0);
+    store4(e.C, e.c_dtype, (long long)m * e.ldc + n, acc);
+    if (e.C2) store4(e.C2, e.c2_dtype, (long long)m * e.ldc2 + n, acc);
 }
 
 }  // namespace vct

@@ -57,7 +57,7 @@ __device__ __forceinline__ void stash_tile(float (*S)[BM + PAD], const float* re
     }
 }
 
-template <typename T, bool A_TRANS, bool B_TRANS>
+template <typename T, bool A_TRANS, bool B_TRANS, int ACT>
 __global__ void __launch_bounds__(THREADS)
 gemm_simt_kernel(const T* __restrict__ A, long long lda, const T* __restrict__ B, long long ldb, int M, int N, int K,
                  bool a_vec, bool b_vec, Epilogue epi) {
@@ -97,15 +97,14 @@ gemm_simt_kernel(const T* __restrict__ A, long long lda, const T* __restrict__ B
         }
         __syncthreads();
     }
-    const Rng rng = make_rng(epi.rng_state, epi.act != VCT_ACT_NONE ? epi.drop_p : 0.f);
+    const Rng rng = make_rng(epi.rng_state, ACT != VCT_ACT_NONE ? epi.drop_p : 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + ty * 8 + i;
 #pragma unroll
-        for (int jg = 0; jg < 2; ++jg) {
-            float v[4] = {acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]};
-            epilogue_store4(epi, rng, m, n0 + tx * 8 + jg * 4, v);
-        }
+        for (int jg = 0; jg < 2; ++jg)
+            epilogue_store4<ACT>(epi, rng, m, n0 + tx * 8 + jg * 4,
+                                 make_float4(acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]));
     }
 }
 
@@ -119,11 +118,16 @@ int launch(const vct_gemm_args* a, cudaStream_t st) {
     const bool b_vec = (a->ldb % vecel == 0) && ((reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
     const T* A = (const T*)a->A;
     const T* B = (const T*)a->B;
-#define GO(AT, BT) gemm_simt_kernel<T, AT, BT><<<grid, THREADS, 0, st>>>(A, a->lda, B, a->ldb, a->M, a->N, a->K, a_vec, b_vec, epi)
-    if (!a->a_trans && !a->b_trans) GO(false, false);
-    else if (!a->a_trans && a->b_trans) GO(false, true);
-    else if (a->a_trans && !a->b_trans) GO(true, false);
-    else GO(true, true);
+#define GO(AT, BT, ACT) gemm_simt_kernel<T, AT, BT, ACT><<<grid, THREADS, 0, st>>>(A, a->lda, B, a->ldb, a->M, a->N, a->K, a_vec, b_vec, epi)
+#define GO_ACT(AT, BT)                                      \
+    if (a->act == VCT_ACT_GELU_FWD) GO(AT, BT, VCT_ACT_GELU_FWD);   \
+    else if (a->act == VCT_ACT_GELU_BWD) GO(AT, BT, VCT_ACT_GELU_BWD); \
+    else GO(AT, BT, VCT_ACT_NONE)
+    if (!a->a_trans && !a->b_trans) { GO_ACT(false, false); }
+    else if (!a->a_trans && a->b_trans) { GO_ACT(false, true); }
+    else if (a->a_trans && !a->b_trans) { GO(true, false, VCT_ACT_NONE); }
+    else { GO(true, true, VCT_ACT_NONE); }
+#undef GO_ACT
 #undef GO
     return check_launch("vct_gemm(simt)");
 }
@@ -150,6 +154,7 @@ extern "C" int vct_gemm(const vct_gemm_args* a, vct_stream_t stream) {
     VCT_REQUIRE((reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (a->C2 == nullptr || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0),
                 "vct_gemm: outputs must be 16-byte aligned");
     VCT_REQUIRE(a->act != VCT_ACT_GELU_BWD || a->aux != nullptr, "vct_gemm: GELU_BWD needs aux (the pre-activation)");
+    VCT_REQUIRE(a->act == VCT_ACT_NONE || !a->a_trans, "vct_gemm: activation epilogues are built for a_trans = 0 only");
     VCT_REQUIRE(a->row_table == nullptr || a->row_period > 0, "vct_gemm: row_table needs row_period > 0");
     VCT_REQUIRE(a->addend == nullptr || a->ld_addend >= a->N, "vct_gemm: ld_addend too small");
     if (a->impl == VCT_GEMM_TCGEN05) return vct::gemm_tcgen05(a, (cudaStream_t)stream);

@@ -74,7 +74,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
            ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES>
+template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, Epilogue epi) {
     constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
@@ -168,30 +168,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int m = m0 + q * 32 + lane;
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const Rng rng = make_rng(epi.rng_state, epi.act != VCT_ACT_NONE ? epi.drop_p : 0.f);
+        const Rng rng = make_rng(epi.rng_state, ACT != VCT_ACT_NONE ? epi.drop_p : 0.f);
+        // 16 accumulator columns per TMEM load, 4 column groups per iteration: keeps the epilogue code small
+        // (instruction-cache footprint dominates the many ~5 us GEMMs of a step)
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 32; ++c) {
-            uint32_t r[32];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
+        for (int c = 0; c < BLOCK_N / 16; ++c) {
+            uint32_t r[16];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
             asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-                  "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-                  "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int nb = n0 + c * 32;
+            const int nb = n0 + c * 16;
             if (m < epi.M && nb < epi.N) {
 #pragma unroll
-                for (int g = 0; g < 8; ++g) {
-                    float v[4] = {__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                  __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])};
-                    epilogue_store4(epi, rng, m, nb + g * 4, v);
-                }
+                for (int g = 0; g < 4; ++g)
+                    epilogue_store4<ACT>(epi, rng, m, nb + g * 4,
+                                         make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
+                                                     __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])));
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -266,12 +264,12 @@ int get_map(const void* ptr, long long inner, long long outer, long long ld, int
     return 0;
 }
 
-template <int BLOCK_N, bool A_MN, bool B_MN>
+template <int BLOCK_N, bool A_MN, bool B_MN, int ACT>
 int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
     constexpr int kStage = kABytes + BLOCK_N * BLOCK_K * 2;
     constexpr int STAGES = kSmemBudget / kStage > 8 ? 8 : kSmemBudget / kStage;
     constexpr int smem = STAGES * kStage + 1024;
-    auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, STAGES>;
+    auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, STAGES, ACT>;
     static bool once = false;
     if (!once) {
         VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -284,10 +282,21 @@ int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tm
 
 template <int BLOCK_N>
 int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
-    if (!a->a_trans && !a->b_trans) return launch<BLOCK_N, false, false>(a, tmA, tmB, st);
-    if (!a->a_trans && a->b_trans) return launch<BLOCK_N, false, true>(a, tmA, tmB, st);
-    if (a->a_trans && !a->b_trans) return launch<BLOCK_N, true, false>(a, tmA, tmB, st);
-    return launch<BLOCK_N, true, true>(a, tmA, tmB, st);
+    // activation epilogues exist where the path uses them: GELU forward on x W1^T (K-major, K-major) and GELU
+    // backward on dY W2 (K-major, MN-major); everything else carries the small plain epilogue
+    if (a->act == VCT_ACT_GELU_FWD) {
+        VCT_REQUIRE(!a->a_trans && !a->b_trans, "vct_gemm(tcgen05): GELU_FWD is built for a_trans = b_trans = 0");
+        return launch<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, st);
+    }
+    if (a->act == VCT_ACT_GELU_BWD) {
+        VCT_REQUIRE(!a->a_trans, "vct_gemm(tcgen05): GELU_BWD is built for a_trans = 0");
+        if (a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_GELU_BWD>(a, tmA, tmB, st);
+        return launch<BLOCK_N, false, false, VCT_ACT_GELU_BWD>(a, tmA, tmB, st);
+    }
+    if (!a->a_trans && !a->b_trans) return launch<BLOCK_N, false, false, VCT_ACT_NONE>(a, tmA, tmB, st);
+    if (!a->a_trans && a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_NONE>(a, tmA, tmB, st);
+    if (a->a_trans && !a->b_trans) return launch<BLOCK_N, true, false, VCT_ACT_NONE>(a, tmA, tmB, st);
+    return launch<BLOCK_N, true, true, VCT_ACT_NONE>(a, tmA, tmB, st);
 }
 
 }  // namespace

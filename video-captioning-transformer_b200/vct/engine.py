@@ -36,20 +36,57 @@ def _dec_site(layer: int, k: int) -> int: return 1000 + 16 * layer + k     # 0 s
 
 
 class Plan:
-    """A pre-built sequence of C-ABI calls; ``run(stream)`` issues them in order."""
+    """A pre-built sequence of C-ABI calls.  ``run`` issues them in order on the main stream; calls added
+    with ``lane=1`` (weight-gradient GEMMs and bias column sums, which nothing on the critical path of
+    backward consumes) go to a side stream that forks from / joins the main stream through events, so that
+    under CUDA-graph capture they become parallel branches of the graph."""
 
     def __init__(self):
         self.calls: List[Tuple] = []
         self.keep: List = []      # keeps ctypes structs / tensors alive
+        self.lane = 0             # lane given to calls added while it is set (see CaptionEngine._side)
+        self._events: List = []
 
     def add(self, name: str, fn, *args):
-        self.calls.append((name, fn, args))
+        self.calls.append((name, fn, args, self.lane))
 
-    def run(self, stream: int) -> int:
-        for name, fn, args in self.calls:
-            rc = fn(*args, stream)
+    def run(self, main, side=None) -> int:
+        """main / side: torch.cuda.Stream objects (side may be None: everything runs on main)."""
+        mp = main.cuda_stream
+        if side is None or not any(c[3] for c in self.calls):
+            for name, fn, args, _ in self.calls:
+                rc = fn(*args, mp)
+                if rc != 0:
+                    L.check(rc, name)
+            return len(self.calls)
+        sp = side.cuda_stream
+        ev_i, main_dirty, side_used = 0, True, False
+
+        def event():
+            nonlocal ev_i
+            if ev_i == len(self._events):
+                self._events.append(torch.cuda.Event())
+            ev_i += 1
+            return self._events[ev_i - 1]
+
+        for name, fn, args, lane in self.calls:
+            if lane == 0:
+                rc = fn(*args, mp)
+                main_dirty = True
+            else:
+                if main_dirty:                    # side work may read anything main has produced so far
+                    e = event()
+                    e.record(main)
+                    side.wait_event(e)
+                    main_dirty = False
+                rc = fn(*args, sp)
+                side_used = True
             if rc != 0:
                 L.check(rc, name)
+        if side_used:
+            e = event()
+            e.record(side)
+            main.wait_event(e)
         return len(self.calls)
 
     def __len__(self):
@@ -93,6 +130,7 @@ class CaptionEngine:
         self.hyper = torch.zeros(8, dtype=torch.float32, device=device)
         self.counters = torch.zeros(1024, dtype=torch.int32, device=device)
         self.upstream = torch.ones(1, dtype=torch.float32, device=device)
+        self.side_stream = torch.cuda.Stream(device=device) if os.environ.get("VCT_SIDE_STREAM", "1") != "0" else None
         self._tempo: Dict[int, torch.Tensor] = {}
         self._ws: Dict[Tuple, SimpleNamespace] = {}
         self._shadow_version = None
@@ -136,6 +174,22 @@ class CaptionEngine:
     def _stream(self) -> int:
         return torch.cuda.current_stream(self.device).cuda_stream
 
+    class _Side:
+        def __init__(self, plan): self.plan = plan
+        def __enter__(self): self.plan.lane = 1
+        def __exit__(self, *a): self.plan.lane = 0
+
+    def _side(self, plan: Plan):
+        """``with self._side(plan):`` -- calls added inside run on the side stream (off the critical path)."""
+        return CaptionEngine._Side(plan)
+
+    def _scratch(self, ws, tag: str, rows: int, cols: int, dtype) -> torch.Tensor:
+        """Per-use gradient scratch (never shared between call sites, so side-stream readers cannot race
+        with later writers on the main stream)."""
+        if tag not in ws.scratch:
+            ws.scratch[tag] = torch.empty((rows, cols), dtype=dtype, device=self.device)
+        return ws.scratch[tag]
+
     def tempo_table(self, T: int) -> torch.Tensor:
         """[T+1, d] temporal-encoding rows: row 0 zeros (global token), row i = pe[i-1]
         (model/MMEncoder.py:89-104 for one modality: indices = linspace(0, T-1, T) = 0..T-1).
@@ -172,7 +226,8 @@ class CaptionEngine:
         plan.add("vct_gemm:" + tag, self.lib.vct_gemm, C.byref(g))
 
     def _colsum(self, plan: Plan, tag: str, X, ld, M, N, out, ws):
-        plan.add("vct_colsum:" + tag, self.lib.vct_colsum, X, self.cdt, ld, M, N, out, ws.partials.data_ptr(),
+        # column sums run on the side lane: they get their own partials buffer (LN backward uses ws.partials)
+        plan.add("vct_colsum:" + tag, self.lib.vct_colsum, X, self.cdt, ld, M, N, out, ws.partials_side.data_ptr(),
                  self.counters.data_ptr() + 4 * 8)
 
     def _ln_fwd(self, plan: Plan, tag, x, r, gname, bname, y, y_c, s_out, mean, rstd, R, p, site):
@@ -289,18 +344,15 @@ class CaptionEngine:
             self._buf(ws, "g_a", (rmax, d), f32)          # fp32 activation-gradient ping/pong
             self._buf(ws, "g_b", (rmax, d), f32)
             self._buf(ws, "g_s", (rmax, d), f32)          # ds of the LN being processed
-            self._buf(ws, "g_r_c", (rmax, d), cdt)        # dr (branch gradient), compute dtype
             self._buf(ws, "g_o_c", (rmax, d), cdt)        # gradient wrt attention output
-            self._buf(ws, "g_z_c", (rmax, Fm), cdt)       # gradient wrt FFN pre-activation
-            self._buf(ws, "g_qkv_c", (rmax, 3 * d), cdt)
-            self._buf(ws, "g_q_c", (Rd, d), cdt)
-            self._buf(ws, "g_kv_c", (Re, 2 * d), cdt)
             self._buf(ws, "g_mem", (Re, d), f32)
             self._buf(ws, "g_x0_c", (Re, d), cdt)
             nws = max(int(self.lib.vct_ln_bwd_workspace_floats(rmax, d)),
                       int(self.lib.vct_colsum_workspace_floats(rmax, max(3 * d, Fm))),
                       int(self.lib.vct_colsum_workspace_floats(Rd, D.V)))
             self._buf(ws, "partials", (nws,), f32)
+            self._buf(ws, "partials_side", (nws,), f32)
+            ws.scratch = {}
         ws.plans = {}
         self._ws[key] = ws
         return ws
@@ -459,15 +511,17 @@ class CaptionEngine:
         D, lib = self.dims, self.lib
         d, B, S, M = D.d, ws.B, ws.S, ws.M
         Re, Rd = B * M, B * S
-        cd = self.cdt
+        cd, cdt, es = self.cdt, _TDT[self.cdt], _ESIZE[self.cdt]
         pd = float(D.dropout)
+        side = self._side
         if sce_first:
             self._sce(p, ws, with_loss=False, with_grad=True)
         dl = ws.dlogits.data_ptr()
         # ---- generator -------------------------------------------------------------------------
-        self._gemm(p, "generator.wgrad", D.V, d, Rd, dl, ws.Vp, 1, ws.hfin_c.data_ptr(), d, 1,
-                   self._g("cap_decoder.generator.weight"), F32, d)
-        self._colsum(p, "generator.bias", dl, ws.Vp, Rd, D.V, self._g("cap_decoder.generator.bias"), ws)
+        with side(p):
+            self._gemm(p, "generator.wgrad", D.V, d, Rd, dl, ws.Vp, 1, ws.hfin_c.data_ptr(), d, 1,
+                       self._g("cap_decoder.generator.weight"), F32, d)
+            self._colsum(p, "generator.bias", dl, ws.Vp, Rd, D.V, self._g("cap_decoder.generator.bias"), ws)
         self._gemm(p, "generator.dgrad", Rd, d, D.V, dl, ws.Vp, 0, self._w("cap_decoder.generator.weight"), d, 1,
                    ws.g_a.data_ptr(), F32, d)
         self._ln_bwd(p, "dec.norm", ws.g_a.data_ptr(), ws.dec_out.data_ptr(), ws.hfin_stats[0].data_ptr(),
@@ -479,63 +533,76 @@ class CaptionEngine:
             e = ws.dec[l]
             pre = f"cap_decoder.decoder.layers.{l}."
             xin_c = (ws.dec[l - 1].x3_c if l > 0 else ws.e0_c)
+            g_r3 = self._scratch(ws, f"dec{l}.dr3", Rd, d, cdt).data_ptr()
+            g_z = self._scratch(ws, f"dec{l}.dz", Rd, D.F_dec, cdt).data_ptr()
+            g_r2 = self._scratch(ws, f"dec{l}.dr2", Rd, d, cdt).data_ptr()
+            g_q = self._scratch(ws, f"dec{l}.dq", Rd, d, cdt).data_ptr()
+            g_kv = self._scratch(ws, f"dec{l}.dkv", Re, 2 * d, cdt).data_ptr()
+            g_r1 = self._scratch(ws, f"dec{l}.dr1", Rd, d, cdt).data_ptr()
+            gq = self._scratch(ws, f"dec{l}.dqkv", Rd, 3 * d, cdt).data_ptr()
+            g_o = ws.g_o_c.data_ptr()        # consumed on the main lane only
             # norm3 / FFN
             self._ln_bwd(p, f"dec{l}.norm3", dx.data_ptr(), e.s3.data_ptr(), e.stats[4].data_ptr(), e.stats[5].data_ptr(),
-                         pre + "norm3.weight", pre + "norm3.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         pre + "norm3.weight", pre + "norm3.bias", ws.g_s.data_ptr(), g_r3,
                          self._g(pre + "linear2.bias"), Rd, pd, _dec_site(l, 5), ws)
-            self._gemm(p, f"dec{l}.linear2.wgrad", d, D.F_dec, Rd, ws.g_r_c.data_ptr(), d, 1, e.h.data_ptr(), D.F_dec, 1,
-                       self._g(pre + "linear2.weight"), F32, D.F_dec)
-            self._gemm(p, f"dec{l}.linear2.dgrad", Rd, D.F_dec, d, ws.g_r_c.data_ptr(), d, 0, self._w(pre + "linear2.weight"),
-                       D.F_dec, 1, ws.g_z_c.data_ptr(), cd, D.F_dec, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_dec,
+            with side(p):
+                self._gemm(p, f"dec{l}.linear2.wgrad", d, D.F_dec, Rd, g_r3, d, 1, e.h.data_ptr(), D.F_dec, 1,
+                           self._g(pre + "linear2.weight"), F32, D.F_dec)
+            self._gemm(p, f"dec{l}.linear2.dgrad", Rd, D.F_dec, d, g_r3, d, 0, self._w(pre + "linear2.weight"),
+                       D.F_dec, 1, g_z, cd, D.F_dec, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_dec,
                        drop_p=pd, site=_dec_site(l, 4))
-            self._gemm(p, f"dec{l}.linear1.wgrad", D.F_dec, d, Rd, ws.g_z_c.data_ptr(), D.F_dec, 1, e.x2_c.data_ptr(), d, 1,
-                       self._g(pre + "linear1.weight"), F32, d)
-            self._colsum(p, f"dec{l}.linear1.bias", ws.g_z_c.data_ptr(), D.F_dec, Rd, D.F_dec, self._g(pre + "linear1.bias"), ws)
-            self._gemm(p, f"dec{l}.linear1.dgrad", Rd, d, D.F_dec, ws.g_z_c.data_ptr(), D.F_dec, 0, self._w(pre + "linear1.weight"),
+            with side(p):
+                self._gemm(p, f"dec{l}.linear1.wgrad", D.F_dec, d, Rd, g_z, D.F_dec, 1, e.x2_c.data_ptr(), d, 1,
+                           self._g(pre + "linear1.weight"), F32, d)
+                self._colsum(p, f"dec{l}.linear1.bias", g_z, D.F_dec, Rd, D.F_dec, self._g(pre + "linear1.bias"), ws)
+            self._gemm(p, f"dec{l}.linear1.dgrad", Rd, d, D.F_dec, g_z, D.F_dec, 0, self._w(pre + "linear1.weight"),
                        d, 1, other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
             dx, other = other, dx           # dx = grad wrt x2
             # norm2 / cross attention
             self._ln_bwd(p, f"dec{l}.norm2", dx.data_ptr(), e.s2.data_ptr(), e.stats[2].data_ptr(), e.stats[3].data_ptr(),
-                         pre + "norm2.weight", pre + "norm2.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         pre + "norm2.weight", pre + "norm2.bias", ws.g_s.data_ptr(), g_r2,
                          self._g(pre + "multihead_attn.out_proj.bias"), Rd, pd, _dec_site(l, 3), ws)
-            self._gemm(p, f"dec{l}.cross.out_proj.wgrad", d, d, Rd, ws.g_r_c.data_ptr(), d, 1, e.ao2.data_ptr(), d, 1,
-                       self._g(pre + "multihead_attn.out_proj.weight"), F32, d)
-            self._gemm(p, f"dec{l}.cross.out_proj.dgrad", Rd, d, d, ws.g_r_c.data_ptr(), d, 0,
-                       self._w(pre + "multihead_attn.out_proj.weight"), d, 1, ws.g_o_c.data_ptr(), cd, d)
-            es = _ESIZE[cd]
+            with side(p):
+                self._gemm(p, f"dec{l}.cross.out_proj.wgrad", d, d, Rd, g_r2, d, 1, e.ao2.data_ptr(), d, 1,
+                           self._g(pre + "multihead_attn.out_proj.weight"), F32, d)
+            self._gemm(p, f"dec{l}.cross.out_proj.dgrad", Rd, d, d, g_r2, d, 0,
+                       self._w(pre + "multihead_attn.out_proj.weight"), d, 1, g_o, cd, d)
             self._attn(p, f"dec{l}.cross", True, B=B, H=D.H_dec, Lq=S, Lk=M, q=e.q.data_ptr(), q_ld=d,
                        k=e.kv.data_ptr(), k_ld=2 * d, v=e.kv.data_ptr() + d * es, v_ld=2 * d, o=None, o_ld=d,
-                       p=pd, site=_dec_site(l, 2), d_o=ws.g_o_c.data_ptr(), do_ld=d, dq=ws.g_q_c.data_ptr(), dq_ld=d,
-                       dk=ws.g_kv_c.data_ptr(), dk_ld=2 * d, dv=ws.g_kv_c.data_ptr() + d * es, dv_ld=2 * d)
+                       p=pd, site=_dec_site(l, 2), d_o=g_o, do_ld=d, dq=g_q, dq_ld=d,
+                       dk=g_kv, dk_ld=2 * d, dv=g_kv + d * es, dv_ld=2 * d)
             wname, bname = pre + "multihead_attn.in_proj_weight", pre + "multihead_attn.in_proj_bias"
-            self._gemm(p, f"dec{l}.cross.q.wgrad", d, d, Rd, ws.g_q_c.data_ptr(), d, 1, e.x1_c.data_ptr(), d, 1,
-                       self._g(wname), F32, d)
-            self._colsum(p, f"dec{l}.cross.q.bias", ws.g_q_c.data_ptr(), d, Rd, d, self._g(bname), ws)
-            self._gemm(p, f"dec{l}.cross.kv.wgrad", 2 * d, d, Re, ws.g_kv_c.data_ptr(), 2 * d, 1, ws.mem_c.data_ptr(), d, 1,
-                       self._g(wname, d * d), F32, d)
-            self._colsum(p, f"dec{l}.cross.kv.bias", ws.g_kv_c.data_ptr(), 2 * d, Re, 2 * d, self._g(bname, d), ws)
-            self._gemm(p, f"dec{l}.cross.q.dgrad", Rd, d, d, ws.g_q_c.data_ptr(), d, 0, self._w(wname), d, 1,
+            with side(p):
+                self._gemm(p, f"dec{l}.cross.q.wgrad", d, d, Rd, g_q, d, 1, e.x1_c.data_ptr(), d, 1, self._g(wname), F32, d)
+                self._colsum(p, f"dec{l}.cross.q.bias", g_q, d, Rd, d, self._g(bname), ws)
+                self._gemm(p, f"dec{l}.cross.kv.wgrad", 2 * d, d, Re, g_kv, 2 * d, 1, ws.mem_c.data_ptr(), d, 1,
+                           self._g(wname, d * d), F32, d)
+                self._colsum(p, f"dec{l}.cross.kv.bias", g_kv, 2 * d, Re, 2 * d, self._g(bname, d), ws)
+            self._gemm(p, f"dec{l}.cross.q.dgrad", Rd, d, d, g_q, d, 0, self._w(wname), d, 1,
                        other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
-            self._gemm(p, f"dec{l}.cross.kv.dgrad", Re, d, 2 * d, ws.g_kv_c.data_ptr(), 2 * d, 0, self._w(wname, d), d, 1,
+            self._gemm(p, f"dec{l}.cross.kv.dgrad", Re, d, 2 * d, g_kv, 2 * d, 0, self._w(wname, d), d, 1,
                        ws.g_mem.data_ptr(), F32, d, addend=None if first_mem else ws.g_mem.data_ptr(), ld_addend=d)
             first_mem = False
             dx, other = other, dx           # dx = grad wrt x1
             # norm1 / self attention
             self._ln_bwd(p, f"dec{l}.norm1", dx.data_ptr(), e.s1.data_ptr(), e.stats[0].data_ptr(), e.stats[1].data_ptr(),
-                         pre + "norm1.weight", pre + "norm1.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         pre + "norm1.weight", pre + "norm1.bias", ws.g_s.data_ptr(), g_r1,
                          self._g(pre + "self_attn.out_proj.bias"), Rd, pd, _dec_site(l, 1), ws)
-            self._gemm(p, f"dec{l}.self.out_proj.wgrad", d, d, Rd, ws.g_r_c.data_ptr(), d, 1, e.ao.data_ptr(), d, 1,
-                       self._g(pre + "self_attn.out_proj.weight"), F32, d)
-            self._gemm(p, f"dec{l}.self.out_proj.dgrad", Rd, d, d, ws.g_r_c.data_ptr(), d, 0,
-                       self._w(pre + "self_attn.out_proj.weight"), d, 1, ws.g_o_c.data_ptr(), cd, d)
-            qkv, gq = e.qkv.data_ptr(), ws.g_qkv_c.data_ptr()
+            with side(p):
+                self._gemm(p, f"dec{l}.self.out_proj.wgrad", d, d, Rd, g_r1, d, 1, e.ao.data_ptr(), d, 1,
+                           self._g(pre + "self_attn.out_proj.weight"), F32, d)
+            self._gemm(p, f"dec{l}.self.out_proj.dgrad", Rd, d, d, g_r1, d, 0,
+                       self._w(pre + "self_attn.out_proj.weight"), d, 1, g_o, cd, d)
+            qkv = e.qkv.data_ptr()
             self._attn(p, f"dec{l}.self", True, B=B, H=D.H_dec, Lq=S, Lk=S, q=qkv, q_ld=3 * d, k=qkv + d * es, k_ld=3 * d,
                        v=qkv + 2 * d * es, v_ld=3 * d, o=None, o_ld=d, key_pad=ws.tok_pad.data_ptr(), causal=1, p=pd,
-                       site=_dec_site(l, 0), d_o=ws.g_o_c.data_ptr(), do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
+                       site=_dec_site(l, 0), d_o=g_o, do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
                        dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d)
             wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
-            self._gemm(p, f"dec{l}.self.in_proj.wgrad", 3 * d, d, Rd, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d)
-            self._colsum(p, f"dec{l}.self.in_proj.bias", gq, 3 * d, Rd, 3 * d, self._g(bname), ws)
+            with side(p):
+                self._gemm(p, f"dec{l}.self.in_proj.wgrad", 3 * d, d, Rd, gq, 3 * d, 1, xin_c.data_ptr(), d, 1,
+                           self._g(wname), F32, d)
+                self._colsum(p, f"dec{l}.self.in_proj.bias", gq, 3 * d, Rd, 3 * d, self._g(bname), ws)
             self._gemm(p, f"dec{l}.self.in_proj.dgrad", Rd, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
                        addend=ws.g_s.data_ptr(), ld_addend=d)
             dx, other = other, dx           # dx = grad wrt the layer input
@@ -547,55 +614,65 @@ class CaptionEngine:
         D, lib = self.dims, self.lib
         d, B, M = D.d, ws.B, ws.M
         Re = B * M
-        cd = self.cdt
+        cd, cdt, es = self.cdt, _TDT[self.cdt], _ESIZE[self.cdt]
         pd = float(D.dropout)
+        side = self._side
         self._ln_bwd(p, "enc.norm", ws.g_mem.data_ptr(), ws.enc_out.data_ptr(), ws.mem_stats[0].data_ptr(),
                      ws.mem_stats[1].data_ptr(), "video_encoder.transformer_encoder.norm.weight",
                      "video_encoder.transformer_encoder.norm.bias", ws.g_a.data_ptr(), None, None, Re, 0.0, 0, ws)
         dx, other = ws.g_a, ws.g_b
-        es = _ESIZE[cd]
+        g_o = ws.g_o_c.data_ptr()
         for l in reversed(range(D.L_enc)):
             e = ws.enc[l]
             pre = f"video_encoder.transformer_encoder.layers.{l}."
             xin_c = (ws.enc[l - 1].x2_c if l > 0 else ws.x0_c)
+            g_r2 = self._scratch(ws, f"enc{l}.dr2", Re, d, cdt).data_ptr()
+            g_z = self._scratch(ws, f"enc{l}.dz", Re, D.F_enc, cdt).data_ptr()
+            g_r1 = self._scratch(ws, f"enc{l}.dr1", Re, d, cdt).data_ptr()
+            gq = self._scratch(ws, f"enc{l}.dqkv", Re, 3 * d, cdt).data_ptr()
             self._ln_bwd(p, f"enc{l}.norm2", dx.data_ptr(), e.s2.data_ptr(), e.stats[2].data_ptr(), e.stats[3].data_ptr(),
-                         pre + "norm2.weight", pre + "norm2.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         pre + "norm2.weight", pre + "norm2.bias", ws.g_s.data_ptr(), g_r2,
                          self._g(pre + "linear2.bias"), Re, pd, _enc_site(l, 3), ws)
-            self._gemm(p, f"enc{l}.linear2.wgrad", d, D.F_enc, Re, ws.g_r_c.data_ptr(), d, 1, e.h.data_ptr(), D.F_enc, 1,
-                       self._g(pre + "linear2.weight"), F32, D.F_enc)
-            self._gemm(p, f"enc{l}.linear2.dgrad", Re, D.F_enc, d, ws.g_r_c.data_ptr(), d, 0, self._w(pre + "linear2.weight"),
-                       D.F_enc, 1, ws.g_z_c.data_ptr(), cd, D.F_enc, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_enc,
+            with side(p):
+                self._gemm(p, f"enc{l}.linear2.wgrad", d, D.F_enc, Re, g_r2, d, 1, e.h.data_ptr(), D.F_enc, 1,
+                           self._g(pre + "linear2.weight"), F32, D.F_enc)
+            self._gemm(p, f"enc{l}.linear2.dgrad", Re, D.F_enc, d, g_r2, d, 0, self._w(pre + "linear2.weight"),
+                       D.F_enc, 1, g_z, cd, D.F_enc, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_enc,
                        drop_p=pd, site=_enc_site(l, 2))
-            self._gemm(p, f"enc{l}.linear1.wgrad", D.F_enc, d, Re, ws.g_z_c.data_ptr(), D.F_enc, 1, e.x1_c.data_ptr(), d, 1,
-                       self._g(pre + "linear1.weight"), F32, d)
-            self._colsum(p, f"enc{l}.linear1.bias", ws.g_z_c.data_ptr(), D.F_enc, Re, D.F_enc, self._g(pre + "linear1.bias"), ws)
-            self._gemm(p, f"enc{l}.linear1.dgrad", Re, d, D.F_enc, ws.g_z_c.data_ptr(), D.F_enc, 0, self._w(pre + "linear1.weight"),
+            with side(p):
+                self._gemm(p, f"enc{l}.linear1.wgrad", D.F_enc, d, Re, g_z, D.F_enc, 1, e.x1_c.data_ptr(), d, 1,
+                           self._g(pre + "linear1.weight"), F32, d)
+                self._colsum(p, f"enc{l}.linear1.bias", g_z, D.F_enc, Re, D.F_enc, self._g(pre + "linear1.bias"), ws)
+            self._gemm(p, f"enc{l}.linear1.dgrad", Re, d, D.F_enc, g_z, D.F_enc, 0, self._w(pre + "linear1.weight"),
                        d, 1, other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
             dx, other = other, dx
             self._ln_bwd(p, f"enc{l}.norm1", dx.data_ptr(), e.s1.data_ptr(), e.stats[0].data_ptr(), e.stats[1].data_ptr(),
-                         pre + "norm1.weight", pre + "norm1.bias", ws.g_s.data_ptr(), ws.g_r_c.data_ptr(),
+                         pre + "norm1.weight", pre + "norm1.bias", ws.g_s.data_ptr(), g_r1,
                          self._g(pre + "self_attn.out_proj.bias"), Re, pd, _enc_site(l, 1), ws)
-            self._gemm(p, f"enc{l}.out_proj.wgrad", d, d, Re, ws.g_r_c.data_ptr(), d, 1, e.ao.data_ptr(), d, 1,
-                       self._g(pre + "self_attn.out_proj.weight"), F32, d)
-            self._gemm(p, f"enc{l}.out_proj.dgrad", Re, d, d, ws.g_r_c.data_ptr(), d, 0, self._w(pre + "self_attn.out_proj.weight"),
-                       d, 1, ws.g_o_c.data_ptr(), cd, d)
-            qkv, gq = e.qkv.data_ptr(), ws.g_qkv_c.data_ptr()
+            with side(p):
+                self._gemm(p, f"enc{l}.out_proj.wgrad", d, d, Re, g_r1, d, 1, e.ao.data_ptr(), d, 1,
+                           self._g(pre + "self_attn.out_proj.weight"), F32, d)
+            self._gemm(p, f"enc{l}.out_proj.dgrad", Re, d, d, g_r1, d, 0, self._w(pre + "self_attn.out_proj.weight"),
+                       d, 1, g_o, cd, d)
+            qkv = e.qkv.data_ptr()
             self._attn(p, f"enc{l}.self", True, B=B, H=D.H_enc, Lq=M, Lk=M, q=qkv, q_ld=3 * d, k=qkv + d * es, k_ld=3 * d,
                        v=qkv + 2 * d * es, v_ld=3 * d, o=None, o_ld=d, key_pad=ws.vid_pad.data_ptr(), causal=0, p=pd,
-                       site=_enc_site(l, 0), d_o=ws.g_o_c.data_ptr(), do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
+                       site=_enc_site(l, 0), d_o=g_o, do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
                        dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d)
             wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
-            self._gemm(p, f"enc{l}.in_proj.wgrad", 3 * d, d, Re, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d)
-            self._colsum(p, f"enc{l}.in_proj.bias", gq, 3 * d, Re, 3 * d, self._g(bname), ws)
+            with side(p):
+                self._gemm(p, f"enc{l}.in_proj.wgrad", 3 * d, d, Re, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d)
+                self._colsum(p, f"enc{l}.in_proj.bias", gq, 3 * d, Re, 3 * d, self._g(bname), ws)
             last = l == 0
             self._gemm(p, f"enc{l}.in_proj.dgrad", Re, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
                        addend=ws.g_s.data_ptr(), ld_addend=d,
                        C2=ws.g_x0_c.data_ptr() if (last and cd == BF16) else None, c2_dtype=cd, ldc2=d)
             dx, other = other, dx
         g_x0_c = ws.g_x0_c.data_ptr() if cd == BF16 else dx.data_ptr()
-        self._gemm(p, "unify.wgrad", d, D.Din, Re, g_x0_c, d, 1, ws.a0.data_ptr(), D.Din, 1,
-                   self._g("video_encoder.unify.0.weight"), F32, D.Din)
-        self._colsum(p, "unify.bias", g_x0_c, d, Re, d, self._g("video_encoder.unify.0.bias"), ws)
+        with side(p):
+            self._gemm(p, "unify.wgrad", d, D.Din, Re, g_x0_c, d, 1, ws.a0.data_ptr(), D.Din, 1,
+                       self._g("video_encoder.unify.0.weight"), F32, D.Din)
+            self._colsum(p, "unify.bias", g_x0_c, d, Re, d, self._g("video_encoder.unify.0.bias"), ws)
 
     # ------------------------------------------------------------------------------------------
     # running
@@ -613,7 +690,7 @@ class CaptionEngine:
             torch.eq(ws.ids[:, :-1], self.dims.pad_id, out=ws.tok_pad.view(torch.bool))
 
     def run(self, plan: Plan) -> None:
-        self.launches += plan.run(self._stream())
+        self.launches += plan.run(torch.cuda.current_stream(self.device), self.side_stream)
 
     def zero_scatter_grads(self) -> None:
         """Only the embedding gradient is accumulated with atomics; every other gradient is overwritten."""
