@@ -172,8 +172,12 @@ int vct_ln_residual_fwd(const float* x, const float* r, const float* gamma, cons
  * Column sums: dgamma += sum dy*xhat, dbeta += sum dy, dbias_r = sum dr (bias gradient of the
  * linear that produced r; NULL to skip).  `partials` is a fp32 workspace of
  * vct_ln_bwd_workspace_floats(R, d) floats; `counter` is unused (kept for ABI stability, may be NULL).
- * dgamma/dbeta/dbias_r are OVERWRITTEN (deterministic two-kernel reduction, no atomics). */
+ * dgamma/dbeta/dbias_r are OVERWRITTEN (deterministic two-kernel reduction, no atomics).
+ * If dgamma, dbeta and dbias_r are ALL NULL only the per-CTA partials are produced and the caller
+ * finishes with vct_ln_bwd_reduce (same R, d) -- e.g. on a side stream, off the critical path of backward. */
 long long vct_ln_bwd_workspace_floats(int R, int d);
+int vct_ln_bwd_reduce(const float* partials, int R, int d, float* dgamma, float* dbeta, float* dbias_r,
+                      vct_stream_t stream);
 int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
                         float* ds, void* dr_c, int dr_dtype, float* dgamma, float* dbeta, float* dbias_r,
                         float* partials, unsigned int* counter,

@@ -107,6 +107,17 @@ __device__ __forceinline__ void weighted_rows(const float* __restrict__ wt, int 
     }
 }
 
+// dropout keep-multipliers of one probability row for the key slots (lane, lane + 32): lane t draws the 8
+// decisions of keys 8t..8t+7 (one Philox call per row and warp), the bits are exchanged with shuffles.
+// Index space: row r = (b*H + h)*Lq + i owns groups r*8 .. r*8+7 (Lk <= 64).
+__device__ __forceinline__ void row_dropout(const Rng& rng, unsigned int site, long long row, int lane, float& sc0, float& sc1) {
+    const uint32_t bits = dropout_bits8(rng, site, (unsigned long long)row * 8ull + (unsigned long long)(lane & 7));
+    const uint32_t m0 = __shfl_sync(0xffffffffu, bits, lane >> 3);
+    const uint32_t m1 = __shfl_sync(0xffffffffu, bits, 4 + (lane >> 3));
+    sc0 = ((m0 >> (lane & 7)) & 1u) ? rng.inv_keep : 0.f;
+    sc1 = ((m1 >> (lane & 7)) & 1u) ? rng.inv_keep : 0.f;
+}
+
 template <typename T, int DHP>
 __global__ void __launch_bounds__(kThreads)
 attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
@@ -145,8 +156,10 @@ attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
             if (lane + 32 < Lk) probs[pbase + lane + 32] = p1;
         }
         if (rng.p > 0.f) {
-            if (lane < Lk) p0 *= dropout_scale1(rng, site, (unsigned long long)(pbase + lane));
-            if (lane + 32 < Lk) p1 *= dropout_scale1(rng, site, (unsigned long long)(pbase + lane + 32));
+            float sc0, sc1;
+            row_dropout(rng, site, (long long)bh * Lq + i, lane, sc0, sc1);
+            p0 *= sc0;
+            p1 *= sc1;
         }
         if (lane < Lk) Pt[lane * LqP + i] = p0;
         if (lane + 32 < Lk) Pt[(lane + 32) * LqP + i] = p1;
@@ -207,14 +220,13 @@ attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
         for (int i = r0; i < r1; ++i) {
             float p[2];
             softmax_row(Ss + i * LkP, Lk, i, lane, D.causal != 0, pad_row, D.scale, p[0], p[1]);
-            const long long pbase = ((long long)bh * Lq + i) * Lk;
             float sc[2] = {1.f, 1.f}, dP[2] = {0.f, 0.f};
             float dsum = 0.f;
+            if (rng.p > 0.f) row_dropout(rng, site, (long long)bh * Lq + i, lane, sc[0], sc[1]);
 #pragma unroll
             for (int t = 0; t < 2; ++t) {
                 const int j = lane + 32 * t;
                 if (j < Lk) {
-                    if (rng.p > 0.f) sc[t] = dropout_scale1(rng, site, (unsigned long long)(pbase + j));
                     dP[t] = dPs[i * LkP + j] * sc[t];
                     dsum += p[t] * dP[t];
                 }

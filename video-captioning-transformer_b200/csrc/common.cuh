@@ -78,14 +78,18 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 counter RNG for dropout.  The mask of element `idx` at dropout site `site` in
-// training step `rng[1]` with seed `rng[0]` is a pure function of those four numbers, so forward
-// and backward (and the debug entry vct_dropout_mask) regenerate identical masks without storing.
-// One call yields the uniforms of the 4 consecutive elements idx4*4 .. idx4*4+3.
+// Philox4x32-7 counter RNG for dropout.  The mask of element `idx` at dropout site `site` in training
+// step `rng[1]` with seed `rng[0]` is a pure function of those four numbers, so forward and backward
+// (and the debug entry vct_dropout_mask) regenerate identical masks without storing them.
+// One call yields 128 bits = 16-bit uniforms for the 8 consecutive elements idx8*8 .. idx8*8+7
+// (keep iff r16 >= round(p * 65536)): the RNG is ~1/3 of the instruction count of a train step if
+// done per 4 elements with 10 rounds, so bits are not wasted.  7 rounds is the minimum the Philox
+// authors qualify (Salmon et al., SC11, table 2: Philox4x32-7 passes BigCrush).
 // ---------------------------------------------------------------------------------------------
 struct Rng {
     uint32_t k0, k1, step_lo;
-    float p;       // drop probability; p <= 0 disables
+    uint32_t thresh;   // drop iff r16 < thresh
+    float p;           // drop probability; p <= 0 disables
     float inv_keep;
 };
 
@@ -93,6 +97,7 @@ __device__ __forceinline__ Rng make_rng(const unsigned long long* rng_state, flo
     Rng r;
     r.p = p;
     r.inv_keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+    r.thresh = p > 0.f ? (uint32_t)(p * 65536.f + 0.5f) : 0u;
     if (p > 0.f && rng_state != nullptr) {
         unsigned long long seed = rng_state[0], step = rng_state[1];
         r.k0 = (uint32_t)seed;
@@ -104,9 +109,9 @@ __device__ __forceinline__ Rng make_rng(const unsigned long long* rng_state, flo
     return r;
 }
 
-__device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
+__device__ __forceinline__ uint4 philox4x32_7(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, uint32_t k0, uint32_t k1) {
 #pragma unroll
-    for (int i = 0; i < 10; ++i) {
+    for (int i = 0; i < 7; ++i) {
         uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -116,24 +121,70 @@ __device__ __forceinline__ uint4 philox4(uint32_t c0, uint32_t c1, uint32_t c2, 
     return make_uint4(c0, c1, c2, c3);
 }
 
-// keep-multipliers (0 or 1/(1-p)) for elements idx4*4 .. idx4*4+3 of `site`
-__device__ __forceinline__ float4 dropout_scale4(const Rng& r, uint32_t site, unsigned long long idx4) {
-    if (r.p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
-    uint4 u = philox4((uint32_t)idx4, (uint32_t)(idx4 >> 32), site, r.step_lo, r.k0, r.k1);
-    const float s = 1.0f / 16777216.0f;
-    float4 o;
-    o.x = ((u.x >> 8) * s >= r.p) ? r.inv_keep : 0.f;
-    o.y = ((u.y >> 8) * s >= r.p) ? r.inv_keep : 0.f;
-    o.z = ((u.z >> 8) * s >= r.p) ? r.inv_keep : 0.f;
-    o.w = ((u.w >> 8) * s >= r.p) ? r.inv_keep : 0.f;
-    return o;
+// keep-multipliers (0 or 1/(1-p)) of elements idx8*8 .. idx8*8+7 of `site`
+__device__ __forceinline__ void dropout_scale8(const Rng& r, uint32_t site, unsigned long long idx8, float* out) {
+    if (r.p <= 0.f) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) out[q] = 1.f;
+        return;
+    }
+    const uint4 u = philox4x32_7((uint32_t)idx8, (uint32_t)(idx8 >> 32), site, r.step_lo, r.k0, r.k1);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        out[2 * q + 0] = (w[q] & 0xFFFFu) >= r.thresh ? r.inv_keep : 0.f;
+        out[2 * q + 1] = (w[q] >> 16) >= r.thresh ? r.inv_keep : 0.f;
+    }
 }
-// single element
+// the same 8 decisions as a bit mask (bit q set = element idx8*8+q is kept)
+__device__ __forceinline__ uint32_t dropout_bits8(const Rng& r, uint32_t site, unsigned long long idx8) {
+    if (r.p <= 0.f) return 0xFFu;
+    const uint4 u = philox4x32_7((uint32_t)idx8, (uint32_t)(idx8 >> 32), site, r.step_lo, r.k0, r.k1);
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    uint32_t bits = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        bits |= ((w[q] & 0xFFFFu) >= r.thresh ? 1u : 0u) << (2 * q);
+        bits |= ((w[q] >> 16) >= r.thresh ? 1u : 0u) << (2 * q + 1);
+    }
+    return bits;
+}
+// load / store 8 consecutive elements as fp32 (pointer must be 8-element aligned for bf16, 4 for fp32)
+__device__ __forceinline__ void ld8(const float* p, float* o) {
+    const float4 a = ld4(p), b = ld4(p + 4);
+    o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w;
+}
+__device__ __forceinline__ void ld8(const __nv_bfloat16* p, float* o) {
+    const uint4 r = *reinterpret_cast<const uint4*>(p);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[q]));
+        o[2 * q] = f.x; o[2 * q + 1] = f.y;
+    }
+}
+__device__ __forceinline__ void st8(float* p, const float* v) {
+    st4(p, make_float4(v[0], v[1], v[2], v[3]));
+    st4(p + 4, make_float4(v[4], v[5], v[6], v[7]));
+}
+__device__ __forceinline__ void st8(__nv_bfloat16* p, const float* v) {
+    uint32_t w[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * q], v[2 * q + 1]);
+        w[q] = *reinterpret_cast<uint32_t*>(&h);
+    }
+    *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+// single element (scalar fallback paths)
 __device__ __forceinline__ float dropout_scale1(const Rng& r, uint32_t site, unsigned long long idx) {
     if (r.p <= 0.f) return 1.f;
-    float4 v = dropout_scale4(r, site, idx >> 2);
-    int c = (int)(idx & 3ull);
-    return c == 0 ? v.x : c == 1 ? v.y : c == 2 ? v.z : v.w;
+    float v[8];
+    dropout_scale8(r, site, idx >> 3, v);
+    float o = v[0];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) o = (int)(idx & 7ull) == q ? v[q] : o;
+    return o;
 }
 
 // exact-erf GELU and its derivative (activation "gelu" -> F.gelu(approximate='none'))

@@ -96,7 +96,7 @@ extern "C" int vct_prep_frames(const float* feats, void* out, int out_dtype, int
 }
 
 // ------------------------------------------------------------------------------------------------
-// residual + dropout + LayerNorm forward: one warp per row, NV float4 per lane
+// residual + dropout + LayerNorm forward: one warp per row, NV chunks of 8 elements per lane
 // ------------------------------------------------------------------------------------------------
 constexpr int kLnWarps = 8;
 
@@ -109,23 +109,25 @@ ln_fwd_kernel(const float* __restrict__ x, const float* r, const float* __restri
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kLnWarps + warp;
     if (row >= R) return;
-    const int nv = d >> 2;
+    const int nv = d >> 3;
     const Rng rng = make_rng(rng_state, x != nullptr ? drop_p : 0.f);
     const long long base = (long long)row * d;
-    float4 v[NV];
+    float v[NV][8];
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nv) {
-            float4 rv = ld4(r + base + c * 4);
+            ld8(r + base + c * 8, v[i]);
             if (x != nullptr) {
-                float4 sc = dropout_scale4(rng, site, (unsigned long long)(base >> 2) + c);
-                float4 xv = ld4(x + base + c * 4);
-                rv = make_float4(xv.x + rv.x * sc.x, xv.y + rv.y * sc.y, xv.z + rv.z * sc.z, xv.w + rv.w * sc.w);
+                float sc[8], xv[8];
+                dropout_scale8(rng, site, (unsigned long long)(base >> 3) + c, sc);
+                ld8(x + base + c * 8, xv);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[i][q] = xv[q] + v[i][q] * sc[q];
             }
-            v[i] = rv;
-            sum += rv.x + rv.y + rv.z + rv.w;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sum += v[i][q];
         }
     }
     const float mean = warp_sum(sum) / (float)d;
@@ -134,8 +136,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* r, const float* __restri
     for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nv) {
-            float a = v[i].x - mean, b = v[i].y - mean, e = v[i].z - mean, f = v[i].w - mean;
-            sq += a * a + b * b + e * e + f * f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { const float a = v[i][q] - mean; sq += a * a; }
         }
     }
     const float rstd = rsqrtf(warp_sum(sq) / (float)d + 1e-5f);
@@ -147,12 +149,14 @@ ln_fwd_kernel(const float* __restrict__ x, const float* r, const float* __restri
     for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nv) {
-            if (s_out) st4(s_out + base + c * 4, v[i]);
-            float4 g = ld4(gamma + c * 4), b = ld4(beta + c * 4);
-            float4 o = make_float4((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y,
-                                   (v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
-            if (y) st4(y + base + c * 4, o);
-            if (y_c) st4(y_c + base + c * 4, o);
+            if (s_out) st8(s_out + base + c * 8, v[i]);
+            float g[8], b[8], o[8];
+            ld8(gamma + c * 8, g);
+            ld8(beta + c * 8, b);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) o[q] = (v[i][q] - mean) * rstd * g[q] + b[q];
+            if (y) st8(y + base + c * 8, o);
+            if (y_c) st8(y_c + base + c * 8, o);
         }
     }
 }
@@ -162,15 +166,14 @@ static int launch_ln_fwd(const float* x, const float* r, const float* gamma, con
                          float* s_out, float* mean, float* rstd, int R, int d, float drop_p,
                          const unsigned long long* rng_state, unsigned int site, cudaStream_t st) {
     const int blocks = (R + kLnWarps - 1) / kLnWarps;
-    const int nvl = (d / 4 + 31) / 32;
+    const int nvl = (d / 8 + 31) / 32;
 #define LN_FWD_CASE(NVV)                                                                                         \
     ln_fwd_kernel<NVV, TC><<<blocks, kLnWarps * 32, 0, st>>>(x, r, gamma, beta, y, y_c, s_out, mean, rstd, R, d, \
                                                               drop_p, rng_state, site)
     if (nvl <= 1) LN_FWD_CASE(1);
     else if (nvl <= 2) LN_FWD_CASE(2);
-    else if (nvl <= 4) LN_FWD_CASE(4);
-    else if (nvl <= 6) LN_FWD_CASE(6);
-    else LN_FWD_CASE(8);
+    else if (nvl <= 3) LN_FWD_CASE(3);
+    else LN_FWD_CASE(4);
 #undef LN_FWD_CASE
     return check_launch("vct_ln_residual_fwd");
 }
@@ -179,7 +182,7 @@ extern "C" int vct_ln_residual_fwd(const float* x, const float* r, const float* 
                                    void* y_c, int y_c_dtype, float* s_out, float* mean, float* rstd, int R, int d,
                                    float drop_p, const unsigned long long* rng_state, unsigned int site,
                                    vct_stream_t stream) {
-    VCT_REQUIRE(d % 4 == 0 && d <= 1024 && R > 0, "vct_ln_residual_fwd: need d %% 4 == 0, d <= 1024 (d=%d)", d);
+    VCT_REQUIRE(d % 8 == 0 && d <= 1024 && R > 0, "vct_ln_residual_fwd: need d %% 8 == 0, d <= 1024 (d=%d)", d);
     VCT_REQUIRE(r && gamma && beta, "vct_ln_residual_fwd: null input");
     if (y_c_dtype == VCT_BF16)
         return launch_ln_fwd<__nv_bfloat16>(x, r, gamma, beta, y, (__nv_bfloat16*)y_c, s_out, mean, rstd, R, d, drop_p,
@@ -193,10 +196,13 @@ extern "C" int vct_ln_residual_fwd(const float* x, const float* r, const float* 
 //   kernel 1: one warp per row (grid ~ 1-2 CTAs per SM), per-CTA column partials [3][d] -> workspace
 //   kernel 2: deterministic reduction of the partials over CTAs -> dgamma, dbeta, dbias
 // ------------------------------------------------------------------------------------------------
+constexpr int kLnBwdWarps = 4;          // ~195 registers/thread: 4 warps -> 2 CTAs per SM
+
 static inline int ln_bwd_rows_per_cta(int R) {
+    // one wave: at most 2 CTAs per SM
     int rows = (R + 2 * kNumSMs - 1) / (2 * kNumSMs);
-    rows = ((rows + kLnWarps - 1) / kLnWarps) * kLnWarps;
-    return rows < kLnWarps ? kLnWarps : rows;
+    rows = ((rows + kLnBwdWarps - 1) / kLnBwdWarps) * kLnBwdWarps;
+    return rows < kLnBwdWarps ? kLnBwdWarps : rows;
 }
 static inline int ln_bwd_blocks(int R) {
     const int rows = ln_bwd_rows_per_cta(R);
@@ -205,43 +211,50 @@ static inline int ln_bwd_blocks(int R) {
 
 extern "C" long long vct_ln_bwd_workspace_floats(int R, int d) { return (long long)ln_bwd_blocks(R) * 3 * d; }
 
+// Column partials are kept in a "q-major" order inside each [d] vector: element (chunk c, q) of the 8-wide
+// chunking sits at q * (d/8) + c, which makes every shared-memory access of the reduction conflict-free.
+// ln_bwd_reduce_kernel undoes the permutation when it writes dgamma / dbeta / dbias.
 template <int NV, typename TC>
-__global__ void __launch_bounds__(kLnWarps * 32)
+__global__ void __launch_bounds__(kLnBwdWarps * 32)
 ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const float* __restrict__ mean,
               const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ ds,
               TC* __restrict__ dr_c, float* __restrict__ partials, int R, int d, int rows_per_cta, float drop_p,
               const unsigned long long* __restrict__ rng_state, unsigned int site) {
-    extern __shared__ float sm[];  // [3][d]
+    extern __shared__ float sm[];  // [kLnBwdWarps][3][d]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nv = d >> 2;
+    const int nv = d >> 3;
     const Rng rng = make_rng(rng_state, drop_p);
-    float4 acc_g[NV], acc_b[NV], acc_r[NV];
-    float4 gam[NV];
+    float acc_g[NV][8], acc_b[NV][8], acc_r[NV][8], gam[NV][8];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
-        acc_g[i] = acc_b[i] = acc_r[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         const int c = lane + 32 * i;
-        gam[i] = c < nv ? ld4(gamma + c * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc_g[i][q] = acc_b[i][q] = acc_r[i][q] = gam[i][q] = 0.f;
+        if (c < nv) ld8(gamma + c * 8, gam[i]);
     }
     const int row_end = min(R, (blockIdx.x + 1) * rows_per_cta);
 #pragma unroll 1
-    for (int row = blockIdx.x * rows_per_cta + warp; row < row_end; row += kLnWarps) {
+    for (int row = blockIdx.x * rows_per_cta + warp; row < row_end; row += kLnBwdWarps) {
         const long long base = (long long)row * d;
         const float mu = mean[row], rs = rstd[row];
-        float4 g[NV], xh[NV];
+        float g[NV][8], xh[NV][8];
         float c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < nv) {
-                float4 dyv = ld4(dy + base + c * 4), sv = ld4(s + base + c * 4);
-                xh[i] = make_float4((sv.x - mu) * rs, (sv.y - mu) * rs, (sv.z - mu) * rs, (sv.w - mu) * rs);
-                g[i] = make_float4(dyv.x * gam[i].x, dyv.y * gam[i].y, dyv.z * gam[i].z, dyv.w * gam[i].w);
-                c1 += g[i].x + g[i].y + g[i].z + g[i].w;
-                c2 += g[i].x * xh[i].x + g[i].y * xh[i].y + g[i].z * xh[i].z + g[i].w * xh[i].w;
-                acc_g[i].x += dyv.x * xh[i].x; acc_g[i].y += dyv.y * xh[i].y;
-                acc_g[i].z += dyv.z * xh[i].z; acc_g[i].w += dyv.w * xh[i].w;
-                acc_b[i].x += dyv.x; acc_b[i].y += dyv.y; acc_b[i].z += dyv.z; acc_b[i].w += dyv.w;
+                float dyv[8], sv[8];
+                ld8(dy + base + c * 8, dyv);
+                ld8(s + base + c * 8, sv);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    xh[i][q] = (sv[q] - mu) * rs;
+                    g[i][q] = dyv[q] * gam[i][q];
+                    c1 += g[i][q];
+                    c2 += g[i][q] * xh[i][q];
+                    acc_g[i][q] += dyv[q] * xh[i][q];
+                    acc_b[i][q] += dyv[q];
+                }
             }
         }
         c1 = warp_sum(c1) / (float)d;
@@ -250,81 +263,97 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const f
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < nv) {
-                float4 o = make_float4(rs * (g[i].x - c1 - xh[i].x * c2), rs * (g[i].y - c1 - xh[i].y * c2),
-                                       rs * (g[i].z - c1 - xh[i].z * c2), rs * (g[i].w - c1 - xh[i].w * c2));
-                if (ds) st4(ds + base + c * 4, o);
-                float4 sc = dropout_scale4(rng, site, (unsigned long long)(base >> 2) + c);
-                float4 dr = make_float4(o.x * sc.x, o.y * sc.y, o.z * sc.z, o.w * sc.w);
-                if (dr_c) st4(dr_c + base + c * 4, dr);
-                acc_r[i].x += dr.x; acc_r[i].y += dr.y; acc_r[i].z += dr.z; acc_r[i].w += dr.w;
-            }
-        }
-    }
-    // cross-warp reduction in shared memory, warp by warp (deterministic order)
-    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    for (int w = 0; w < kLnWarps; ++w) {
-        if (warp == w) {
+                float o[8], sc[8], dr[8];
+                dropout_scale8(rng, site, (unsigned long long)(base >> 3) + c, sc);
 #pragma unroll
-            for (int i = 0; i < NV; ++i) {
-                const int c = lane + 32 * i;
-                if (c < nv) {
-                    float* p0 = sm + c * 4;
-                    p0[0] += acc_g[i].x; p0[1] += acc_g[i].y; p0[2] += acc_g[i].z; p0[3] += acc_g[i].w;
-                    float* p1 = sm + d + c * 4;
-                    p1[0] += acc_b[i].x; p1[1] += acc_b[i].y; p1[2] += acc_b[i].z; p1[3] += acc_b[i].w;
-                    float* p2 = sm + 2 * d + c * 4;
-                    p2[0] += acc_r[i].x; p2[1] += acc_r[i].y; p2[2] += acc_r[i].z; p2[3] += acc_r[i].w;
+                for (int q = 0; q < 8; ++q) {
+                    o[q] = rs * (g[i][q] - c1 - xh[i][q] * c2);
+                    dr[q] = o[q] * sc[q];
+                    acc_r[i][q] += dr[q];
                 }
+                if (ds) st8(ds + base + c * 8, o);
+                if (dr_c) st8(dr_c + base + c * 8, dr);
             }
         }
-        __syncthreads();
     }
+    // every warp parks its column sums in its own shared-memory slab (q-major, conflict-free) ...
+    float* slab = sm + (size_t)warp * 3 * d;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                slab[q * nv + c] = acc_g[i][q];
+                slab[d + q * nv + c] = acc_b[i][q];
+                slab[2 * d + q * nv + c] = acc_r[i][q];
+            }
+        }
+    }
+    __syncthreads();
+    // ... and the CTA adds the slabs in a fixed order
     float* mine = partials + (long long)blockIdx.x * 3 * d;
-    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) mine[i] = sm[i];
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kLnBwdWarps; ++w) a += sm[(size_t)w * 3 * d + i];
+        mine[i] = a;
+    }
 }
 
-// out[col] = sum_b partials[b][col]; 32 columns x 8 block-groups per CTA, fixed summation order
-__global__ void __launch_bounds__(256)
+// out[k][c*8+q] = sum_b partials[b][k*d + q*(d/8) + c]; 32 entries x 32 block-groups per CTA, fixed summation order
+__global__ void __launch_bounds__(1024)
 ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias_r) {
-    __shared__ float red[8][33];
+    __shared__ float red[32][33];
     const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
-    const int col = blockIdx.x * 32 + cx;
+    const int idx = blockIdx.x * 32 + cx;
     float a = 0.f;
-    if (col < 3 * d)
-        for (int b = gy; b < nblocks; b += 8) a += partials[(long long)b * 3 * d + col];
+    if (idx < 3 * d)
+        for (int b = gy; b < nblocks; b += 32) a += partials[(long long)b * 3 * d + idx];
     red[gy][cx] = a;
     __syncthreads();
-    if (gy == 0 && col < 3 * d) {
+    if (gy == 0 && idx < 3 * d) {
         float t = 0.f;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) t += red[g][cx];
-        if (col < d) { if (dgamma) dgamma[col] = t; }
-        else if (col < 2 * d) { if (dbeta) dbeta[col - d] = t; }
-        else { if (dbias_r) dbias_r[col - 2 * d] = t; }
+        for (int g = 0; g < 32; ++g) t += red[g][cx];
+        const int nv = d >> 3;
+        const int k = idx / d, r = idx % d, q = r / nv, c = r % nv;
+        const int col = c * 8 + q;
+        float* out = k == 0 ? dgamma : (k == 1 ? dbeta : dbias_r);
+        if (out) out[col] = t;
     }
 }
 
 template <typename TC>
 static int launch_ln_bwd(const float* dy, const float* s, const float* mean, const float* rstd, const float* gamma,
-                         float* ds, TC* dr_c, float* dgamma, float* dbeta, float* dbias_r, float* partials, int R, int d,
-                         float drop_p, const unsigned long long* rng_state, unsigned int site, cudaStream_t st) {
+                         float* ds, TC* dr_c, float* partials, int R, int d, float drop_p,
+                         const unsigned long long* rng_state, unsigned int site, cudaStream_t st) {
     const int rows = ln_bwd_rows_per_cta(R), blocks = ln_bwd_blocks(R);
-    const int nvl = (d / 4 + 31) / 32;
-    const size_t smem = (size_t)3 * d * sizeof(float);
+    const int nvl = (d / 8 + 31) / 32;
+    const size_t smem = (size_t)kLnBwdWarps * 3 * d * sizeof(float);
 #define LN_BWD_CASE(NVV)                                                                                        \
-    ln_bwd_kernel<NVV, TC><<<blocks, kLnWarps * 32, smem, st>>>(dy, s, mean, rstd, gamma, ds, dr_c, partials, R, d, rows, \
-                                                                 drop_p, rng_state, site)
-    if (nvl <= 1) LN_BWD_CASE(1);
-    else if (nvl <= 2) LN_BWD_CASE(2);
-    else if (nvl <= 4) LN_BWD_CASE(4);
-    else if (nvl <= 6) LN_BWD_CASE(6);
-    else LN_BWD_CASE(8);
+    {                                                                                                           \
+        auto kern = ln_bwd_kernel<NVV, TC>;                                                                     \
+        static bool once = false;                                                                               \
+        if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); once = true; } \
+        kern<<<blocks, kLnBwdWarps * 32, smem, st>>>(dy, s, mean, rstd, gamma, ds, dr_c, partials, R, d, rows, drop_p, \
+                                                     rng_state, site);                                          \
+    }
+    if (nvl <= 1) LN_BWD_CASE(1)
+    else if (nvl <= 2) LN_BWD_CASE(2)
+    else if (nvl <= 3) LN_BWD_CASE(3)
+    else LN_BWD_CASE(4)
 #undef LN_BWD_CASE
-    if (int e = check_launch("vct_ln_residual_bwd")) return e;
-    ln_bwd_reduce_kernel<<<(3 * d + 31) / 32, 256, 0, st>>>(partials, blocks, d, dgamma, dbeta, dbias_r);
-    return check_launch("vct_ln_residual_bwd(reduce)");
+    return check_launch("vct_ln_residual_bwd");
+}
+
+extern "C" int vct_ln_bwd_reduce(const float* partials, int R, int d, float* dgamma, float* dbeta, float* dbias_r,
+                                 vct_stream_t stream) {
+    VCT_REQUIRE(partials && d % 8 == 0 && d <= 1024 && R > 0, "vct_ln_bwd_reduce: bad arguments");
+    ln_bwd_reduce_kernel<<<(3 * d + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partials, ln_bwd_blocks(R), d, dgamma, dbeta,
+                                                                              dbias_r);
+    return check_launch("vct_ln_bwd_reduce");
 }
 
 extern "C" int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, const float* rstd,
@@ -333,24 +362,30 @@ extern "C" int vct_ln_residual_bwd(const float* dy, const float* s, const float*
                                    float drop_p, const unsigned long long* rng_state, unsigned int site,
                                    vct_stream_t stream) {
     (void)counter;   // kept in the ABI; the two-kernel reduction needs no counter
-    VCT_REQUIRE(d % 4 == 0 && d <= 1024 && R > 0, "vct_ln_residual_bwd: need d %% 4 == 0, d <= 1024 (d=%d)", d);
+    VCT_REQUIRE(d % 8 == 0 && d <= 1024 && R > 0, "vct_ln_residual_bwd: need d %% 8 == 0, d <= 1024 (d=%d)", d);
     VCT_REQUIRE(dy && s && mean && rstd && gamma && partials, "vct_ln_residual_bwd: null input");
+    int e;
     if (dr_dtype == VCT_BF16)
-        return launch_ln_bwd<__nv_bfloat16>(dy, s, mean, rstd, gamma, ds, (__nv_bfloat16*)dr_c, dgamma, dbeta, dbias_r,
-                                            partials, R, d, drop_p, rng_state, site, (cudaStream_t)stream);
-    return launch_ln_bwd<float>(dy, s, mean, rstd, gamma, ds, (float*)dr_c, dgamma, dbeta, dbias_r, partials, R, d, drop_p,
-                                rng_state, site, (cudaStream_t)stream);
+        e = launch_ln_bwd<__nv_bfloat16>(dy, s, mean, rstd, gamma, ds, (__nv_bfloat16*)dr_c, partials, R, d, drop_p,
+                                         rng_state, site, (cudaStream_t)stream);
+    else
+        e = launch_ln_bwd<float>(dy, s, mean, rstd, gamma, ds, (float*)dr_c, partials, R, d, drop_p, rng_state, site,
+                                 (cudaStream_t)stream);
+    if (e) return e;
+    // all three outputs NULL: the caller runs vct_ln_bwd_reduce itself (e.g. on another stream)
+    if (dgamma == nullptr && dbeta == nullptr && dbias_r == nullptr) return 0;
+    return vct_ln_bwd_reduce(partials, R, d, dgamma, dbeta, dbias_r, stream);
 }
 
 // ------------------------------------------------------------------------------------------------
-// embedding
+// embedding (8 elements per thread: one Philox draw covers them)
 // ------------------------------------------------------------------------------------------------
 template <typename TC>
 __global__ void embed_fwd_kernel(const long long* __restrict__ ids, long long ids_ld, const float* __restrict__ E,
                                  const float* __restrict__ pos, float* __restrict__ x, TC* __restrict__ x_c, int B,
                                  int S, int d, int V, int pos_offset, float drop_p,
                                  const unsigned long long* __restrict__ rng_state, unsigned int site) {
-    const int nv = d >> 2;
+    const int nv = d >> 3;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * S * nv) return;
     const int c = (int)(gid % nv);
@@ -359,18 +394,21 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, long long id
     long long id = ids[(long long)b * ids_ld + sidx];
     id = id < 0 ? 0 : (id >= V ? V - 1 : id);
     const Rng rng = make_rng(rng_state, drop_p);
-    float4 e = ld4(E + id * d + c * 4), p = ld4(pos + (long long)(sidx + pos_offset) * d + c * 4);
-    float4 sc = dropout_scale4(rng, site, (unsigned long long)gid);
-    float4 o = make_float4((e.x + p.x) * sc.x, (e.y + p.y) * sc.y, (e.z + p.z) * sc.z, (e.w + p.w) * sc.w);
-    if (x) st4(x + row * d + c * 4, o);
-    if (x_c) st4(x_c + row * d + c * 4, o);
+    float e[8], p[8], sc[8], o[8];
+    ld8(E + id * d + c * 8, e);
+    ld8(pos + (long long)(sidx + pos_offset) * d + c * 8, p);
+    dropout_scale8(rng, site, (unsigned long long)gid, sc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) o[q] = (e[q] + p[q]) * sc[q];
+    if (x) st8(x + row * d + c * 8, o);
+    if (x_c) st8(x_c + row * d + c * 8, o);
 }
 
 extern "C" int vct_embed_fwd(const long long* ids, long long ids_ld, const float* E, const float* pos, float* x,
                              void* x_c, int x_c_dtype, int B, int S, int d, int V, int pos_offset, float drop_p,
                              const unsigned long long* rng_state, unsigned int site, vct_stream_t stream) {
-    VCT_REQUIRE(d % 4 == 0 && B > 0 && S > 0, "vct_embed_fwd: need d %% 4 == 0 and non-empty input");
-    long long n = (long long)B * S * (d / 4);
+    VCT_REQUIRE(d % 8 == 0 && B > 0 && S > 0, "vct_embed_fwd: need d %% 8 == 0 and non-empty input");
+    long long n = (long long)B * S * (d / 8);
     int blocks = (int)((n + 255) / 256);
     if (x_c_dtype == VCT_BF16)
         embed_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, E, pos, x, (__nv_bfloat16*)x_c, B, S, d,
@@ -384,7 +422,7 @@ extern "C" int vct_embed_fwd(const long long* ids, long long ids_ld, const float
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, long long ids_ld, const float* __restrict__ dx,
                                  float* __restrict__ dE, int B, int S, int d, int V, int pad_id, float drop_p,
                                  const unsigned long long* __restrict__ rng_state, unsigned int site) {
-    const int nv = d >> 2;
+    const int nv = d >> 3;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * S * nv) return;
     const int c = (int)(gid % nv);
@@ -393,20 +431,19 @@ __global__ void embed_bwd_kernel(const long long* __restrict__ ids, long long id
     const long long id = ids[(long long)b * ids_ld + sidx];
     if (id == pad_id || id < 0 || id >= V) return;
     const Rng rng = make_rng(rng_state, drop_p);
-    float4 g = ld4(dx + row * d + c * 4);
-    float4 sc = dropout_scale4(rng, site, (unsigned long long)gid);
-    float* dst = dE + id * d + c * 4;
-    atomicAdd(dst + 0, g.x * sc.x);
-    atomicAdd(dst + 1, g.y * sc.y);
-    atomicAdd(dst + 2, g.z * sc.z);
-    atomicAdd(dst + 3, g.w * sc.w);
+    float g[8], sc[8];
+    ld8(dx + row * d + c * 8, g);
+    dropout_scale8(rng, site, (unsigned long long)gid, sc);
+    float* dst = dE + id * d + c * 8;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) atomicAdd(dst + q, g[q] * sc[q]);
 }
 
 extern "C" int vct_embed_bwd(const long long* ids, long long ids_ld, const float* dx, float* dE, int B, int S, int d,
                              int V, int pad_id, float drop_p, const unsigned long long* rng_state, unsigned int site,
                              vct_stream_t stream) {
-    VCT_REQUIRE(d % 4 == 0 && B > 0 && S > 0, "vct_embed_bwd: need d %% 4 == 0 and non-empty input");
-    long long n = (long long)B * S * (d / 4);
+    VCT_REQUIRE(d % 8 == 0 && B > 0 && S > 0, "vct_embed_bwd: need d %% 8 == 0 and non-empty input");
+    long long n = (long long)B * S * (d / 8);
     int blocks = (int)((n + 255) / 256);
     embed_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, dx, dE, B, S, d, V, pad_id, drop_p,
                                                                rng_state, site);
@@ -573,18 +610,18 @@ extern "C" int vct_argmax_append(const float* logits, long long ld_logits, int B
 __global__ void dropout_mask_kernel(unsigned char* out, long long n, float p, const unsigned long long* rng_state,
                                     unsigned int site) {
     const Rng rng = make_rng(rng_state, p);
-    long long i4 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i4 * 4 >= n) return;
-    float4 sc = dropout_scale4(rng, site, (unsigned long long)i4);
-    float e[4] = {sc.x, sc.y, sc.z, sc.w};
-    for (int k = 0; k < 4; ++k)
-        if (i4 * 4 + k < n) out[i4 * 4 + k] = e[k] != 0.f;
+    long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i8 * 8 >= n) return;
+    float sc[8];
+    dropout_scale8(rng, site, (unsigned long long)i8, sc);
+    for (int k = 0; k < 8; ++k)
+        if (i8 * 8 + k < n) out[i8 * 8 + k] = sc[k] != 0.f;
 }
 
 extern "C" int vct_dropout_mask(unsigned char* out, long long n, float drop_p, const unsigned long long* rng_state,
                                 unsigned int site, vct_stream_t stream) {
     VCT_REQUIRE(n > 0, "vct_dropout_mask: empty");
-    long long n4 = (n + 3) / 4;
-    dropout_mask_kernel<<<(int)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, drop_p, rng_state, site);
+    long long n8 = (n + 7) / 8;
+    dropout_mask_kernel<<<(int)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, drop_p, rng_state, site);
     return check_launch("vct_dropout_mask");
 }

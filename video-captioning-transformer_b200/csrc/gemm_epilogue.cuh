@@ -36,7 +36,9 @@ inline Epilogue make_epilogue(const vct_gemm_args* a) {
                (a->addend == nullptr || (a->ld_addend % 4 == 0 && al16(a->addend))) &&
                (a->aux == nullptr || (a->ld_aux % 4 == 0 && al16(a->aux))) && (a->bias == nullptr || al16(a->bias)) &&
                (a->row_table == nullptr || (al16(a->row_table) && a->N % 4 == 0)) &&
-               (a->act == VCT_ACT_NONE || a->N % 4 == 0);
+               (a->act == VCT_ACT_NONE || (a->N % 8 == 0 && a->ldc % 8 == 0 && (a->C2 == nullptr || a->ldc2 % 8 == 0) &&
+                                           (a->aux == nullptr || a->ld_aux % 8 == 0) &&
+                                           (a->addend == nullptr || a->ld_addend % 8 == 0)));
     return e;
 }
 
@@ -78,11 +80,10 @@ __device__ __noinline__ void epilogue_scalar(const Epilogue& e, const Rng& rng, 
     }
 }
 
-// acc = accumulators of row m, columns n..n+3 (n % 4 == 0).  Rows >= M / columns >= N are dropped.
-template <int ACT>
-__device__ __forceinline__ void epilogue_store4(const Epilogue& e, const Rng& rng, int m, int n, float4 acc) {
+// plain epilogue: acc = accumulators of row m, columns n..n+3 (n % 4 == 0).  Rows >= M / columns >= N are dropped.
+__device__ __forceinline__ void epilogue_plain4(const Epilogue& e, const Rng& rng, int m, int n, float4 acc) {
     if (m >= e.M || n >= e.N) return;
-    if (!e.vec_ok || n + 4 > e.N) { epilogue_scalar<ACT>(e, rng, m, n, acc); return; }
+    if (!e.vec_ok || n + 4 > e.N) { epilogue_scalar<VCT_ACT_NONE>(e, rng, m, n, acc); return; }
     if (e.bias) {
         const float4 b = ld4(e.bias + n);
         acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
@@ -91,29 +92,79 @@ __device__ __forceinline__ void epilogue_store4(const Epilogue& e, const Rng& rn
         const float4 t = ld4(e.row_table + (long long)(m % e.row_period) * e.N + n);
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
-    if (ACT != VCT_ACT_NONE) {
-        float4 sc = make_float4(1.f, 1.f, 1.f, 1.f);
-        if (rng.p > 0.f)    // vec_ok implies N % 4 == 0 for activation epilogues, so (m * N + n) / 4 is exact
-            sc = dropout_scale4(rng, e.site, ((unsigned long long)m * (unsigned long long)e.N + (unsigned long long)n) >> 2);
-        if (ACT == VCT_ACT_GELU_FWD) {
-            store4(e.C, e.c_dtype, (long long)m * e.ldc + n, acc);
-            if (e.C2)
-                store4(e.C2, e.c2_dtype, (long long)m * e.ldc2 + n,
-                       make_float4(gelu_f(acc.x) * sc.x, gelu_f(acc.y) * sc.y, gelu_f(acc.z) * sc.z, gelu_f(acc.w) * sc.w));
-            return;
-        }
-        const long long ao = (long long)m * e.ld_aux + n;
-        const float4 z = e.aux_dtype == VCT_BF16 ? ld4(reinterpret_cast<const __nv_bfloat16*>(e.aux) + ao)
-                                                 : ld4(reinterpret_cast<const float*>(e.aux) + ao);
-        acc.x *= dgelu_f(z.x) * sc.x; acc.y *= dgelu_f(z.y) * sc.y;
-        acc.z *= dgelu_f(z.z) * sc.z; acc.w *= dgelu_f(z.w) * sc.w;
-    }
     if (e.addend) {
         const float4 ad = ld4(e.addend + (long long)m * e.ld_addend + n);
         acc.x += ad.x; acc.y += ad.y; acc.z += ad.z; acc.w += ad.w;
     }
     store4(e.C, e.c_dtype, (long long)m * e.ldc + n, acc);
     if (e.C2) store4(e.C2, e.c2_dtype, (long long)m * e.ldc2 + n, acc);
+}
+
+// a0, a1 = accumulators of row m, columns n..n+7 (n % 8 == 0): one Philox draw covers the 8 dropout decisions
+template <int ACT>
+__device__ __forceinline__ void epilogue_store8(const Epilogue& e, const Rng& rng, int m, int n, float4 a0, float4 a1) {
+    if (ACT == VCT_ACT_NONE) {
+        epilogue_plain4(e, rng, m, n, a0);
+        epilogue_plain4(e, rng, m, n + 4, a1);
+        return;
+    }
+    if (m >= e.M || n >= e.N) return;
+    if (!e.vec_ok || n + 8 > e.N) {
+        epilogue_scalar<ACT>(e, rng, m, n, a0);
+        if (n + 4 < e.N) epilogue_scalar<ACT>(e, rng, m, n + 4, a1);
+        return;
+    }
+    float v[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+    if (e.bias) {
+        float b[8];
+        ld8(e.bias + n, b);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] += b[q];
+    }
+    if (e.row_table) {
+        float t[8];
+        ld8(e.row_table + (long long)(m % e.row_period) * e.N + n, t);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] += t[q];
+    }
+    float sc[8];
+    dropout_scale8(rng, e.site, ((unsigned long long)m * (unsigned long long)e.N + (unsigned long long)n) >> 3, sc);
+    if (ACT == VCT_ACT_GELU_FWD) {
+        const long long o = (long long)m * e.ldc + n;
+        if (e.c_dtype == VCT_BF16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
+        else st8(reinterpret_cast<float*>(e.C) + o, v);
+        if (e.C2) {
+            float h[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) h[q] = gelu_f(v[q]) * sc[q];
+            const long long o2 = (long long)m * e.ldc2 + n;
+            if (e.c2_dtype == VCT_BF16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, h);
+            else st8(reinterpret_cast<float*>(e.C2) + o2, h);
+        }
+        return;
+    }
+    {   // GELU backward
+        float z[8];
+        const long long ao = (long long)m * e.ld_aux + n;
+        if (e.aux_dtype == VCT_BF16) ld8(reinterpret_cast<const __nv_bfloat16*>(e.aux) + ao, z);
+        else ld8(reinterpret_cast<const float*>(e.aux) + ao, z);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] *= dgelu_f(z[q]) * sc[q];
+    }
+    if (e.addend) {
+        float ad[8];
+        ld8(e.addend + (long long)m * e.ld_addend + n, ad);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) v[q] += ad[q];
+    }
+    const long long o = (long long)m * e.ldc + n;
+    if (e.c_dtype == VCT_BF16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
+    else st8(reinterpret_cast<float*>(e.C) + o, v);
+    if (e.C2) {
+        const long long o2 = (long long)m * e.ldc2 + n;
+        if (e.c2_dtype == VCT_BF16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, v);
+        else st8(reinterpret_cast<float*>(e.C2) + o2, v);
+    }
 }
 
 }  // namespace vct

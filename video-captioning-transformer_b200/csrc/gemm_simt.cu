@@ -101,10 +101,8 @@ gemm_simt_kernel(const T* __restrict__ A, long long lda, const T* __restrict__ B
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int m = m0 + ty * 8 + i;
-#pragma unroll
-        for (int jg = 0; jg < 2; ++jg)
-            epilogue_store4<ACT>(epi, rng, m, n0 + tx * 8 + jg * 4,
-                                 make_float4(acc[i][jg * 4 + 0], acc[i][jg * 4 + 1], acc[i][jg * 4 + 2], acc[i][jg * 4 + 3]));
+        epilogue_store8<ACT>(epi, rng, m, n0 + tx * 8, make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]),
+                             make_float4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]));
     }
 }
 

@@ -186,10 +186,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int nb = n0 + c * 16;
             if (m < epi.M && nb < epi.N) {
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    epilogue_store4<ACT>(epi, rng, m, nb + g * 4,
-                                         make_float4(__uint_as_float(r[g * 4 + 0]), __uint_as_float(r[g * 4 + 1]),
-                                                     __uint_as_float(r[g * 4 + 2]), __uint_as_float(r[g * 4 + 3])));
+                for (int g = 0; g < 2; ++g)
+                    epilogue_store8<ACT>(epi, rng, m, nb + g * 8,
+                                         make_float4(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]),
+                                                     __uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
+                                         make_float4(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]),
+                                                     __uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
             }
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

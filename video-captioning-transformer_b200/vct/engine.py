@@ -235,9 +235,15 @@ class CaptionEngine:
                  self.cdt, s_out, mean, rstd, R, self.dims.d, p, self.rng_state.data_ptr(), site)
 
     def _ln_bwd(self, plan: Plan, tag, dy, s, mean, rstd, gname, bname, ds, dr_c, dbias, R, p, site, ws):
+        # main lane: ds / dr and the per-CTA column partials; side lane: the partials -> dgamma, dbeta, dbias
+        # reduction, which nothing before Adam consumes (own partials buffer per call site)
+        n = int(self.lib.vct_ln_bwd_workspace_floats(R, self.dims.d))
+        part = self._scratch(ws, "ln_partials:" + tag, 1, n, torch.float32).data_ptr()
         plan.add("vct_ln_residual_bwd:" + tag, self.lib.vct_ln_residual_bwd, dy, s, mean, rstd, self._p(gname), ds, dr_c,
-                 self.cdt, self._g(gname), self._g(bname), dbias, ws.partials.data_ptr(), self.counters.data_ptr(),
-                 R, self.dims.d, p, self.rng_state.data_ptr(), site)
+                 self.cdt, None, None, None, part, None, R, self.dims.d, p, self.rng_state.data_ptr(), site)
+        with self._side(plan):
+            plan.add("vct_ln_bwd_reduce:" + tag, self.lib.vct_ln_bwd_reduce, part, R, self.dims.d, self._g(gname),
+                     self._g(bname), dbias)
 
     def _attn(self, plan: Plan, tag, bwd, *, B, H, Lq, Lk, q, q_ld, k, k_ld, v, v_ld, o, o_ld, key_pad=None, causal=0,
               p=0.0, site=0, probs=None, d_o=None, do_ld=0, dq=None, dq_ld=0, dk=None, dk_ld=0, dv=None, dv_ld=0,
