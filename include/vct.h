@@ -84,6 +84,9 @@ typedef struct {
     const void* aux; int aux_dtype; long long ld_aux;/* z for VCT_ACT_GELU_BWD */
     float drop_p; const unsigned long long* rng_state; unsigned int site;
     int impl;
+    /* optional split-K workspace (fp32, caller-allocated): lets the tcgen05 path split a long K (e.g. the
+     * generator dgrad, K = vocab) over several CTAs and reduce deterministically in a second kernel */
+    void* splitk_ws; long long splitk_ws_floats;
 } vct_gemm_args;
 
 int vct_gemm(const vct_gemm_args* args, vct_stream_t stream);

@@ -76,7 +76,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, Epilogue epi) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K, Epilogue epi,
+               float* __restrict__ splitk_ws, long long ldw) {
     constexpr uint32_t kBBytes = BLOCK_N * BLOCK_K * 2;
     constexpr uint32_t kStageBytes = kABytes + kBBytes;
     extern __shared__ __align__(1024) unsigned char smem_raw[];
@@ -88,7 +89,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
-    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    // split-K: blockIdx.z owns the k-blocks [kb0, kb0 + num_kb)
+    const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const int kb_per = (total_kb + (int)gridDim.z - 1) / (int)gridDim.z;
+    const int kb0 = (int)blockIdx.z * kb_per;
+    const int num_kb = max(0, min(kb_per, total_kb - kb0));
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -121,7 +126,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const uint32_t full = smem_u32(&full_bar[s]);
                 mbar_expect_tx(full, kStageBytes);
                 const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
-                const int k0 = kb * BLOCK_K;
+                const int k0 = (kb0 + kb) * BLOCK_K;
                 if (!A_MN) {
                     tma_load_2d(sa, &tmA, k0, m0, full);
                 } else {
@@ -164,43 +169,83 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
     } else {
         // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
+        // phase 1: TMEM -> registers -> shared memory (the operand ring is free once the accumulator is complete)
+        // phase 2: shared memory -> fused epilogue -> global, with the threads remapped so that a warp touches
+        //          contiguous global memory (the TMEM layout gives each thread a ROW, which would make every
+        //          global access a 16-byte piece of a different cache line)
+        constexpr int RS = BLOCK_N + 4;                       // padded row stride (floats): conflict-free 16 B stores
+        float* stage = reinterpret_cast<float*>(smem);
         const int q = warp & 3;
-        const int m = m0 + q * 32 + lane;
+        const int row = q * 32 + lane;
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const Rng rng = make_rng(epi.rng_state, ACT != VCT_ACT_NONE ? epi.drop_p : 0.f);
-        // 16 accumulator columns per TMEM load, 4 column groups per iteration: keeps the epilogue code small
-        // (instruction-cache footprint dominates the many ~5 us GEMMs of a step)
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 16; ++c) {
             uint32_t r[16];
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                  "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                : "r"(taddr)
-                : "memory");
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            const int nb = n0 + c * 16;
-            if (m < epi.M && nb < epi.N) {
+            if (num_kb > 0) {
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                    : "r"(taddr)
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            } else {
 #pragma unroll
-                for (int g = 0; g < 2; ++g)
-                    epilogue_store8<ACT>(epi, rng, m, nb + g * 8,
-                                         make_float4(__uint_as_float(r[g * 8 + 0]), __uint_as_float(r[g * 8 + 1]),
-                                                     __uint_as_float(r[g * 8 + 2]), __uint_as_float(r[g * 8 + 3])),
-                                         make_float4(__uint_as_float(r[g * 8 + 4]), __uint_as_float(r[g * 8 + 5]),
-                                                     __uint_as_float(r[g * 8 + 6]), __uint_as_float(r[g * 8 + 7])));
+                for (int i = 0; i < 16; ++i) r[i] = 0u;        // empty K range (split-K tail): contributes zeros
             }
+            uint4* dst = reinterpret_cast<uint4*>(stage + row * RS + c * 16);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
+        const Rng rng = make_rng(epi.rng_state, ACT != VCT_ACT_NONE ? epi.drop_p : 0.f);
+        const int t = threadIdx.x - 64;
+        constexpr int CG = BLOCK_N / 8;                       // 8-column groups per row
+#pragma unroll 2
+        for (int id = t; id < BLOCK_M * CG; id += 128) {
+            const int rr = id / CG, cg = id % CG;
+            const int m = m0 + rr, n = n0 + cg * 8;
+            if (m >= epi.M || n >= epi.N) continue;
+            const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * RS + cg * 8);
+            const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * RS + cg * 8 + 4);
+            if (splitk_ws != nullptr) {
+                // raw partial sums; vct's split-K reduce kernel applies the epilogue
+                float* w = splitk_ws + ((long long)blockIdx.z * epi.M + m) * ldw + n;
+                *reinterpret_cast<float4*>(w) = a0;
+                *reinterpret_cast<float4*>(w + 4) = a1;
+            } else {
+                epilogue_store8<ACT>(epi, rng, m, n, a0, a1);
+            }
+        }
     }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
     }
+}
+
+// split-K second pass: sum the partial tiles in a fixed order and apply the fused epilogue
+template <int ACT>
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long ldw, Epilogue epi) {
+    const int cg_per_row = (epi.N + 7) / 8;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (id >= (long long)epi.M * cg_per_row) return;
+    const int m = (int)(id / cg_per_row), n = (int)(id % cg_per_row) * 8;
+    float4 a0 = make_float4(0.f, 0.f, 0.f, 0.f), a1 = a0;
+    for (int z = 0; z < splits; ++z) {
+        const float* w = ws + ((long long)z * epi.M + m) * ldw + n;
+        const float4 b0 = *reinterpret_cast<const float4*>(w), b1 = *reinterpret_cast<const float4*>(w + 4);
+        a0.x += b0.x; a0.y += b0.y; a0.z += b0.z; a0.w += b0.w;
+        a1.x += b1.x; a1.y += b1.y; a1.z += b1.z; a1.w += b1.w;
+    }
+    const Rng rng = make_rng(epi.rng_state, ACT != VCT_ACT_NONE ? epi.drop_p : 0.f);
+    epilogue_store8<ACT>(epi, rng, m, n, a0, a1);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -267,7 +312,7 @@ int get_map(const void* ptr, long long inner, long long outer, long long ld, int
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int ACT>
-int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
     constexpr int kStage = kABytes + BLOCK_N * BLOCK_K * 2;
     constexpr int STAGES = kSmemBudget / kStage > 8 ? 8 : kSmemBudget / kStage;
     constexpr int smem = STAGES * kStage + 1024;
@@ -277,28 +322,36 @@ int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tm
         VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         once = true;
     }
-    dim3 grid((a->N + BLOCK_N - 1) / BLOCK_N, (a->M + BLOCK_M - 1) / BLOCK_M);
-    kern<<<grid, kThreads, smem, st>>>(tmA, tmB, a->K, make_epilogue(a));
-    return check_launch("vct_gemm(tcgen05)");
+    dim3 grid((a->N + BLOCK_N - 1) / BLOCK_N, (a->M + BLOCK_M - 1) / BLOCK_M, splits);
+    const Epilogue epi = make_epilogue(a);
+    const long long ldw = ((long long)a->N + 7) / 8 * 8;
+    kern<<<grid, kThreads, smem, st>>>(tmA, tmB, a->K, epi, splits > 1 ? (float*)a->splitk_ws : nullptr, ldw);
+    if (int e = check_launch("vct_gemm(tcgen05)")) return e;
+    if (splits > 1) {
+        const long long items = (long long)a->M * ((a->N + 7) / 8);
+        splitk_reduce_kernel<ACT><<<(unsigned)((items + 255) / 256), 256, 0, st>>>((const float*)a->splitk_ws, splits, ldw, epi);
+        return check_launch("vct_gemm(tcgen05 split-K reduce)");
+    }
+    return 0;
 }
 
 template <int BLOCK_N>
-int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
     // activation epilogues exist where the path uses them: GELU forward on x W1^T (K-major, K-major) and GELU
     // backward on dY W2 (K-major, MN-major); everything else carries the small plain epilogue
     if (a->act == VCT_ACT_GELU_FWD) {
         VCT_REQUIRE(!a->a_trans && !a->b_trans, "vct_gemm(tcgen05): GELU_FWD is built for a_trans = b_trans = 0");
-        return launch<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, st);
+        return launch<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, splits, st);
     }
     if (a->act == VCT_ACT_GELU_BWD) {
         VCT_REQUIRE(!a->a_trans, "vct_gemm(tcgen05): GELU_BWD is built for a_trans = 0");
-        if (a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_GELU_BWD>(a, tmA, tmB, st);
-        return launch<BLOCK_N, false, false, VCT_ACT_GELU_BWD>(a, tmA, tmB, st);
+        if (a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
+        return launch<BLOCK_N, false, false, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
     }
-    if (!a->a_trans && !a->b_trans) return launch<BLOCK_N, false, false, VCT_ACT_NONE>(a, tmA, tmB, st);
-    if (!a->a_trans && a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_NONE>(a, tmA, tmB, st);
-    if (a->a_trans && !a->b_trans) return launch<BLOCK_N, true, false, VCT_ACT_NONE>(a, tmA, tmB, st);
-    return launch<BLOCK_N, true, true, VCT_ACT_NONE>(a, tmA, tmB, st);
+    if (!a->a_trans && !a->b_trans) return launch<BLOCK_N, false, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    if (!a->a_trans && a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    if (a->a_trans && !a->b_trans) return launch<BLOCK_N, true, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    return launch<BLOCK_N, true, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
 }
 
 }  // namespace
@@ -310,18 +363,36 @@ int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     VCT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "vct_gemm(tcgen05): lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
     VCT_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
                 "vct_gemm(tcgen05): operands must be 16-byte aligned");
-    // tile width: the widest N tile that still yields about one wave of CTAs
+    // Tile width and split-K factor from a small cost model (cycles): these GEMMs are bounded by the fixed cost of
+    // a CTA (launch, TMEM alloc, first TMA round trip, epilogue ~ 9k cycles) and by L2 -> SM operand traffic
+    // (~42 B/clk/SM when all SMs pull), not by the tensor pipe, so fewer / fuller waves win.
     const long long tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M;
-    int bn = 256;
-    while (bn > 64 && tiles_m * ((a->N + bn - 1) / bn) < kNumSMs) bn >>= 1;
+    const int total_kb = (a->K + BLOCK_K - 1) / BLOCK_K;
+    const long long ldw = ((long long)a->N + 7) / 8 * 8;
+    int bn = 64, splits = 1;
+    double best = 1e30;
+    for (int cand : {256, 128, 64}) {
+        const long long tiles = tiles_m * ((a->N + cand - 1) / cand);
+        const double cyc_kb = fmax(2.0 * cand, (16384.0 + 128.0 * cand) / 42.0);
+        for (int sp : {1, 2, 3, 4, 5, 6, 8}) {
+            if (sp > 1 && (a->splitk_ws == nullptr || total_kb < 16 * sp ||
+                           (long long)sp * a->M * ldw > a->splitk_ws_floats)) continue;
+            const long long ctas = tiles * sp;
+            const double waves = (double)((ctas + kNumSMs - 1) / kNumSMs);
+            const int kbs = (total_kb + sp - 1) / sp;
+            double t = waves * (9000.0 + kbs * cyc_kb);
+            if (sp > 1) t += 8000.0 + (double)sp * a->M * a->N * 4.0 / 3000.0;
+            if (t < best) { best = t; bn = cand; splits = sp; }
+        }
+    }
     CUtensorMap tmA, tmB;
     if (!a->a_trans) { if (int e = get_map(a->A, a->K, a->M, a->lda, BLOCK_K, BLOCK_M, &tmA)) return e; }
     else             { if (int e = get_map(a->A, a->M, a->K, a->lda, 64, BLOCK_K, &tmA)) return e; }
     if (!a->b_trans) { if (int e = get_map(a->B, a->K, a->N, a->ldb, BLOCK_K, bn, &tmB)) return e; }
     else             { if (int e = get_map(a->B, a->N, a->K, a->ldb, 64, BLOCK_K, &tmB)) return e; }
-    if (bn == 256) return dispatch_major<256>(a, tmA, tmB, st);
-    if (bn == 128) return dispatch_major<128>(a, tmA, tmB, st);
-    return dispatch_major<64>(a, tmA, tmB, st);
+    if (bn == 256) return dispatch_major<256>(a, tmA, tmB, splits, st);
+    if (bn == 128) return dispatch_major<128>(a, tmA, tmB, splits, st);
+    return dispatch_major<64>(a, tmA, tmB, splits, st);
 }
 
 }  // namespace vct

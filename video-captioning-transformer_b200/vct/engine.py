@@ -222,6 +222,10 @@ class CaptionEngine:
         g.aux, g.aux_dtype, g.ld_aux = aux, self.cdt, ld_aux
         g.drop_p, g.rng_state, g.site = drop_p, self.rng_state.data_ptr(), site
         g.impl = self.gemm_impl
+        ws = getattr(plan, "ws", None)
+        if ws is not None and getattr(ws, "splitk", None) is not None:
+            sk = ws.splitk[1 if plan.lane else 0]           # one workspace per lane: the lanes run concurrently
+            g.splitk_ws, g.splitk_ws_floats = sk.data_ptr(), sk.numel()
         plan.keep.append(g)
         plan.add("vct_gemm:" + tag, self.lib.vct_gemm, C.byref(g))
 
@@ -359,6 +363,9 @@ class CaptionEngine:
             self._buf(ws, "partials", (nws,), f32)
             self._buf(ws, "partials_side", (nws,), f32)
             ws.scratch = {}
+        # split-K workspaces (fp32 partial tiles) for long-K GEMMs, one per lane
+        ws.splitk = [torch.empty(8 * max(Re, Rd) * max(d, 8), dtype=f32, device=self.device) for _ in range(2)] \
+            if self.gemm_impl == L.GEMM_TCGEN05 else None
         ws.plans = {}
         self._ws[key] = ws
         return ws
@@ -480,6 +487,7 @@ class CaptionEngine:
         key = ("fwd", fused_grad, part, with_loss)
         if key not in ws.plans:
             p = Plan()
+            p.ws = ws
             pd = float(self.dims.dropout) if ws.training else 0.0
             if part == "all":
                 self._build_encoder(p, ws, pd)
@@ -490,6 +498,7 @@ class CaptionEngine:
     def plan_encode(self, ws) -> Plan:
         if "encode" not in ws.plans:
             p = Plan()
+            p.ws = ws
             self._build_encoder(p, ws, float(self.dims.dropout) if ws.training else 0.0)
             ws.plans["encode"] = p
         return ws.plans["encode"]
@@ -506,6 +515,7 @@ class CaptionEngine:
         if not ws.training:
             raise RuntimeError("backward needs a training workspace")
         p = Plan()
+        p.ws = ws
         if part in ("all", "dec"):
             self._build_decoder_bwd(p, ws, sce_first)
         if part in ("all", "enc"):

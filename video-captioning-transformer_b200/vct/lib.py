@@ -37,6 +37,7 @@ class GemmArgs(C.Structure):
         ("aux", vp), ("aux_dtype", i32), ("ld_aux", ll),
         ("drop_p", f32), ("rng_state", vp), ("site", u32),
         ("impl", i32),
+        ("splitk_ws", vp), ("splitk_ws_floats", ll),
     ]
 
 
