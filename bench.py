@@ -235,6 +235,12 @@ def main():
     xd, vd, td = x.to(dev), vm.to(dev), tok.to(dev)
     xh, vh, th = x.pin_memory(), vm.pin_memory(), tok.pin_memory()
 
+    verbose = os.environ.get("VCT_BENCH_VERBOSE") == "1"
+
+    def note(msg):
+        if verbose:
+            print(f"[bench rank {rank}] {msg}", file=sys.stderr, flush=True)
+
     def sync_all():
         torch.cuda.synchronize()
         if world > 1:
@@ -242,9 +248,13 @@ def main():
             torch.cuda.synchronize()
 
     # ---- warm-up (also builds plans / captures the graph: needs >= 3 steps) -------------------------
-    for _ in range(max(args.warmup, 3)):
+    note("model built")
+    for i in range(max(args.warmup, 3)):
         trainer.step(xd, vd, td)
+        torch.cuda.synchronize()
+        note(f"warm-up step {i} done")
     sync_all()
+    note("warm-up done")
     # ---- value: device-resident inputs ----------------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
@@ -263,6 +273,7 @@ def main():
     ms_total = float(ms.item())
     launches = eng.launches - launches0
     final_loss = float(loss.item())
+    note("timed region done")
     # ---- e2e: pinned host inputs, H2D + loss read-back every step -----------------------------------
     sync_all()
     t0 = time.perf_counter()
@@ -273,6 +284,7 @@ def main():
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    note("e2e done")
     clocks = sampler.stop() if rank == 0 else None
     h2d = x.numel() * 4 + vm.numel() + tok.numel() * 8
     # ---- roofline of the dominant kernel (rank 0): per-launch CUDA-event times of one eager step ------

@@ -394,7 +394,8 @@ def test_argmax_append_ties_and_end_flags(lib):
 
 # ---- tcgen05 GEMM (TMA + UMMA, bf16 operands, fp32 TMEM accumulators) ---------------------------------
 TC_SHAPES = [(128, 256, 64), (128, 64, 128), (256, 512, 768), (1280, 768, 768), (832, 2304, 768), (200, 136, 72),
-             (64, 96, 40), (1280, 2048, 768), (768, 2048, 1280), (300, 30522, 96), (1280, 768, 30522)]
+             (64, 96, 40), (1280, 2048, 768), (768, 2048, 1280), (300, 30522, 96), (1280, 768, 30522),
+             (30522, 768, 200), (5000, 2000, 136)]
 
 
 @pytest.mark.parametrize("a_trans,b_trans", [(0, 0), (0, 1), (1, 0), (1, 1)])

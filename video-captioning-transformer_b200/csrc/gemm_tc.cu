@@ -14,6 +14,7 @@
 // transposed copies.  Out-of-bounds rows / K tails are zero-filled by TMA.
 #include <cuda.h>
 
+#include <cstdlib>
 #include <mutex>
 #include <unordered_map>
 
@@ -229,6 +230,172 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Persistent variant for GEMMs with several tiles per SM (the generator forward / weight gradient):
+// grid = #SMs, every CTA walks tiles round-robin; two 256-column TMEM accumulators let the epilogue of tile i
+// (TMEM -> smem staging -> coalesced global stores, in 64-column chunks) overlap the TMA/MMA main loop of
+// tile i+1, and the barrier / TMEM / descriptor setup is paid once per CTA instead of once per tile.
+// ---------------------------------------------------------------------------------------------------
+constexpr int P_BN = 256, P_STAGES = 3, P_CH = 64, P_RS = P_CH + 4;
+constexpr uint32_t kPBBytes = P_BN * BLOCK_K * 2, kPStage = kABytes + kPBBytes;
+constexpr int kPSmem = P_STAGES * (int)kPStage + BLOCK_M * P_RS * 4 + 1024;
+
+template <bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int K,
+                          Epilogue epi, int tiles_m, int tiles_n) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    float* stage = reinterpret_cast<float*>(smem + P_STAGES * kPStage);
+    __shared__ __align__(8) unsigned long long full_bar[P_STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[P_STAGES];
+    __shared__ __align__(8) unsigned long long tmem_full_bar[2];
+    __shared__ __align__(8) unsigned long long tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
+    const int num_tiles = tiles_m * tiles_n;
+    const bool m_fast = tiles_m <= tiles_n;     // consecutive CTAs share the tile of the LARGER operand
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+        for (int s = 0; s < P_STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[a]), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+                const int mt = m_fast ? tile % tiles_m : tile / tiles_n, nt = m_fast ? tile / tiles_m : tile % tiles_n;
+                const int m0 = mt * BLOCK_M, n0 = nt * P_BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % P_STAGES, ph = (it / P_STAGES) & 1u;
+                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
+                    const uint32_t full = smem_u32(&full_bar[s]);
+                    mbar_expect_tx(full, kPStage);
+                    const uint32_t sa = smem_u32(smem + (size_t)s * kPStage), sb = sa + kABytes;
+                    const int k0 = kb * BLOCK_K;
+                    if (!A_MN) {
+                        tma_load_2d(sa, &tmA, k0, m0, full);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, k0, full);
+                    }
+                    if (!B_MN) {
+                        tma_load_2d(sb, &tmB, k0, n0, full);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < P_BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, k0, full);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+            uint32_t it = 0, ti = 0;
+            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+                const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+                mbar_wait(smem_u32(&tmem_empty_bar[acc]), aph ^ 1u);     // epilogue has drained this accumulator
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d_tmem = tmem_base + acc * (uint32_t)P_BN;
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const uint32_t s = it % P_STAGES, ph = (it / P_STAGES) & 1u;
+                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t sa = smem_u32(smem + (size_t)s * kPStage), sb = sa + kABytes;
+                    const uint64_t adesc = A_MN ? make_desc(sa, 8192, 1024) : make_desc(sa, 16, 1024);
+                    const uint64_t bdesc = B_MN ? make_desc(sb, 8192, 1024) : make_desc(sb, 16, 1024);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t ak = adesc + (uint64_t)((A_MN ? 2048u : 32u) * k >> 4);
+                        const uint64_t bk = bdesc + (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
+                        umma_bf16(d_tmem, ak, bk, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(smem_u32(&empty_bar[s]));
+                }
+                umma_commit(smem_u32(&tmem_full_bar[acc]));
+            }
+        }
+    } else {
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int t = threadIdx.x - 64;
+        const Rng rng = make_rng(nullptr, 0.f);
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int mt = m_fast ? tile % tiles_m : tile / tiles_n, nt = m_fast ? tile / tiles_m : tile % tiles_n;
+            const int m0 = mt * BLOCK_M, n0 = nt * P_BN;
+            const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int ch = 0; ch < P_BN / P_CH; ++ch) {
+#pragma unroll
+                for (int c = 0; c < P_CH / 16; ++c) {
+                    uint32_t r[16];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)P_BN + (uint32_t)(ch * P_CH + c * 16);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                        : "r"(taddr)
+                        : "memory");
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    uint4* dst = reinterpret_cast<uint4*>(stage + row * P_RS + c * 16);
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+                }
+                if (ch == P_BN / P_CH - 1) {
+                    // every TMEM read of this accumulator has completed: hand it back to the MMA warp
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                constexpr int CG = P_CH / 8;
+#pragma unroll 2
+                for (int id = t; id < BLOCK_M * CG; id += 128) {
+                    const int rr = id / CG, cg = id % CG;
+                    const int m = m0 + rr, n = n0 + ch * P_CH + cg * 8;
+                    if (m < epi.M && n < epi.N) {
+                        const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * P_RS + cg * 8);
+                        const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * P_RS + cg * 8 + 4);
+                        epilogue_store8<VCT_ACT_NONE>(epi, rng, m, n, a0, a1);
+                    }
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer is reused by the next chunk
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // split-K second pass: sum the partial tiles in a fixed order and apply the fused epilogue
 template <int ACT>
 __global__ void __launch_bounds__(256)
@@ -335,6 +502,20 @@ int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tm
     return 0;
 }
 
+template <bool A_MN, bool B_MN>
+int launch_persistent(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, cudaStream_t st) {
+    auto kern = gemm_tc_persistent_kernel<A_MN, B_MN>;
+    static bool once = false;
+    if (!once) {
+        VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+        once = true;
+    }
+    const int tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M, tiles_n = (a->N + P_BN - 1) / P_BN;
+    const int grid = tiles_m * tiles_n < kNumSMs ? tiles_m * tiles_n : kNumSMs;
+    kern<<<grid, kThreads, kPSmem, st>>>(tmA, tmB, a->K, make_epilogue(a), tiles_m, tiles_n);
+    return check_launch("vct_gemm(tcgen05 persistent)");
+}
+
 template <int BLOCK_N>
 int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
     // activation epilogues exist where the path uses them: GELU forward on x W1^T (K-major, K-major) and GELU
@@ -371,6 +552,10 @@ int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     const long long ldw = ((long long)a->N + 7) / 8 * 8;
     int bn = 64, splits = 1;
     double best = 1e30;
+    // several 128x256 tiles per SM: the persistent kernel (epilogue overlapped with the next tile's main loop)
+    const bool persistent = tiles_m * ((a->N + 255) / 256) >= 2 * kNumSMs && a->act == VCT_ACT_NONE &&
+                            getenv("VCT_NO_PERSISTENT") == nullptr;
+    if (persistent) { bn = 256; splits = 1; best = 0.0; }
     for (int cand : {256, 128, 64}) {
         const long long tiles = tiles_m * ((a->N + cand - 1) / cand);
         const double cyc_kb = fmax(2.0 * cand, (16384.0 + 128.0 * cand) / 42.0);
@@ -390,6 +575,12 @@ int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     else             { if (int e = get_map(a->A, a->M, a->K, a->lda, 64, BLOCK_K, &tmA)) return e; }
     if (!a->b_trans) { if (int e = get_map(a->B, a->K, a->N, a->ldb, BLOCK_K, bn, &tmB)) return e; }
     else             { if (int e = get_map(a->B, a->N, a->K, a->ldb, 64, BLOCK_K, &tmB)) return e; }
+    if (bn == 256 && splits == 1 && a->act == VCT_ACT_NONE && persistent) {
+        if (!a->a_trans && !a->b_trans) return launch_persistent<false, false>(a, tmA, tmB, st);
+        if (!a->a_trans && a->b_trans) return launch_persistent<false, true>(a, tmA, tmB, st);
+        if (a->a_trans && !a->b_trans) return launch_persistent<true, false>(a, tmA, tmB, st);
+        return launch_persistent<true, true>(a, tmA, tmB, st);
+    }
     if (bn == 256) return dispatch_major<256>(a, tmA, tmB, splits, st);
     if (bn == 128) return dispatch_major<128>(a, tmA, tmB, splits, st);
     return dispatch_major<64>(a, tmA, tmB, splits, st);

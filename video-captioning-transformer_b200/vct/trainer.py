@@ -83,19 +83,44 @@ class CaptionTrainer:
         self.engine.set_lr(lr)
 
     # ---- one step -----------------------------------------------------------------------------------
-    def _body(self, ws) -> None:
+    def _compute(self, ws) -> None:
         eng = self.engine
         eng.tick()
         eng.zero_scatter_grads()
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
         eng.run(eng.plan_backward(ws, sce_first=False, part="all"))
-        if self.world > 1:
-            all_reduce_flat(eng.arena.grad, self.buckets, self.group)
-        eng.adam(grad_scale=1.0 / self.world)
+
+    def _update(self) -> None:
+        self.engine.adam(grad_scale=1.0 / self.world)
+
+    def _graphed(self, key, fn):
+        """Run ``fn`` eagerly twice (plan building, kernel attributes), then capture it once and replay."""
+        eng = self.engine
+        if not self.use_graph:
+            fn()
+            return
+        if key not in self._graphs:
+            if self._warm.get(key, 0) < 2:
+                self._warm[key] = self._warm.get(key, 0) + 1
+                fn()
+                return
+            g = torch.cuda.CUDAGraph()
+            before = eng.launches
+            with torch.cuda.graph(g):
+                fn()
+            self._graphs[key] = (g, eng.launches - before)
+            eng.launches = before          # capture issued nothing; the replay below is this step
+        g, n = self._graphs[key]
+        g.replay()
+        eng.launches += n
 
     def step(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: torch.Tensor) -> torch.Tensor:
         """feats fp32 [B,T,Din], vid_pad bool [B,T] | None, ids int64 [B,S+1] (host -- ideally pinned -- or
-        device tensors).  Returns the step's loss as a device scalar (no host sync)."""
+        device tensors).  Returns the step's loss as a device scalar (no host sync).
+
+        world == 1: [tick, forward, backward, Adam] is ONE CUDA graph.
+        world  > 1: graph [tick, forward, backward] -> NCCL SUM all-reduce of the gradient arena (bucketed,
+        issued eagerly: collectives stay outside graph capture) -> graph [Adam with 1/world folded in]."""
         eng = self.engine
         B, T, _ = feats.shape
         S = ids.shape[1] - 1
@@ -103,23 +128,10 @@ class CaptionTrainer:
         eng.check_arena()
         eng.refresh_shadow()               # no-op unless the masters were edited outside vct_adam
         eng.stage_inputs(ws, feats, vid_pad, ids)
-        key = (B, T, S)
-        if not self.use_graph:
-            self._body(ws)
-            return ws.loss[0]
-        if key not in self._graphs:
-            if self._warm.get(key, 0) < 2:
-                # eager warm-up: builds plans, sets kernel attributes, lets NCCL set up its channels
-                self._warm[key] = self._warm.get(key, 0) + 1
-                self._body(ws)
-                return ws.loss[0]
-            g = torch.cuda.CUDAGraph()
-            before = eng.launches
-            with torch.cuda.graph(g):
-                self._body(ws)
-            self._graphs[key] = (g, eng.launches - before)
-            eng.launches = before          # capture issued nothing; the replay below is this step
-        g, n = self._graphs[key]
-        g.replay()
-        eng.launches += n
+        if self.world == 1:
+            self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()))
+        else:
+            self._graphed((B, T, S, "compute"), lambda: self._compute(ws))
+            all_reduce_flat(eng.arena.grad, self.buckets, self.group)
+            self._graphed(("update",), self._update)
         return ws.loss[0]
