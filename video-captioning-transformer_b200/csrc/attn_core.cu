@@ -123,6 +123,8 @@ __global__ void __launch_bounds__(kThreads)
 attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
                 const unsigned char* __restrict__ key_pad, float* __restrict__ probs, Dims D, float drop_p,
                 const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
@@ -188,6 +190,8 @@ __global__ void __launch_bounds__(kThreads)
 attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ d_o,
                 T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, const unsigned char* __restrict__ key_pad,
                 Dims D, float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(16) float sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
@@ -340,7 +344,7 @@ int launch_fwd(const vct_attn_args* a, cudaStream_t st) {
     auto kern = attn_fwd_kernel<T, DHP>;
     static bool once = false;
     if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
-    kern<<<a->B * a->H, kThreads, smem, st>>>((const T*)a->q, (const T*)a->k, (const T*)a->v, (T*)a->o, a->key_pad, a->probs,
+    vct::launch(kern, dim3(a->B * a->H), dim3(kThreads), smem, st, (const T*)a->q, (const T*)a->k, (const T*)a->v, (T*)a->o, a->key_pad, a->probs,
                                               make_dims(a), a->drop_p, a->rng_state, a->site);
     return check_launch("vct_attn_fwd");
 }
@@ -353,7 +357,7 @@ int launch_bwd(const vct_attn_args* a, cudaStream_t st) {
     auto kern = attn_bwd_kernel<T, DHP>;
     static bool once = false;
     if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
-    kern<<<a->B * a->H, kThreads, smem, st>>>((const T*)a->q, (const T*)a->k, (const T*)a->v, (const T*)a->d_o, (T*)a->dq,
+    vct::launch(kern, dim3(a->B * a->H), dim3(kThreads), smem, st, (const T*)a->q, (const T*)a->k, (const T*)a->v, (const T*)a->d_o, (T*)a->dq,
                                               (T*)a->dk, (T*)a->dv, a->key_pad, make_dims(a), a->drop_p, a->rng_state, a->site);
     return check_launch("vct_attn_bwd");
 }

@@ -36,6 +36,34 @@ int check_launch(const char* what);
 constexpr int kNumSMs = 148;   // B200
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every kernel is launched with the stream-serialization attribute, lets its
+// dependents start early (griddepcontrol.launch_dependents) and waits for its prerequisites
+// (griddepcontrol.wait) before touching global memory.  A step is a chain of ~160 short dependent kernels, so
+// overlapping each kernel's launch + prologue with its predecessor's tail is worth ~2 us per launch.
+// Both instructions are no-ops when the kernel was launched without the attribute.  VCT_PDL=0 disables it.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // dtype helpers (VCT_F32 / VCT_BF16 storage, fp32 arithmetic)
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float to_f32(float v) { return v; }

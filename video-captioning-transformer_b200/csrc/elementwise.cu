@@ -1,6 +1,7 @@
 // HBM-bound kernels of the hot path: frame staging, residual+dropout+LayerNorm (fwd/bwd),
 // embedding (fwd/bwd), column sums, Adam, casts, greedy argmax, step tick, error plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -13,6 +14,14 @@ void set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+bool pdl_enabled() {
+    static const bool on = [] {
+        const char* e = getenv("VCT_PDL");
+        return !(e && e[0] == '0');
+    }();
+    return on;
 }
 
 int check_launch(const char* what) {
@@ -47,6 +56,8 @@ extern "C" int vct_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 // step tick
 // ------------------------------------------------------------------------------------------------
 __global__ void step_tick_kernel(unsigned long long* rng_state, float* hyper) {
+    pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         if (rng_state) rng_state[1] += 1ull;
         if (hyper) {
@@ -59,7 +70,7 @@ __global__ void step_tick_kernel(unsigned long long* rng_state, float* hyper) {
 }
 
 extern "C" int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, vct_stream_t stream) {
-    step_tick_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(rng_state, adam_hyper);
+    vct::launch(step_tick_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, rng_state, adam_hyper);
     return check_launch("vct_step_tick");
 }
 
@@ -68,6 +79,8 @@ extern "C" int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, v
 // ------------------------------------------------------------------------------------------------
 template <typename TO>
 __global__ void prep_frames_kernel(const float* __restrict__ feats, TO* __restrict__ out, int B, int T, int Din) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int nv = Din >> 2;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * nv) return;
@@ -89,9 +102,9 @@ extern "C" int vct_prep_frames(const float* feats, void* out, int out_dtype, int
     long long n = (long long)B * (Din / 4);
     int blocks = (int)((n + 255) / 256);
     if (out_dtype == VCT_BF16)
-        prep_frames_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feats, (__nv_bfloat16*)out, B, T, Din);
+        vct::launch(prep_frames_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, feats, (__nv_bfloat16*)out, B, T, Din);
     else
-        prep_frames_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(feats, (float*)out, B, T, Din);
+        vct::launch(prep_frames_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, feats, (float*)out, B, T, Din);
     return check_launch("vct_prep_frames");
 }
 
@@ -106,6 +119,8 @@ ln_fwd_kernel(const float* __restrict__ x, const float* r, const float* __restri
               const float* __restrict__ beta, float* __restrict__ y, TC* __restrict__ y_c, float* s_out,
               float* __restrict__ mean_out, float* __restrict__ rstd_out, int R, int d, float drop_p,
               const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int row = blockIdx.x * kLnWarps + warp;
     if (row >= R) return;
@@ -168,7 +183,7 @@ static int launch_ln_fwd(const float* x, const float* r, const float* gamma, con
     const int blocks = (R + kLnWarps - 1) / kLnWarps;
     const int nvl = (d / 8 + 31) / 32;
 #define LN_FWD_CASE(NVV)                                                                                         \
-    ln_fwd_kernel<NVV, TC><<<blocks, kLnWarps * 32, 0, st>>>(x, r, gamma, beta, y, y_c, s_out, mean, rstd, R, d, \
+    vct::launch(ln_fwd_kernel<NVV, TC>, dim3(blocks), dim3(kLnWarps * 32), 0, st, x, r, gamma, beta, y, y_c, s_out, mean, rstd, R, d, \
                                                               drop_p, rng_state, site)
     if (nvl <= 1) LN_FWD_CASE(1);
     else if (nvl <= 2) LN_FWD_CASE(2);
@@ -220,6 +235,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const f
               const float* __restrict__ rstd, const float* __restrict__ gamma, float* __restrict__ ds,
               TC* __restrict__ dr_c, float* __restrict__ partials, int R, int d, int rows_per_cta, float drop_p,
               const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sm[];  // [kLnBwdWarps][3][d]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = d >> 3;
@@ -305,6 +322,8 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const f
 __global__ void __launch_bounds__(1024)
 ln_bwd_reduce_kernel(const float* __restrict__ partials, int nblocks, int d, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dbias_r) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float red[32][33];
     const int cx = threadIdx.x & 31, gy = threadIdx.x >> 5;
     const int idx = blockIdx.x * 32 + cx;
@@ -337,7 +356,7 @@ static int launch_ln_bwd(const float* dy, const float* s, const float* mean, con
         auto kern = ln_bwd_kernel<NVV, TC>;                                                                     \
         static bool once = false;                                                                               \
         if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024)); once = true; } \
-        kern<<<blocks, kLnBwdWarps * 32, smem, st>>>(dy, s, mean, rstd, gamma, ds, dr_c, partials, R, d, rows, drop_p, \
+        vct::launch(kern, dim3(blocks), dim3(kLnBwdWarps * 32), smem, st, dy, s, mean, rstd, gamma, ds, dr_c, partials, R, d, rows, drop_p, \
                                                      rng_state, site);                                          \
     }
     if (nvl <= 1) LN_BWD_CASE(1)
@@ -351,7 +370,7 @@ static int launch_ln_bwd(const float* dy, const float* s, const float* mean, con
 extern "C" int vct_ln_bwd_reduce(const float* partials, int R, int d, float* dgamma, float* dbeta, float* dbias_r,
                                  vct_stream_t stream) {
     VCT_REQUIRE(partials && d % 8 == 0 && d <= 1024 && R > 0, "vct_ln_bwd_reduce: bad arguments");
-    ln_bwd_reduce_kernel<<<(3 * d + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(partials, ln_bwd_blocks(R), d, dgamma, dbeta,
+    vct::launch(ln_bwd_reduce_kernel, dim3((3 * d + 31) / 32), dim3(1024), 0, (cudaStream_t)stream, partials, ln_bwd_blocks(R), d, dgamma, dbeta,
                                                                               dbias_r);
     return check_launch("vct_ln_bwd_reduce");
 }
@@ -385,6 +404,8 @@ __global__ void embed_fwd_kernel(const long long* __restrict__ ids, long long id
                                  const float* __restrict__ pos, float* __restrict__ x, TC* __restrict__ x_c, int B,
                                  int S, int d, int V, int pos_offset, float drop_p,
                                  const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int nv = d >> 3;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * S * nv) return;
@@ -411,10 +432,10 @@ extern "C" int vct_embed_fwd(const long long* ids, long long ids_ld, const float
     long long n = (long long)B * S * (d / 8);
     int blocks = (int)((n + 255) / 256);
     if (x_c_dtype == VCT_BF16)
-        embed_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, E, pos, x, (__nv_bfloat16*)x_c, B, S, d,
+        vct::launch(embed_fwd_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, ids, ids_ld, E, pos, x, (__nv_bfloat16*)x_c, B, S, d,
                                                                    V, pos_offset, drop_p, rng_state, site);
     else
-        embed_fwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, E, pos, x, (float*)x_c, B, S, d, V,
+        vct::launch(embed_fwd_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, ids, ids_ld, E, pos, x, (float*)x_c, B, S, d, V,
                                                                    pos_offset, drop_p, rng_state, site);
     return check_launch("vct_embed_fwd");
 }
@@ -422,6 +443,8 @@ extern "C" int vct_embed_fwd(const long long* ids, long long ids_ld, const float
 __global__ void embed_bwd_kernel(const long long* __restrict__ ids, long long ids_ld, const float* __restrict__ dx,
                                  float* __restrict__ dE, int B, int S, int d, int V, int pad_id, float drop_p,
                                  const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int nv = d >> 3;
     long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gid >= (long long)B * S * nv) return;
@@ -445,7 +468,7 @@ extern "C" int vct_embed_bwd(const long long* ids, long long ids_ld, const float
     VCT_REQUIRE(d % 8 == 0 && B > 0 && S > 0, "vct_embed_bwd: need d %% 8 == 0 and non-empty input");
     long long n = (long long)B * S * (d / 8);
     int blocks = (int)((n + 255) / 256);
-    embed_bwd_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(ids, ids_ld, dx, dE, B, S, d, V, pad_id, drop_p,
+    vct::launch(embed_bwd_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, ids, ids_ld, dx, dE, B, S, d, V, pad_id, drop_p,
                                                                rng_state, site);
     return check_launch("vct_embed_bwd");
 }
@@ -463,6 +486,8 @@ template <typename T>
 __global__ void __launch_bounds__(kCsCols)
 colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, float* __restrict__ out,
               float* __restrict__ partials, unsigned int* counters) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ bool is_last;
     const int n = blockIdx.x * kCsCols + threadIdx.x;
     const int m0 = blockIdx.y * kCsRows, m1 = min(M, m0 + kCsRows);
@@ -494,9 +519,9 @@ extern "C" int vct_colsum(const void* X, int dtype, long long ld, int M, int N, 
     VCT_REQUIRE(M > 0 && N > 0 && N <= 65536, "vct_colsum: need 0 < N <= 65536 (counter array has 256 entries)");
     dim3 grid((N + kCsCols - 1) / kCsCols, (M + kCsRows - 1) / kCsRows);
     if (dtype == VCT_BF16)
-        colsum_kernel<<<grid, kCsCols, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)X, ld, M, N, out, partials, counter);
+        vct::launch(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(kCsCols), 0, (cudaStream_t)stream, (const __nv_bfloat16*)X, ld, M, N, out, partials, counter);
     else
-        colsum_kernel<<<grid, kCsCols, 0, (cudaStream_t)stream>>>((const float*)X, ld, M, N, out, partials, counter);
+        vct::launch(colsum_kernel<float>, dim3(grid), dim3(kCsCols), 0, (cudaStream_t)stream, (const float*)X, ld, M, N, out, partials, counter);
     return check_launch("vct_colsum");
 }
 
@@ -506,6 +531,8 @@ extern "C" int vct_colsum(const void* X, int dtype, long long ld, int M, int N, 
 __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __nv_bfloat16* __restrict__ p_c, long long n4, const float* __restrict__ hyper, float grad_scale) {
+    pdl_launch_dependents();
+    pdl_wait();
     const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
     const float step_size = lr / hyper[6], inv_sqrt_bc2 = rsqrtf(hyper[7]);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
@@ -535,7 +562,7 @@ extern "C" int vct_adam(float* p, const float* g, float* m, float* v, void* p_c,
     const long long n4 = n / 4;
     long long want = (n4 + 255) / 256;
     int blocks = (int)(want < (long long)kNumSMs * 8 ? want : (long long)kNumSMs * 8);
-    adam_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, (__nv_bfloat16*)p_c, n4, hyper, grad_scale);
+    vct::launch(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)p_c, n4, hyper, grad_scale);
     return check_launch("vct_adam");
 }
 
@@ -544,6 +571,8 @@ extern "C" int vct_adam(float* p, const float* g, float* m, float* v, void* p_c,
 // ------------------------------------------------------------------------------------------------
 template <typename TO>
 __global__ void cast_kernel(const float* __restrict__ src, TO* __restrict__ dst, long long n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long n4 = n >> 2;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x)
         st4(dst + i * 4, ld4(src + i * 4));
@@ -555,9 +584,9 @@ extern "C" int vct_cast(const float* src, void* dst, int dst_dtype, long long n,
     long long want = (n / 4 + 255) / 256 + 1;
     int blocks = (int)(want < (long long)kNumSMs * 8 ? want : (long long)kNumSMs * 8);
     if (dst_dtype == VCT_BF16)
-        cast_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (__nv_bfloat16*)dst, n);
+        vct::launch(cast_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, (__nv_bfloat16*)dst, n);
     else
-        cast_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, (float*)dst, n);
+        vct::launch(cast_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, src, (float*)dst, n);
     return check_launch("vct_cast");
 }
 
@@ -567,6 +596,8 @@ extern "C" int vct_cast(const float* src, void* dst, int dst_dtype, long long n,
 __global__ void __launch_bounds__(256)
 argmax_append_kernel(const float* __restrict__ logits, long long ld, int V, long long* __restrict__ ys, long long ys_ld,
                      int t, int end_id, int* __restrict__ ended, int* __restrict__ n_ended) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sv[8];
     __shared__ int si[8];
     const int b = blockIdx.x;
@@ -600,7 +631,7 @@ argmax_append_kernel(const float* __restrict__ logits, long long ld, int V, long
 extern "C" int vct_argmax_append(const float* logits, long long ld_logits, int B, int V, long long* ys, long long ys_ld,
                                  int t, int end_id, int* ended, int* n_ended, vct_stream_t stream) {
     VCT_REQUIRE(B > 0 && V > 0 && logits && ys, "vct_argmax_append: bad arguments");
-    argmax_append_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(logits, ld_logits, V, ys, ys_ld, t, end_id, ended, n_ended);
+    vct::launch(argmax_append_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, logits, ld_logits, V, ys, ys_ld, t, end_id, ended, n_ended);
     return check_launch("vct_argmax_append");
 }
 
@@ -609,6 +640,8 @@ extern "C" int vct_argmax_append(const float* logits, long long ld_logits, int B
 // ------------------------------------------------------------------------------------------------
 __global__ void dropout_mask_kernel(unsigned char* out, long long n, float p, const unsigned long long* rng_state,
                                     unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
     const Rng rng = make_rng(rng_state, p);
     long long i8 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i8 * 8 >= n) return;
@@ -622,6 +655,6 @@ extern "C" int vct_dropout_mask(unsigned char* out, long long n, float drop_p, c
                                 unsigned int site, vct_stream_t stream) {
     VCT_REQUIRE(n > 0, "vct_dropout_mask: empty");
     long long n8 = (n + 7) / 8;
-    dropout_mask_kernel<<<(int)((n8 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(out, n, drop_p, rng_state, site);
+    vct::launch(dropout_mask_kernel, dim3((int)((n8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, out, n, drop_p, rng_state, site);
     return check_launch("vct_dropout_mask");
 }

@@ -61,6 +61,8 @@ template <typename T, bool A_TRANS, bool B_TRANS, int ACT>
 __global__ void __launch_bounds__(THREADS)
 gemm_simt_kernel(const T* __restrict__ A, long long lda, const T* __restrict__ B, long long ldb, int M, int N, int K,
                  bool a_vec, bool b_vec, Epilogue epi) {
+    pdl_launch_dependents();
+    pdl_wait();
     __shared__ __align__(16) float As[BK][BM + PAD];
     __shared__ __align__(16) float Bs[BK][BN + PAD];
     const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -107,7 +109,7 @@ gemm_simt_kernel(const T* __restrict__ A, long long lda, const T* __restrict__ B
 }
 
 template <typename T>
-int launch(const vct_gemm_args* a, cudaStream_t st) {
+int launch_simt(const vct_gemm_args* a, cudaStream_t st) {
     const Epilogue epi = make_epilogue(a);
     dim3 grid((a->N + BN - 1) / BN, (a->M + BM - 1) / BM);
     const int esz = (int)sizeof(T);
@@ -116,7 +118,7 @@ int launch(const vct_gemm_args* a, cudaStream_t st) {
     const bool b_vec = (a->ldb % vecel == 0) && ((reinterpret_cast<uintptr_t>(a->B) & 15) == 0);
     const T* A = (const T*)a->A;
     const T* B = (const T*)a->B;
-#define GO(AT, BT, ACT) gemm_simt_kernel<T, AT, BT, ACT><<<grid, THREADS, 0, st>>>(A, a->lda, B, a->ldb, a->M, a->N, a->K, a_vec, b_vec, epi)
+#define GO(AT, BT, ACT) vct::launch(gemm_simt_kernel<T, AT, BT, ACT>, dim3(grid), dim3(THREADS), 0, st, A, a->lda, B, a->ldb, a->M, a->N, a->K, a_vec, b_vec, epi)
 #define GO_ACT(AT, BT)                                      \
     if (a->act == VCT_ACT_GELU_FWD) GO(AT, BT, VCT_ACT_GELU_FWD);   \
     else if (a->act == VCT_ACT_GELU_BWD) GO(AT, BT, VCT_ACT_GELU_BWD); \
@@ -134,8 +136,8 @@ int launch(const vct_gemm_args* a, cudaStream_t st) {
 
 namespace vct {
 int gemm_simt(const vct_gemm_args* a, cudaStream_t st) {
-    if (a->a_dtype == VCT_BF16) return launch<__nv_bfloat16>(a, st);
-    return launch<float>(a, st);
+    if (a->a_dtype == VCT_BF16) return launch_simt<__nv_bfloat16>(a, st);
+    return launch_simt<float>(a, st);
 }
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st);   // gemm_tc.cu
 }  // namespace vct

@@ -88,6 +88,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __shared__ __align__(8) unsigned long long tmem_full_bar;
     __shared__ uint32_t tmem_base_slot;
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
     // split-K: blockIdx.z owns the k-blocks [kb0, kb0 + num_kb)
@@ -116,6 +117,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; nothing
+    // before this point reads or writes global memory that another kernel of the step produces
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -253,10 +257,13 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     __shared__ __align__(8) unsigned long long tmem_empty_bar[2];
     __shared__ uint32_t tmem_base_slot;
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_kb = (K + BLOCK_K - 1) / BLOCK_K;
     const int num_tiles = tiles_m * tiles_n;
-    const bool m_fast = tiles_m <= tiles_n;     // consecutive CTAs share the tile of the LARGER operand
+    // n-fastest tile order: CTAs running at the same time write adjacent column ranges of the SAME output rows
+    // (DRAM-page-friendly stores; the operands are L2-resident either way)
+    const bool m_fast = false;
 
     if (warp == 0 && lane == 0) {
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
@@ -281,6 +288,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; nothing
+    // before this point reads or writes global memory that another kernel of the step produces
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -400,6 +410,8 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 template <int ACT>
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long ldw, Epilogue epi) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int cg_per_row = (epi.N + 7) / 8;
     const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (id >= (long long)epi.M * cg_per_row) return;
@@ -479,7 +491,7 @@ int get_map(const void* ptr, long long inner, long long outer, long long ld, int
 }
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int ACT>
-int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
+int launch_tile(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
     constexpr int kStage = kABytes + BLOCK_N * BLOCK_K * 2;
     constexpr int STAGES = kSmemBudget / kStage > 8 ? 8 : kSmemBudget / kStage;
     constexpr int smem = STAGES * kStage + 1024;
@@ -492,11 +504,11 @@ int launch(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tm
     dim3 grid((a->N + BLOCK_N - 1) / BLOCK_N, (a->M + BLOCK_M - 1) / BLOCK_M, splits);
     const Epilogue epi = make_epilogue(a);
     const long long ldw = ((long long)a->N + 7) / 8 * 8;
-    kern<<<grid, kThreads, smem, st>>>(tmA, tmB, a->K, epi, splits > 1 ? (float*)a->splitk_ws : nullptr, ldw);
+    vct::launch(kern, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, a->K, epi, splits > 1 ? (float*)a->splitk_ws : nullptr, ldw);
     if (int e = check_launch("vct_gemm(tcgen05)")) return e;
     if (splits > 1) {
         const long long items = (long long)a->M * ((a->N + 7) / 8);
-        splitk_reduce_kernel<ACT><<<(unsigned)((items + 255) / 256), 256, 0, st>>>((const float*)a->splitk_ws, splits, ldw, epi);
+        vct::launch(splitk_reduce_kernel<ACT>, dim3((unsigned)((items + 255) / 256)), dim3(256), 0, st, (const float*)a->splitk_ws, splits, ldw, epi);
         return check_launch("vct_gemm(tcgen05 split-K reduce)");
     }
     return 0;
@@ -512,7 +524,7 @@ int launch_persistent(const vct_gemm_args* a, const CUtensorMap& tmA, const CUte
     }
     const int tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M, tiles_n = (a->N + P_BN - 1) / P_BN;
     const int grid = tiles_m * tiles_n < kNumSMs ? tiles_m * tiles_n : kNumSMs;
-    kern<<<grid, kThreads, kPSmem, st>>>(tmA, tmB, a->K, make_epilogue(a), tiles_m, tiles_n);
+    vct::launch(kern, dim3(grid), dim3(kThreads), kPSmem, st, tmA, tmB, a->K, make_epilogue(a), tiles_m, tiles_n);
     return check_launch("vct_gemm(tcgen05 persistent)");
 }
 
@@ -522,17 +534,17 @@ int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtenso
     // backward on dY W2 (K-major, MN-major); everything else carries the small plain epilogue
     if (a->act == VCT_ACT_GELU_FWD) {
         VCT_REQUIRE(!a->a_trans && !a->b_trans, "vct_gemm(tcgen05): GELU_FWD is built for a_trans = b_trans = 0");
-        return launch<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, splits, st);
+        return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, splits, st);
     }
     if (a->act == VCT_ACT_GELU_BWD) {
         VCT_REQUIRE(!a->a_trans, "vct_gemm(tcgen05): GELU_BWD is built for a_trans = 0");
-        if (a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
-        return launch<BLOCK_N, false, false, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
+        if (a->b_trans) return launch_tile<BLOCK_N, false, true, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
+        return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
     }
-    if (!a->a_trans && !a->b_trans) return launch<BLOCK_N, false, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
-    if (!a->a_trans && a->b_trans) return launch<BLOCK_N, false, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
-    if (a->a_trans && !a->b_trans) return launch<BLOCK_N, true, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
-    return launch<BLOCK_N, true, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    if (!a->a_trans && !a->b_trans) return launch_tile<BLOCK_N, false, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    if (!a->a_trans && a->b_trans) return launch_tile<BLOCK_N, false, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    if (a->a_trans && !a->b_trans) return launch_tile<BLOCK_N, true, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    return launch_tile<BLOCK_N, true, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
 }
 
 }  // namespace

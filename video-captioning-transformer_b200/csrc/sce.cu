@@ -43,6 +43,8 @@ sce_kernel(const float* __restrict__ logits, long long ld_logits, const long lon
            int B, int S, int V, float alpha, float beta, int pad_id, float* __restrict__ loss_out,
            float* __restrict__ row_parts, unsigned int* counter, TD* __restrict__ dlogits, long long ld_dl,
            const float* __restrict__ upstream) {
+    pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
     float* zs = reinterpret_cast<float*>(smem_raw);   // [ld_logits]
     __shared__ __align__(8) unsigned long long bar;
@@ -184,7 +186,7 @@ extern "C" int vct_sce(const float* logits, long long ld_logits, const long long
             VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attr_done[1] = true;
         }
-        kern<<<B * S, kThreads, smem, st>>>(logits, ld_logits, ids, ids_ld, B, S, V, alpha, beta, pad_id, loss_out,
+        vct::launch(kern, dim3(B * S), dim3(kThreads), smem, st, logits, ld_logits, ids, ids_ld, B, S, V, alpha, beta, pad_id, loss_out,
                                             row_parts, counter, (__nv_bfloat16*)dlogits, ld_dl, upstream);
     } else {
         auto kern = sce_kernel<float>;
@@ -192,7 +194,7 @@ extern "C" int vct_sce(const float* logits, long long ld_logits, const long long
             VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
             attr_done[0] = true;
         }
-        kern<<<B * S, kThreads, smem, st>>>(logits, ld_logits, ids, ids_ld, B, S, V, alpha, beta, pad_id, loss_out,
+        vct::launch(kern, dim3(B * S), dim3(kThreads), smem, st, logits, ld_logits, ids, ids_ld, B, S, V, alpha, beta, pad_id, loss_out,
                                             row_parts, counter, (float*)dlogits, ld_dl, upstream);
     }
     return check_launch("vct_sce");
