@@ -50,17 +50,19 @@ class Plan:
     def add(self, name: str, fn, *args):
         self.calls.append((name, fn, args, self.lane))
 
-    def run(self, main, side=None) -> int:
-        """main / side: torch.cuda.Stream objects (side may be None: everything runs on main)."""
+    def run(self, main, sides=None) -> int:
+        """main: torch.cuda.Stream; sides: list of side streams (lane k runs on sides[k-1]) or None (everything
+        runs on main).  A side-lane call waits for everything main has issued so far; lane 2 (the optimizer lane)
+        additionally waits for lane 1 (whose kernels produce the gradients it consumes).  main joins every used
+        side lane at the end."""
         mp = main.cuda_stream
-        if side is None or not any(c[3] for c in self.calls):
+        if not sides or not any(c[3] for c in self.calls):
             for name, fn, args, _ in self.calls:
                 rc = fn(*args, mp)
                 if rc != 0:
                     L.check(rc, name)
             return len(self.calls)
-        sp = side.cuda_stream
-        ev_i, main_dirty, side_used = 0, True, False
+        ev_i = 0
 
         def event():
             nonlocal ev_i
@@ -69,24 +71,38 @@ class Plan:
             ev_i += 1
             return self._events[ev_i - 1]
 
+        nl = len(sides) + 1
+        main_seen = [False] * nl      # has lane k already waited for main's latest work?
+        lane1_seen2 = True            # has lane 2 already waited for lane 1's latest work?
+        used = [False] * nl
         for name, fn, args, lane in self.calls:
+            lane = min(lane, nl - 1)
             if lane == 0:
                 rc = fn(*args, mp)
-                main_dirty = True
+                main_seen = [False] * nl
             else:
-                if main_dirty:                    # side work may read anything main has produced so far
+                st = sides[lane - 1]
+                if not main_seen[lane]:
                     e = event()
                     e.record(main)
-                    side.wait_event(e)
-                    main_dirty = False
-                rc = fn(*args, sp)
-                side_used = True
+                    st.wait_event(e)
+                    main_seen[lane] = True
+                if lane == 2 and not lane1_seen2 and used[1]:
+                    e = event()
+                    e.record(sides[0])
+                    st.wait_event(e)
+                    lane1_seen2 = True
+                rc = fn(*args, st.cuda_stream)
+                used[lane] = True
+                if lane == 1:
+                    lane1_seen2 = False
             if rc != 0:
                 L.check(rc, name)
-        if side_used:
-            e = event()
-            e.record(side)
-            main.wait_event(e)
+        for k in range(1, nl):
+            if used[k]:
+                e = event()
+                e.record(sides[k - 1])
+                main.wait_event(e)
         return len(self.calls)
 
     def __len__(self):
@@ -130,7 +146,8 @@ class CaptionEngine:
         self.hyper = torch.zeros(8, dtype=torch.float32, device=device)
         self.counters = torch.zeros(1024, dtype=torch.int32, device=device)
         self.upstream = torch.ones(1, dtype=torch.float32, device=device)
-        self.side_stream = torch.cuda.Stream(device=device) if os.environ.get("VCT_SIDE_STREAM", "1") != "0" else None
+        self.side_streams = [torch.cuda.Stream(device=device) for _ in range(2)] \
+            if os.environ.get("VCT_SIDE_STREAM", "1") != "0" else None
         self._tempo: Dict[int, torch.Tensor] = {}
         self._ws: Dict[Tuple, SimpleNamespace] = {}
         self._shadow_version = None
@@ -175,13 +192,31 @@ class CaptionEngine:
         return torch.cuda.current_stream(self.device).cuda_stream
 
     class _Side:
-        def __init__(self, plan): self.plan = plan
-        def __enter__(self): self.plan.lane = 1
-        def __exit__(self, *a): self.plan.lane = 0
+        def __init__(self, plan, lane): self.plan, self.lane = plan, lane
+        def __enter__(self): self.prev, self.plan.lane = self.plan.lane, self.lane
+        def __exit__(self, *a): self.plan.lane = self.prev
 
-    def _side(self, plan: Plan):
-        """``with self._side(plan):`` -- calls added inside run on the side stream (off the critical path)."""
-        return CaptionEngine._Side(plan)
+    def _side(self, plan: Plan, lane: int = 1):
+        """``with self._side(plan):`` -- calls added inside run on a side stream (off the critical path).
+        lane 1: weight-gradient GEMMs, bias column sums, LayerNorm partial reductions; lane 2: optimizer slices."""
+        return CaptionEngine._Side(plan, lane)
+
+    def _adam_slice(self, plan: Plan, first: str, last: str):
+        """Optimizer-in-backward: update the arena slice [first .. last] (parameter names, arena order) on lane 2
+        as soon as backward has produced its gradients and no longer reads its weights."""
+        if not getattr(plan, "fuse_adam", False):
+            return
+        a = self.arena
+        lo = a.offset[first]
+        i = a.names.index(last)
+        hi = a.offset[a.names[i + 1]] if i + 1 < len(a.names) else a.numel
+        a.ensure_optimizer_state()
+        shadow = a.ensure_shadow().data_ptr() + 2 * lo if self.cdt == BF16 else None
+        with self._side(plan, 2):
+            plan.add(f"vct_adam:{first}..{last}", self.lib.vct_adam, a.p32.data_ptr() + 4 * lo, a.grad.data_ptr() + 4 * lo,
+                     a.exp_avg.data_ptr() + 4 * lo, a.exp_avg_sq.data_ptr() + 4 * lo, shadow, hi - lo,
+                     self.hyper.data_ptr(), 1.0)
+        plan.adam_covered = getattr(plan, "adam_covered", 0) + (hi - lo)
 
     def _scratch(self, ws, tag: str, rows: int, cols: int, dtype) -> torch.Tensor:
         """Per-use gradient scratch (never shared between call sites, so side-stream readers cannot race
@@ -506,20 +541,25 @@ class CaptionEngine:
     # ------------------------------------------------------------------------------------------
     # backward plan
     # ------------------------------------------------------------------------------------------
-    def plan_backward(self, ws, *, sce_first: bool, part: str = "all") -> Plan:
+    def plan_backward(self, ws, *, sce_first: bool, part: str = "all", fuse_adam: bool = False) -> Plan:
         """part: 'all' (loss -> every gradient), 'dec' (loss -> decoder grads + d memory in ws.g_mem),
-        'enc' (ws.g_mem -> encoder grads)."""
-        key = ("bwd", sce_first, part)
+        'enc' (ws.g_mem -> encoder grads).  fuse_adam (single-GPU native trainer): every arena slice is updated
+        by vct_adam on lane 2 as soon as its gradient is final, overlapping the optimizer's HBM traffic with the
+        latency-bound remainder of backward."""
+        key = ("bwd", sce_first, part, fuse_adam)
         if key in ws.plans:
             return ws.plans[key]
         if not ws.training:
             raise RuntimeError("backward needs a training workspace")
         p = Plan()
         p.ws = ws
+        p.fuse_adam = fuse_adam
         if part in ("all", "dec"):
             self._build_decoder_bwd(p, ws, sce_first)
         if part in ("all", "enc"):
             self._build_encoder_bwd(p, ws)
+        if fuse_adam and p.adam_covered != self.arena.numel:
+            raise RuntimeError(f"optimizer slices cover {p.adam_covered} of {self.arena.numel} arena elements")
         ws.plans[key] = p
         return p
 
@@ -543,6 +583,7 @@ class CaptionEngine:
         self._ln_bwd(p, "dec.norm", ws.g_a.data_ptr(), ws.dec_out.data_ptr(), ws.hfin_stats[0].data_ptr(),
                      ws.hfin_stats[1].data_ptr(), "cap_decoder.decoder.norm.weight", "cap_decoder.decoder.norm.bias",
                      ws.g_b.data_ptr(), None, None, Rd, 0.0, 0, ws)
+        self._adam_slice(p, "cap_decoder.decoder.norm.weight", "cap_decoder.generator.bias")
         dx, other = ws.g_b, ws.g_a          # dx: gradient wrt the current layer's output
         first_mem = True
         for l in reversed(range(D.L_dec)):
@@ -622,9 +663,11 @@ class CaptionEngine:
             self._gemm(p, f"dec{l}.self.in_proj.dgrad", Rd, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
                        addend=ws.g_s.data_ptr(), ld_addend=d)
             dx, other = other, dx           # dx = grad wrt the layer input
+            self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm3.bias")
         # ---- embedding ---------------------------------------------------------------------------
         p.add("vct_embed_bwd", lib.vct_embed_bwd, ws.ids.data_ptr(), S + 1, dx.data_ptr(),
               self._g("cap_decoder.tgt_to_emb.weight"), B, S, d, D.V, D.pad_id, pd, self.rng_state.data_ptr(), SITE_EMBED)
+        self._adam_slice(p, "cap_decoder.tgt_to_emb.weight", "cap_decoder.tgt_to_emb.weight")
 
     def _build_encoder_bwd(self, p: Plan, ws):
         D, lib = self.dims, self.lib
@@ -636,6 +679,7 @@ class CaptionEngine:
         self._ln_bwd(p, "enc.norm", ws.g_mem.data_ptr(), ws.enc_out.data_ptr(), ws.mem_stats[0].data_ptr(),
                      ws.mem_stats[1].data_ptr(), "video_encoder.transformer_encoder.norm.weight",
                      "video_encoder.transformer_encoder.norm.bias", ws.g_a.data_ptr(), None, None, Re, 0.0, 0, ws)
+        self._adam_slice(p, "video_encoder.transformer_encoder.norm.weight", "video_encoder.transformer_encoder.norm.bias")
         dx, other = ws.g_a, ws.g_b
         g_o = ws.g_o_c.data_ptr()
         for l in reversed(range(D.L_enc)):
@@ -684,11 +728,13 @@ class CaptionEngine:
                        addend=ws.g_s.data_ptr(), ld_addend=d,
                        C2=ws.g_x0_c.data_ptr() if (last and cd == BF16) else None, c2_dtype=cd, ldc2=d)
             dx, other = other, dx
+            self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm2.bias")
         g_x0_c = ws.g_x0_c.data_ptr() if cd == BF16 else dx.data_ptr()
         with side(p):
             self._gemm(p, "unify.wgrad", d, D.Din, Re, g_x0_c, d, 1, ws.a0.data_ptr(), D.Din, 1,
                        self._g("video_encoder.unify.0.weight"), F32, D.Din)
             self._colsum(p, "unify.bias", g_x0_c, d, Re, d, self._g("video_encoder.unify.0.bias"), ws)
+        self._adam_slice(p, "video_encoder.unify.0.weight", "video_encoder.unify.0.bias")
 
     # ------------------------------------------------------------------------------------------
     # running
@@ -706,7 +752,7 @@ class CaptionEngine:
             torch.eq(ws.ids[:, :-1], self.dims.pad_id, out=ws.tok_pad.view(torch.bool))
 
     def run(self, plan: Plan) -> None:
-        self.launches += plan.run(torch.cuda.current_stream(self.device), self.side_stream)
+        self.launches += plan.run(torch.cuda.current_stream(self.device), self.side_streams)
 
     def zero_scatter_grads(self) -> None:
         """Only the embedding gradient is accumulated with atomics; every other gradient is overwritten."""

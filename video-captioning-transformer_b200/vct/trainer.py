@@ -13,6 +13,7 @@ folded into the Adam kernel.
 """
 from __future__ import annotations
 
+import os
 from typing import List, Optional, Tuple
 
 import torch
@@ -68,6 +69,7 @@ class CaptionTrainer:
         self.engine.set_adam(lr, betas, eps, weight_decay)
         self.engine.refresh_shadow(force=True)
         self.use_graph = use_graph
+        self.fuse_adam = os.environ.get("VCT_FUSE_ADAM", "1") != "0" and self.engine.side_streams is not None
         self.group = process_group
         self.world = world_size if world_size is not None else (dist.get_world_size(process_group)
                                                                  if dist.is_available() and dist.is_initialized() else 1)
@@ -83,12 +85,12 @@ class CaptionTrainer:
         self.engine.set_lr(lr)
 
     # ---- one step -----------------------------------------------------------------------------------
-    def _compute(self, ws) -> None:
+    def _compute(self, ws, fuse_adam: bool = False) -> None:
         eng = self.engine
         eng.tick()
         eng.zero_scatter_grads()
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
-        eng.run(eng.plan_backward(ws, sce_first=False, part="all"))
+        eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=fuse_adam))
 
     def _update(self) -> None:
         self.engine.adam(grad_scale=1.0 / self.world)
@@ -128,7 +130,10 @@ class CaptionTrainer:
         eng.check_arena()
         eng.refresh_shadow()               # no-op unless the masters were edited outside vct_adam
         eng.stage_inputs(ws, feats, vid_pad, ids)
-        if self.world == 1:
+        if self.world == 1 and self.fuse_adam:
+            # optimizer-in-backward: vct_adam runs slice by slice on a side lane while backward continues
+            self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True))
+        elif self.world == 1:
             self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()))
         else:
             self._graphed((B, T, S, "compute"), lambda: self._compute(ws))
