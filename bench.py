@@ -324,6 +324,23 @@ def main():
         else:
             roofline = {"kernel": names[top], "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                         "frac": None, "traffic": None, "ms": med[top], "peak_source": peaks["src"]}
+    # ---- phase timing (rank 0): eager run of the same plans with the side lanes active ----------------
+    phase_ms = None
+    if rank == 0:
+        ws = eng.workspace(B, T, S1 - 1, True)
+        fwd = eng.plan_forward(ws, fused_grad=True, part="all")
+        bwd = eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=(world == 1 and trainer.fuse_adam))
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        acc = [0.0, 0.0]
+        for rep in range(4):
+            torch.cuda._sleep(int(2e7))
+            ev[0].record(); eng.run(fwd); ev[1].record(); eng.run(bwd); ev[2].record()
+            torch.cuda.synchronize()
+            if rep:
+                acc[0] += ev[0].elapsed_time(ev[1]) / 3
+                acc[1] += ev[1].elapsed_time(ev[2]) / 3
+        phase_ms = {"forward": round(acc[0], 4), "backward_incl_side_lanes": round(acc[1], 4),
+                    "n_forward_calls": len(fwd), "n_backward_calls": len(bwd)}
     # ---- cpu baseline (rank 0, N = 1 only) --------------------------------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -343,7 +360,7 @@ def main():
                 "e2e": {"value": B * world * args.steps / float(e2e_s.item()), "unit": "captions/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "loss": final_loss, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "kernel_ms": breakdown}
+                "cpu_baseline": cpu, "kernel_ms": breakdown, "phase_ms": phase_ms}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -24,7 +24,11 @@ if os.environ.get("VARIANTS"):
 reps = int(os.environ.get("REPS", "20"))
 if os.environ.get("FIXED"):
     SHAPES = [("tiny 1 cta ", 128, 64, 64, 0, 0, L.F32), ("1cta K768  ", 128, 64, 768, 0, 0, L.F32), ("1cta K768 N256", 128, 256, 768, 0, 0, L.F32),
-              ("120cta K64 ", 1280, 768, 64, 0, 0, L.F32), ("120cta K768", 1280, 768, 768, 0, 0, L.F32)]
+              ("120cta K64 ", 1280, 768, 64, 0, 0, L.F32), ("120cta K768", 1280, 768, 768, 0, 0, L.F32),
+              ("8cta N256  ", 1024, 256, 768, 0, 0, L.F32), ("32cta N256 ", 4096, 256, 768, 0, 0, L.F32),
+              ("90cta N256 ", 1280, 2304, 768, 0, 0, L.F32), ("90cta mfan ", 11520, 256, 768, 0, 0, L.F32),
+              ("90cta nfan ", 128, 23040, 768, 0, 0, L.F32), ("148cta N256", 18944, 256, 768, 0, 0, L.F32),
+              ("148 K3072  ", 18944, 256, 3072, 0, 0, L.F32)]
     # launch gap of a chain of trivial dependent kernels
     rng = torch.zeros(2, dtype=torch.int64, device=dev); hyper = torch.zeros(8, device=dev)
     st = torch.cuda.Stream()

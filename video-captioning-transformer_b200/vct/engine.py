@@ -919,8 +919,29 @@ class CaptionEngine:
         self.run(self.plan_decode_init(dws, enc_ws))
         n = 1
         probs = [[] for _ in dws.layers] if want_probs else None
+        use_graph = os.environ.get("VCT_DECODE_GRAPH", "1") != "0" and not want_probs
         for t in range(max_len - 1):
-            self.run(self.plan_decode_step(dws, t, want_probs))
+            plan = self.plan_decode_step(dws, t, want_probs)
+            if use_graph:
+                # the step's launch sequence is static: first use runs eagerly, second use is captured, later uses replay
+                seen = dws.plans.get(("seen", t), 0)
+                g = dws.plans.get(("graph", t))
+                if g is not None:
+                    g.replay()
+                    self.launches += len(plan)
+                elif seen >= 1:
+                    g = torch.cuda.CUDAGraph()
+                    before = self.launches
+                    with torch.cuda.graph(g):
+                        self.run(plan)
+                    self.launches = before + len(plan)
+                    dws.plans[("graph", t)] = g
+                    g.replay()
+                else:
+                    self.run(plan)
+                    dws.plans[("seen", t)] = seen + 1
+            else:
+                self.run(plan)
             n = t + 2
             if want_probs:
                 for l, e in enumerate(dws.layers):
