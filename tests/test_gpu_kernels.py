@@ -447,3 +447,49 @@ def test_gemm_tcgen05_epilogues_match_simt(lib):
         torch.testing.assert_close(c_t.float(), c_s.float(), **tol)
         if c2_s is not None:
             torch.testing.assert_close(c2_t.float(), c2_s.float(), rtol=2e-2, atol=2e-2)
+
+
+# ---- fused in-projection + attention kernel (attn_fused.cu) vs projection GEMM + stand-alone core -------------
+def _run_self_flavour(lib, x, w, b, key_pad, B, Lq, d, H, causal, impl, drop_p=0.0, rng=None):
+    from vct import lib as VL
+    m = VL.MhaArgs()
+    qkv = torch.full((B * Lq, 3 * d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    o = torch.full((B * Lq, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    probs = torch.zeros(B, H, Lq, Lq, device=DEV)
+    m.B, m.L, m.Lk, m.d, m.H, m.dtype = B, Lq, Lq, d, H, L_BF16
+    m.x, m.w_in, m.b_in = x.data_ptr(), w.data_ptr(), b.data_ptr()
+    m.qkv, m.o, m.key_pad = qkv.data_ptr(), o.data_ptr(), key_pad.data_ptr()
+    m.drop_p, m.rng_state, m.site = drop_p, (rng.data_ptr() if rng is not None else None), 321
+    m.probs = probs.data_ptr()
+    m.gemm_impl = impl
+    fn = lib.vct_attn_dec_self_fwd if causal else lib.vct_attn_enc_self_fwd
+    L_check(fn(C.byref(m), stream()))
+    torch.cuda.synchronize()
+    return qkv, o, probs
+
+
+L_BF16 = L.BF16
+L_check = L.check
+
+
+@pytest.mark.parametrize("B,Lq,d,H,causal", [(64, 13, 768, 8, 0), (64, 20, 768, 8, 1), (7, 20, 768, 8, 1), (16, 33, 768, 8, 0),
+                                             (64, 13, 512, 8, 0), (5, 20, 512, 8, 1), (3, 64, 512, 8, 1)])
+def test_fused_self_attention_matches_composition(lib, B, Lq, d, H, causal, monkeypatch):
+    monkeypatch.setenv("VCT_FUSED_ATTN", "1")       # the fused kernel is opt-in (see attn_fused.cu)
+    g = torch.Generator().manual_seed(B + Lq + d)
+    x = torch.randn(B * Lq, d, generator=g).to(DEV, torch.bfloat16)
+    w = (torch.randn(3 * d, d, generator=g) * 0.04).to(DEV, torch.bfloat16)
+    b = (torch.randn(3 * d, generator=g) * 0.1).to(DEV)
+    key_pad = torch.zeros(B, Lq, dtype=torch.uint8)
+    for bb in range(1, B):
+        key_pad[bb, Lq - (bb % 5):] = 1 if bb % 5 else 0
+    key_pad = key_pad.to(DEV)
+    for p in (0.0, 0.3):
+        rng = torch.tensor([77, 5], dtype=torch.int64, device=DEV)
+        qf, of, pf = _run_self_flavour(lib, x, w, b, key_pad, B, Lq, d, H, causal, L.GEMM_TCGEN05, p, rng)
+        qs, os_, ps = _run_self_flavour(lib, x, w, b, key_pad, B, Lq, d, H, causal, L.GEMM_SIMT, p, rng)
+        assert torch.isfinite(of.float()).all() and torch.isfinite(qf.float()).all()
+        torch.testing.assert_close(qf.float(), qs.float(), rtol=2e-2, atol=2e-2)      # both bf16-rounded projections
+        # the fused kernel attends over un-rounded fp32 q/k/v, the composition over their bf16 roundings
+        torch.testing.assert_close(pf, ps, rtol=5e-2, atol=5e-3)
+        torch.testing.assert_close(of.float(), os_.float(), rtol=5e-2, atol=3e-2)

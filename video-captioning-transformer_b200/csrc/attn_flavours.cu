@@ -1,8 +1,13 @@
-// The three attention flavours of the reference as single C-ABI calls:
-// packed in-projection (GEMM with bias epilogue) followed by the attention core.
+// The three attention flavours of the reference as single C-ABI calls.  Self-attention (encoder, decoder causal)
+// in bf16 runs as ONE fused kernel (attn_fused.cu); the remaining cases compose the packed in-projection GEMM with
+// the stand-alone attention core.
 #include "common.cuh"
 
 using namespace vct;
+
+namespace vct {
+int attn_fused_self(const vct_mha_args* m, int causal, cudaStream_t st);   // attn_fused.cu
+}
 
 namespace {
 
@@ -26,6 +31,12 @@ int self_attention(const vct_mha_args* a, int causal, vct_stream_t stream, const
     VCT_REQUIRE(a && a->x && a->w_in && a->qkv && a->o, "%s: null argument", who);
     VCT_REQUIRE(a->d % a->H == 0, "%s: d %% H != 0", who);
     const int d = a->d, rows = a->B * a->L;
+    // bf16 + tcgen05: ONE kernel does the in-projection and the attention (attn_fused.cu); other dtypes / head sizes
+    // compose the projection GEMM with the stand-alone attention core
+    {
+        const int r = vct::attn_fused_self(a, causal, (cudaStream_t)stream);
+        if (r <= 0) return r;
+    }
     if (int e = project(a->x, rows, d, 3 * d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream)) return e;
     vct_attn_args t;
     memset(&t, 0, sizeof(t));

@@ -19,61 +19,14 @@
 #include <unordered_map>
 
 #include "gemm_epilogue.cuh"
+#include "tc_common.cuh"
 
 using namespace vct;
 
 namespace {
 
-constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 64;                 // 64 bf16 = 128 bytes = one swizzle span
-constexpr int UMMA_K = 16;
 constexpr int kThreads = 192;
-constexpr uint32_t kABytes = BLOCK_M * BLOCK_K * 2;
 constexpr int kSmemBudget = 200 * 1024;
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    uint32_t done = 0;
-    while (true) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (clock64() - t0 > 4000000000ll) __trap();   // ~2 s: a protocol bug must not hang the GPU
-    }
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
-        : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-        : "memory");
-}
-
-// UMMA shared-memory descriptor, SWIZZLE_128B, sm_100 version bits (cute::UMMA::SmemDescriptor)
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-    return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16) |
-           ((uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32) | (1ull << 46) | (2ull << 61);
-}
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -430,66 +383,6 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long ldw, Ep
 // ---------------------------------------------------------------------------------------------------
 // host: tensor maps (cached) and dispatch
 // ---------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    static std::once_flag once;
-    std::call_once(once, [] {
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    });
-    return fn;
-}
-
-struct MapKey {
-    const void* ptr; long long inner, outer, ld; int box_inner, box_outer;
-    bool operator==(const MapKey& o) const {
-        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
-               box_outer == o.box_outer;
-    }
-};
-struct MapHash {
-    size_t operator()(const MapKey& k) const {
-        size_t h = std::hash<const void*>()(k.ptr);
-        auto mix = [&h](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
-        mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
-        return h;
-    }
-};
-
-// 2-D bf16 tensor: `inner` contiguous elements, `outer` rows `ld` elements apart; box [box_inner x box_outer]
-int get_map(const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, CUtensorMap* out) {
-    static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
-    static std::mutex mu;
-    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        auto it = cache.find(key);
-        if (it != cache.end()) { *out = it->second; return 0; }
-    }
-    EncodeTiledFn enc = get_encode();
-    VCT_REQUIRE(enc != nullptr, "vct_gemm(tcgen05): cuTensorMapEncodeTiled not available from the driver");
-    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    VCT_REQUIRE(r == CUDA_SUCCESS, "vct_gemm(tcgen05): cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%lld outer=%lld ld=%lld",
-                (int)r, ptr, inner, outer, ld);
-    std::lock_guard<std::mutex> lk(mu);
-    if (cache.size() > 4096) cache.clear();
-    cache[key] = *out;
-    return 0;
-}
-
 template <int BLOCK_N, bool A_MN, bool B_MN, int ACT>
 int launch_tile(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
     constexpr int kStage = kABytes + BLOCK_N * BLOCK_K * 2;
@@ -551,6 +444,67 @@ int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtenso
 
 namespace vct {
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+struct MapKey {
+    const void* ptr; long long inner, outer, ld; int box_inner, box_outer;
+    bool operator==(const MapKey& o) const {
+        return ptr == o.ptr && inner == o.inner && outer == o.outer && ld == o.ld && box_inner == o.box_inner &&
+               box_outer == o.box_outer;
+    }
+};
+struct MapHash {
+    size_t operator()(const MapKey& k) const {
+        size_t h = std::hash<const void*>()(k.ptr);
+        auto mix = [&h](long long v) { h ^= std::hash<long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+        mix(k.inner); mix(k.outer); mix(k.ld); mix(k.box_inner); mix(k.box_outer);
+        return h;
+    }
+};
+
+// 2-D bf16 tensor: `inner` contiguous elements, `outer` rows `ld` elements apart; box [box_inner x box_outer]
+int get_tensor_map(const void* ptr, long long inner, long long outer, long long ld, int box_inner, int box_outer, CUtensorMap* out) {
+    static std::unordered_map<MapKey, CUtensorMap, MapHash> cache;
+    static std::mutex mu;
+    MapKey key{ptr, inner, outer, ld, box_inner, box_outer};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = get_encode();
+    VCT_REQUIRE(enc != nullptr, "vct_gemm(tcgen05): cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VCT_REQUIRE(r == CUDA_SUCCESS, "vct_gemm(tcgen05): cuTensorMapEncodeTiled failed (%d) ptr=%p inner=%lld outer=%lld ld=%lld",
+                (int)r, ptr, inner, outer, ld);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return 0;
+}
+
+
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     VCT_REQUIRE(a->a_dtype == VCT_BF16, "vct_gemm(tcgen05): operands must be bf16");
     VCT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "vct_gemm(tcgen05): lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
@@ -583,10 +537,10 @@ int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
         }
     }
     CUtensorMap tmA, tmB;
-    if (!a->a_trans) { if (int e = get_map(a->A, a->K, a->M, a->lda, BLOCK_K, BLOCK_M, &tmA)) return e; }
-    else             { if (int e = get_map(a->A, a->M, a->K, a->lda, 64, BLOCK_K, &tmA)) return e; }
-    if (!a->b_trans) { if (int e = get_map(a->B, a->K, a->N, a->ldb, BLOCK_K, bn, &tmB)) return e; }
-    else             { if (int e = get_map(a->B, a->N, a->K, a->ldb, 64, BLOCK_K, &tmB)) return e; }
+    if (!a->a_trans) { if (int e = get_tensor_map(a->A, a->K, a->M, a->lda, BLOCK_K, BLOCK_M, &tmA)) return e; }
+    else             { if (int e = get_tensor_map(a->A, a->M, a->K, a->lda, 64, BLOCK_K, &tmA)) return e; }
+    if (!a->b_trans) { if (int e = get_tensor_map(a->B, a->K, a->N, a->ldb, BLOCK_K, bn, &tmB)) return e; }
+    else             { if (int e = get_tensor_map(a->B, a->N, a->K, a->ldb, 64, BLOCK_K, &tmB)) return e; }
     if (bn == 256 && splits == 1 && a->act == VCT_ACT_NONE && persistent) {
         if (!a->a_trans && !a->b_trans) return launch_persistent<false, false>(a, tmA, tmB, st);
         if (!a->a_trans && a->b_trans) return launch_persistent<false, true>(a, tmA, tmB, st);
