@@ -56,12 +56,13 @@ class Plan:
         additionally waits for lane 1 (whose kernels produce the gradients it consumes).  main joins every used
         side lane at the end."""
         mp = main.cuda_stream
+        n_kernels = sum(1 for c in self.calls if not c[0].startswith("py:"))
         if not sides or not any(c[3] for c in self.calls):
             for name, fn, args, _ in self.calls:
-                rc = fn(*args, mp)
-                if rc != 0:
+                rc = fn(main) if name.startswith("py:") else fn(*args, mp)
+                if rc:
                     L.check(rc, name)
-            return len(self.calls)
+            return n_kernels
         ev_i = 0
 
         def event():
@@ -78,7 +79,7 @@ class Plan:
         for name, fn, args, lane in self.calls:
             lane = min(lane, nl - 1)
             if lane == 0:
-                rc = fn(*args, mp)
+                rc = fn(main) if name.startswith("py:") else fn(*args, mp)
                 main_seen = [False] * nl
             else:
                 st = sides[lane - 1]
@@ -92,18 +93,18 @@ class Plan:
                     e.record(sides[0])
                     st.wait_event(e)
                     lane1_seen2 = True
-                rc = fn(*args, st.cuda_stream)
+                rc = fn(st) if name.startswith("py:") else fn(*args, st.cuda_stream)
                 used[lane] = True
                 if lane == 1:
                     lane1_seen2 = False
-            if rc != 0:
+            if rc:
                 L.check(rc, name)
         for k in range(1, nl):
             if used[k]:
                 e = event()
                 e.record(sides[k - 1])
                 main.wait_event(e)
-        return len(self.calls)
+        return n_kernels
 
     def __len__(self):
         return len(self.calls)
@@ -212,10 +213,25 @@ class CaptionEngine:
         hi = a.offset[a.names[i + 1]] if i + 1 < len(a.names) else a.numel
         a.ensure_optimizer_state()
         shadow = a.ensure_shadow().data_ptr() + 2 * lo if self.cdt == BF16 else None
+        grad_scale = 1.0
         with self._side(plan, 2):
+            ar = getattr(plan, "allreduce", None)
+            if ar is not None:
+                # data parallel: SUM all-reduce of this gradient slice over NCCL on the optimizer lane, overlapping
+                # the rest of backward; 1/world is folded into the Adam kernel (DDP averages, train.py:218)
+                group, world = ar
+                flat = a.grad[lo:hi]
+                grad_scale = 1.0 / world
+
+                def all_reduce(stream, flat=flat, group=group):
+                    import torch.distributed as dist
+                    with torch.cuda.stream(stream):
+                        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                    return 0
+                plan.add(f"py:all_reduce:{first}..{last}", all_reduce)
             plan.add(f"vct_adam:{first}..{last}", self.lib.vct_adam, a.p32.data_ptr() + 4 * lo, a.grad.data_ptr() + 4 * lo,
                      a.exp_avg.data_ptr() + 4 * lo, a.exp_avg_sq.data_ptr() + 4 * lo, shadow, hi - lo,
-                     self.hyper.data_ptr(), 1.0)
+                     self.hyper.data_ptr(), grad_scale)
         plan.adam_covered = getattr(plan, "adam_covered", 0) + (hi - lo)
 
     def _scratch(self, ws, tag: str, rows: int, cols: int, dtype) -> torch.Tensor:
@@ -541,12 +557,12 @@ class CaptionEngine:
     # ------------------------------------------------------------------------------------------
     # backward plan
     # ------------------------------------------------------------------------------------------
-    def plan_backward(self, ws, *, sce_first: bool, part: str = "all", fuse_adam: bool = False) -> Plan:
+    def plan_backward(self, ws, *, sce_first: bool, part: str = "all", fuse_adam: bool = False, allreduce=None) -> Plan:
         """part: 'all' (loss -> every gradient), 'dec' (loss -> decoder grads + d memory in ws.g_mem),
         'enc' (ws.g_mem -> encoder grads).  fuse_adam (single-GPU native trainer): every arena slice is updated
         by vct_adam on lane 2 as soon as its gradient is final, overlapping the optimizer's HBM traffic with the
         latency-bound remainder of backward."""
-        key = ("bwd", sce_first, part, fuse_adam)
+        key = ("bwd", sce_first, part, fuse_adam, allreduce is not None)
         if key in ws.plans:
             return ws.plans[key]
         if not ws.training:
@@ -554,6 +570,7 @@ class CaptionEngine:
         p = Plan()
         p.ws = ws
         p.fuse_adam = fuse_adam
+        p.allreduce = allreduce           # (process group, world size) or None
         if part in ("all", "dec"):
             self._build_decoder_bwd(p, ws, sce_first)
         if part in ("all", "enc"):

@@ -92,6 +92,12 @@ class CaptionTrainer:
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
         eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=fuse_adam))
 
+    def _forward(self, ws) -> None:
+        eng = self.engine
+        eng.tick()
+        eng.zero_scatter_grads()
+        eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
+
     def _update(self) -> None:
         self.engine.adam(grad_scale=1.0 / self.world)
 
@@ -121,8 +127,9 @@ class CaptionTrainer:
         device tensors).  Returns the step's loss as a device scalar (no host sync).
 
         world == 1: [tick, forward, backward, Adam] is ONE CUDA graph.
-        world  > 1: graph [tick, forward, backward] -> NCCL SUM all-reduce of the gradient arena (bucketed,
-        issued eagerly: collectives stay outside graph capture) -> graph [Adam with 1/world folded in]."""
+        world  > 1: graph [tick, forward]; eager backward whose optimizer lane all-reduces (NCCL SUM) and then
+        updates each arena slice as soon as its gradient is final (VCT_FUSE_ADAM=0: graph [tick, forward,
+        backward] -> bucketed all-reduce -> graph [Adam])."""
         eng = self.engine
         B, T, _ = feats.shape
         S = ids.shape[1] - 1
@@ -135,6 +142,12 @@ class CaptionTrainer:
             self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True))
         elif self.world == 1:
             self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()))
+        elif self.fuse_adam:
+            # data parallel with overlap: forward is a CUDA graph; backward runs eagerly because NCCL collectives stay
+            # outside graph capture -- each arena slice is all-reduced and then updated on the optimizer lane while
+            # the rest of backward continues on the main lane
+            self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
+            eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=(self.group, self.world)))
         else:
             self._graphed((B, T, S, "compute"), lambda: self._compute(ws))
             all_reduce_flat(eng.arena.grad, self.buckets, self.group)
