@@ -50,15 +50,21 @@ class Plan:
     def add(self, name: str, fn, *args):
         self.calls.append((name, fn, args, self.lane))
 
+    def add_join(self):
+        """main waits here for everything the side lanes have been given so far."""
+        self.calls.append(("join", None, (), 0))
+
     def run(self, main, sides=None) -> int:
         """main: torch.cuda.Stream; sides: list of side streams (lane k runs on sides[k-1]) or None (everything
         runs on main).  A side-lane call waits for everything main has issued so far; lane 2 (the optimizer lane)
         additionally waits for lane 1 (whose kernels produce the gradients it consumes).  main joins every used
         side lane at the end."""
         mp = main.cuda_stream
-        n_kernels = sum(1 for c in self.calls if not c[0].startswith("py:"))
+        n_kernels = sum(1 for c in self.calls if not c[0].startswith("py:") and c[0] != "join")
         if not sides or not any(c[3] for c in self.calls):
             for name, fn, args, _ in self.calls:
+                if name == "join":
+                    continue
                 rc = fn(main) if name.startswith("py:") else fn(*args, mp)
                 if rc:
                     L.check(rc, name)
@@ -78,6 +84,14 @@ class Plan:
         used = [False] * nl
         for name, fn, args, lane in self.calls:
             lane = min(lane, nl - 1)
+            if name == "join":
+                for k in range(1, nl):
+                    if used[k]:
+                        e = event()
+                        e.record(sides[k - 1])
+                        main.wait_event(e)
+                        used[k] = False
+                continue
             if lane == 0:
                 rc = fn(main) if name.startswith("py:") else fn(*args, mp)
                 main_seen = [False] * nl
@@ -467,7 +481,17 @@ class CaptionEngine:
                      ws.mem_c.data_ptr() if cd == BF16 else None, None, ws.mem_stats[0].data_ptr(),
                      ws.mem_stats[1].data_ptr(), Re, 0.0, 0)
 
-    def _build_decoder(self, plan: Plan, ws, p_drop: float, with_loss: bool, with_grad: bool):
+    def _build_cross_kv(self, plan: Plan, ws):
+        """K/V projections of the encoder memory for every decoder layer (rows [d:3d] of multihead_attn.in_proj)."""
+        D = self.dims
+        d = D.d
+        for l, e in enumerate(ws.dec):
+            pre = f"cap_decoder.decoder.layers.{l}.multihead_attn."
+            self._gemm(plan, f"dec{l}.cross.kv", ws.B * ws.M, 2 * d, d, ws.mem_c.data_ptr(), d, 0,
+                       self._w(pre + "in_proj_weight", d), d, 0, e.kv.data_ptr(), self.cdt, 2 * d,
+                       bias=self._p(pre + "in_proj_bias", d))
+
+    def _build_decoder(self, plan: Plan, ws, p_drop: float, with_loss: bool, with_grad: bool, kv_ready: bool = False):
         D, lib = self.dims, self.lib
         d, B, S, M = D.d, ws.B, ws.S, ws.M
         Re, Rd = B * M, B * S
@@ -495,7 +519,9 @@ class CaptionEngine:
             c.B, c.L, c.Lk, c.d, c.H, c.dtype = B, S, M, d, D.H_dec, cd
             c.x, c.mem = e.x1_c.data_ptr(), ws.mem_c.data_ptr()
             c.w_in, c.b_in = self._w(pre + "multihead_attn.in_proj_weight"), self._p(pre + "multihead_attn.in_proj_bias")
-            c.qkv, c.kv, c.kv_ready, c.o = e.q.data_ptr(), e.kv.data_ptr(), 0, e.ao2.data_ptr()
+            c.qkv, c.kv, c.kv_ready, c.o = e.q.data_ptr(), e.kv.data_ptr(), int(kv_ready), e.ao2.data_ptr()
+            if kv_ready and l == 0:
+                plan.add_join()                  # encoder memory + K/V projections (lane 1) are needed from here on
             c.drop_p, c.rng_state, c.site = p_drop, self.rng_state.data_ptr(), _dec_site(l, 2)
             c.gemm_impl = self.gemm_impl
             plan.keep.append(c)
@@ -541,8 +567,13 @@ class CaptionEngine:
             p.ws = ws
             pd = float(self.dims.dropout) if ws.training else 0.0
             if part == "all":
-                self._build_encoder(p, ws, pd)
-            self._build_decoder(p, ws, pd, with_loss=with_loss, with_grad=fused_grad)
+                # the encoder and the cross-attention K/V projections of every decoder layer run on lane 1 while the
+                # main lane embeds the tokens and runs the first decoder self-attention block; they join before the
+                # first cross-attention
+                with self._side(p, 1):
+                    self._build_encoder(p, ws, pd)
+                    self._build_cross_kv(p, ws)
+            self._build_decoder(p, ws, pd, with_loss=with_loss, with_grad=fused_grad, kv_ready=(part == "all"))
             ws.plans[key] = p
         return ws.plans[key]
 
