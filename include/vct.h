@@ -91,6 +91,17 @@ typedef struct {
 
 int vct_gemm(const vct_gemm_args* args, vct_stream_t stream);
 
+/* Tuning hook for the tcgen05 path (tools/gemm_sweep.py): force the tile width (block_n = 64 / 128 / 256;
+ * 0 restores the built-in cost model), the split-K factor (0/1 = none) and the kernel flavour
+ * (ring = 0: one CTA per SM with the full operand ring, 1: half ring so two CTAs share an SM,
+ * -1: persistent kernel, block_n 256 only).  Process-wide; not used on the product path. */
+int vct_gemm_tune(int block_n, int splits, int ring);
+/* Debug: CTA (0,0,0) of every following tcgen05 tile kernel writes clock64 timestamps of its pipeline phases
+ * into dev_buf (>= 128 int64; NULL turns tracing off): [0] entry, [1] setup done, [2] after griddepcontrol.wait,
+ * [3] last MMA committed, [4] accumulator visible to the epilogue, [5] TMEM drained to smem, [6] stores issued,
+ * [7] exit; [16+kb] TMA of k-block kb issued, [56+kb] operands of k-block kb landed. */
+int vct_gemm_trace(void* dev_buf);
+
 /* ---- frame staging -----------------------------------------------------------------------
  * feats fp32 [B,T,Din] -> out [B*(T+1), Din]: row 0 of each batch element = mean over ALL T
  * frames (padded ones included), rows 1..T = the frames.  Because unify is linear,

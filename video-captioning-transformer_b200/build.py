@@ -13,12 +13,13 @@ from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libvct_b200.so")
-OBJ = os.path.join(HERE, "build")
+TRACE = os.environ.get("VCT_TRACE_BUILD") == "1"      # per-k-block pipeline timestamps in the tcgen05 GEMM (tools/gemm_trace.py)
+OUT = os.path.join(HERE, "libvct_b200_trace.so" if TRACE else "libvct_b200.so")
+OBJ = os.path.join(HERE, "build_trace" if TRACE else "build")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
          "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
-FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"]
+FLAGS = [f for f in FLAGS if f != "--use_fast_math=false"] + (["-DVCT_GEMM_TRACE_KB"] if TRACE else [])
 
 
 def _sources():

@@ -18,6 +18,7 @@ struct Epilogue {
     const void* aux; int aux_dtype; long long ld_aux;
     float drop_p; const unsigned long long* rng_state; unsigned int site;
     int vec_ok;   // leading dimensions / pointers allow 16-byte loads and stores for full groups of 4 columns
+    long long* trace;   // debug: CTA (0,0,0) writes clock64 timestamps of its pipeline phases here (NULL = off)
 };
 
 inline Epilogue make_epilogue(const vct_gemm_args* a) {
@@ -31,6 +32,7 @@ inline Epilogue make_epilogue(const vct_gemm_args* a) {
     e.act = a->act;
     e.aux = a->aux; e.aux_dtype = a->aux_dtype; e.ld_aux = a->ld_aux;
     e.drop_p = a->drop_p; e.rng_state = a->rng_state; e.site = a->site;
+    e.trace = nullptr;
     auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     e.vec_ok = (a->ldc % 4 == 0) && (a->C2 == nullptr || a->ldc2 % 4 == 0) &&
                (a->addend == nullptr || (a->ld_addend % 4 == 0 && al16(a->addend))) &&
@@ -164,6 +166,146 @@ __device__ __forceinline__ void epilogue_store8(const Epilogue& e, const Rng& rn
         const long long o2 = (long long)m * e.ldc2 + n;
         if (e.c2_dtype == VCT_BF16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, v);
         else st8(reinterpret_cast<float*>(e.C2) + o2, v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Tile epilogues of the tcgen05 kernels.  128 threads (t = 0..127) store a [rows x BN] fp32 accumulator tile
+// that has been staged in shared memory (row stride RS floats).  Everything that does not depend on the row
+// (column offset, bias, output pointers, feature flags) is hoisted out of the row loop, so that the loop body is
+// one shared load, the adds, and one (two) fully coalesced global store(s): a warp instruction covers 512
+// contiguous bytes of a row.  The generic per-element functions above remain the path for ragged / unaligned tiles.
+// ---------------------------------------------------------------------------------------------------------
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_plain(const Epilogue& e, const Rng& rng, const float* __restrict__ stage, int RS,
+                                                    int m0, int n0, int t) {
+    constexpr int CG4 = BN / 4, RSTEP = 128 / CG4;          // 4-column groups per row; rows covered per pass
+    const int c4 = t % CG4, n = n0 + c4 * 4;
+    if (n >= e.N) return;
+    const int rows = min(128, e.M - m0);
+    int rr = t / CG4;
+    const float* src = stage + rr * RS + c4 * 4;
+    if (!e.vec_ok || n + 4 > e.N) {
+        for (; rr < rows; rr += RSTEP, src += RSTEP * RS)
+            epilogue_scalar<VCT_ACT_NONE>(e, rng, m0 + rr, n, *reinterpret_cast<const float4*>(src));
+        return;
+    }
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias) b = ld4(e.bias + n);
+    const float* table = e.row_table;
+    const int period = e.row_period, N = e.N;
+    const bool c_bf16 = e.c_dtype == VCT_BF16, c2_bf16 = e.c2_dtype == VCT_BF16;
+    const long long ldc = e.ldc, ldc2 = e.ldc2, lda = e.ld_addend;
+    long long m = m0 + rr;
+    char* c = reinterpret_cast<char*>(e.C) + (m * ldc + n) * (c_bf16 ? 2 : 4);
+    char* c2 = e.C2 ? reinterpret_cast<char*>(e.C2) + (m * ldc2 + n) * (c2_bf16 ? 2 : 4) : nullptr;
+    const float* ad = e.addend ? e.addend + m * lda + n : nullptr;
+    const long long c_step = (long long)RSTEP * ldc * (c_bf16 ? 2 : 4), c2_step = (long long)RSTEP * ldc2 * (c2_bf16 ? 2 : 4);
+#pragma unroll 4
+    for (; rr < rows; rr += RSTEP, src += RSTEP * RS, m += RSTEP) {
+        float4 v = *reinterpret_cast<const float4*>(src);
+        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+        if (table) {
+            const float4 tb = ld4(table + (long long)((int)m % period) * N + n);
+            v.x += tb.x; v.y += tb.y; v.z += tb.z; v.w += tb.w;
+        }
+        if (ad) {
+            const float4 a4 = ld4(ad);
+            v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+            ad += (long long)RSTEP * lda;
+        }
+        if (c_bf16) st4(reinterpret_cast<__nv_bfloat16*>(c), v);
+        else st4(reinterpret_cast<float*>(c), v);
+        c += c_step;
+        if (c2) {
+            if (c2_bf16) st4(reinterpret_cast<__nv_bfloat16*>(c2), v);
+            else st4(reinterpret_cast<float*>(c2), v);
+            c2 += c2_step;
+        }
+    }
+}
+
+// raw fp32 partial sums of a split-K slice: ws[(z * M + m) * ldw + n]
+template <int BN>
+__device__ __forceinline__ void epilogue_tile_partial(float* __restrict__ ws, long long ldw, int M, int N, const float* __restrict__ stage,
+                                                      int RS, int m0, int n0, int t) {
+    constexpr int CG4 = BN / 4, RSTEP = 128 / CG4;
+    const int c4 = t % CG4, n = n0 + c4 * 4;
+    if (n >= N) return;                                     // ldw is a multiple of 8 >= N: whole float4 groups are in bounds
+    const int rows = min(128, M - m0);
+    int rr = t / CG4;
+    const float* src = stage + rr * RS + c4 * 4;
+    float* dst = ws + (long long)(m0 + rr) * ldw + n;
+#pragma unroll 4
+    for (; rr < rows; rr += RSTEP, src += RSTEP * RS, dst += (long long)RSTEP * ldw)
+        *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+}
+
+// activation epilogues (GELU forward / backward): 8-column groups per thread so that one Philox draw covers the
+// group's 8 dropout decisions and bf16 outputs are stored 16 bytes at a time
+template <int ACT, int BN>
+__device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& rng, const float* __restrict__ stage, int RS,
+                                                  int m0, int n0, int t) {
+    constexpr int CG = BN / 8, RSTEP = 128 / CG;
+    const int cg = t % CG, n = n0 + cg * 8;
+    if (n >= e.N) return;
+    const int rows = min(128, e.M - m0);
+    int rr = t / CG;
+    const float* src = stage + rr * RS + cg * 8;
+    if (!e.vec_ok || n + 8 > e.N) {
+        for (; rr < rows; rr += RSTEP, src += RSTEP * RS)
+            epilogue_store8<ACT>(e, rng, m0 + rr, n, *reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4));
+        return;
+    }
+    float b[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) b[q] = 0.f;
+    if (e.bias) ld8(e.bias + n, b);
+    const bool c_bf16 = e.c_dtype == VCT_BF16, c2_bf16 = e.c2_dtype == VCT_BF16, aux_bf16 = e.aux_dtype == VCT_BF16;
+    const long long ldc = e.ldc, ldc2 = e.ldc2, ldx = e.ld_aux, lda = e.ld_addend;
+    const unsigned long long N = (unsigned long long)e.N;
+    const unsigned int site = e.site;
+#pragma unroll 2
+    for (; rr < rows; rr += RSTEP, src += RSTEP * RS) {
+        const long long m = m0 + rr;
+        const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
+        float v[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3], a1.x + b[4], a1.y + b[5], a1.z + b[6], a1.w + b[7]};
+        float sc[8];
+        dropout_scale8(rng, site, ((unsigned long long)m * N + (unsigned long long)n) >> 3, sc);
+        if (ACT == VCT_ACT_GELU_FWD) {
+            const long long o = m * ldc + n;
+            if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
+            else st8(reinterpret_cast<float*>(e.C) + o, v);
+            if (e.C2) {
+                float h[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) h[q] = gelu_f(v[q]) * sc[q];
+                const long long o2 = m * ldc2 + n;
+                if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, h);
+                else st8(reinterpret_cast<float*>(e.C2) + o2, h);
+            }
+        } else {
+            float z[8];
+            const long long ao = m * ldx + n;
+            if (aux_bf16) ld8(reinterpret_cast<const __nv_bfloat16*>(e.aux) + ao, z);
+            else ld8(reinterpret_cast<const float*>(e.aux) + ao, z);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) v[q] *= dgelu_f(z[q]) * sc[q];
+            if (e.addend) {
+                float ad[8];
+                ld8(e.addend + m * lda + n, ad);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] += ad[q];
+            }
+            const long long o = m * ldc + n;
+            if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
+            else st8(reinterpret_cast<float*>(e.C) + o, v);
+            if (e.C2) {
+                const long long o2 = m * ldc2 + n;
+                if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, v);
+                else st8(reinterpret_cast<float*>(e.C2) + o2, v);
+            }
+        }
     }
 }
 

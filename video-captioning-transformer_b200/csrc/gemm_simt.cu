@@ -140,7 +140,21 @@ int gemm_simt(const vct_gemm_args* a, cudaStream_t st) {
     return launch_simt<float>(a, st);
 }
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st);   // gemm_tc.cu
+void gemm_tune(int bn, int splits, int low);                  // gemm_tc.cu
+void gemm_trace(long long* dev_buf);                          // gemm_tc.cu
 }  // namespace vct
+
+extern "C" int vct_gemm_tune(int block_n, int splits, int ring) {
+    VCT_REQUIRE(block_n == 0 || block_n == 64 || block_n == 128 || block_n == 256, "vct_gemm_tune: block_n must be 0, 64, 128 or 256");
+    VCT_REQUIRE(splits >= 0 && splits <= 8 && ring >= -1 && ring <= 1, "vct_gemm_tune: bad splits / ring");
+    vct::gemm_tune(block_n, splits, ring);
+    return 0;
+}
+
+extern "C" int vct_gemm_trace(void* dev_buf) {
+    vct::gemm_trace(reinterpret_cast<long long*>(dev_buf));
+    return 0;
+}
 
 extern "C" int vct_gemm(const vct_gemm_args* a, vct_stream_t stream) {
     VCT_REQUIRE(a != nullptr, "vct_gemm: null args");

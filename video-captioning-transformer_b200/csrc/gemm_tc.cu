@@ -3,9 +3,10 @@
 // instruction) issued by one elected thread, fp32 accumulators in TMEM, epilogue warps read TMEM with
 // tcgen05.ld and apply the fused epilogue (gemm_epilogue.cuh).
 //
-//   warp 0 : TMA producer (one elected lane)
+//   warp 0 : TMA producer of the A operand (one elected lane)
 //   warp 1 : TMEM allocation + MMA issuer (one elected lane)
 //   warps 2-5 : epilogue, one thread per accumulator row (TMEM lane)
+//   warp 6 : TMA producer of the B operand (one elected lane)
 //
 // Operand layouts (vct_gemm): "trans = 0" operands are K-major (rows x K, K contiguous) and are loaded
 // as one [rows x 64] box per stage; "trans = 1" operands are MN-major (K x rows, rows contiguous) and are
@@ -25,8 +26,11 @@ using namespace vct;
 
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;         // warp 0: A producer, 1: MMA issuer, 2-5: epilogue, 6: B producer
 constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudgetLow = 100 * 1024;       // two CTAs per SM (227 KB / 2 minus static smem and slack)
+int g_tune_bn = 0, g_tune_splits = 0, g_tune_low = 0;   // vct_gemm_tune
+long long* g_trace = nullptr;                           // vct_gemm_trace
 
 template <int BLOCK_N, bool A_MN, bool B_MN, int STAGES, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -44,6 +48,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.y * BLOCK_M, n0 = blockIdx.x * BLOCK_N;
+    long long* const trace = (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? epi.trace : nullptr;
+    if (trace && threadIdx.x == 0) trace[0] = clock64();
     // split-K: blockIdx.z owns the k-blocks [kb0, kb0 + num_kb)
     const int total_kb = (K + BLOCK_K - 1) / BLOCK_K;
     const int kb_per = (total_kb + (int)gridDim.z - 1) / (int)gridDim.z;
@@ -54,7 +60,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&full_bar[s]), 2);             // one arrive.expect_tx per producer thread
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         mbar_init(smem_u32(&tmem_full_bar), 1);
@@ -70,66 +76,112 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = tmem_base_slot;
+    if (trace && threadIdx.x == 0) trace[1] = clock64();
     // PDL: barrier init, TMEM allocation and descriptor prefetch above overlapped the predecessor's tail; nothing
     // before this point reads or writes global memory that another kernel of the step produces
     pdl_wait();
+    if (trace && threadIdx.x == 0) trace[2] = clock64();
 
-    if (warp == 0) {
-        if (lane == 0) {
-            // ===== TMA producer =====
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                const uint32_t full = smem_u32(&full_bar[s]);
-                mbar_expect_tx(full, kStageBytes);
-                const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
-                const int k0 = (kb0 + kb) * BLOCK_K;
-                if (!A_MN) {
-                    tma_load_2d(sa, &tmA, k0, m0, full);
-                } else {
+    // The producer and the MMA issuer are single threads: their loops are bound by instruction latency, not by
+    // the tensor pipe or L2 (measured: 536 cycles per k-block with a rolled loop = 4 tcgen05.mma of 32..128 cycles
+    // each).  The k-block loop is therefore unrolled by the ring depth: stage addresses, descriptors and barrier
+    // addresses become immediates, and the barrier probes take the single-instruction fast path.
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    if (warp == 0 || warp == 6) {
+        {
+            // ===== TMA producers: warp 0 loads the A tiles, warp 6 the B tiles =====
+            // (a single thread needs ~200 cycles per cp.async.bulk.tensor it issues, measured; with one thread per
+            // operand the ring fills twice as fast and the two loads of a k-block are in flight together)
+            const bool is_a = warp == 0;
+            uint32_t ph = 1u;                                  // parity of "slot free": passes on the fresh barriers
+            int k0 = kb0 * BLOCK_K;
+            for (int kbase = 0; kbase < num_kb; kbase += STAGES, ph ^= 1u) {
 #pragma unroll
-                    for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, k0, full);
-                }
-                if (!B_MN) {
-                    tma_load_2d(sb, &tmB, k0, n0, full);
-                } else {
+                for (int s = 0; s < STAGES; ++s) {
+                    if (kbase + s < num_kb) {
+                        mbar_wait_fast(empty0 + 8u * s, ph);
+#ifdef VCT_GEMM_TRACE_KB
+                        if (trace && lane == 0 && kbase + s < 20) trace[(is_a ? 16 : 36) + kbase + s] = clock64();
+#endif
+                        const uint32_t full = full0 + 8u * s;
+                        const uint32_t sa = smem0 + (uint32_t)s * kStageBytes, sb = sa + kABytes;
+                        if (elect_one()) {
+                            if (is_a) {
+                                mbar_expect_tx(full, kABytes);
+                                if (!A_MN) {
+                                    tma_load_2d(sa, &tmA, k0, m0, full);
+                                } else {
 #pragma unroll
-                    for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, k0, full);
+                                    for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, k0, full);
+                                }
+                            } else {
+                                mbar_expect_tx(full, kBBytes);
+                                if (!B_MN) {
+                                    tma_load_2d(sb, &tmB, k0, n0, full);
+                                } else {
+#pragma unroll
+                                    for (int c = 0; c < BLOCK_N / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, k0, full);
+                                }
+                            }
+                        }
+                        __syncwarp();
+                        k0 += BLOCK_K;
+                    }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ===== MMA issuer =====
+        {
+            // ===== MMA issuer (warp-uniform loop, one elected lane issues) =====
             // instruction descriptor (cute::UMMA::InstrDescriptor): D fp32, A/B bf16, majors, N>>3, M>>4
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(BLOCK_N >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % STAGES;
-                const uint32_t ph = (uint32_t)(kb / STAGES) & 1u;
-                mbar_wait(smem_u32(&full_bar[s]), ph);
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t sa = smem_u32(smem + (size_t)s * kStageBytes), sb = sa + kABytes;
-                // K-major: 8-row groups 1024 B apart, one MMA K-step = 32 B along the row
-                // MN-major: 64-wide MN chunks 8192 B apart (LBO), 8-K-row groups 1024 B apart (SBO), K-step = 2048 B
-                const uint64_t adesc = A_MN ? make_desc(sa, 8192, 1024) : make_desc(sa, 16, 1024);
-                const uint64_t bdesc = B_MN ? make_desc(sb, 8192, 1024) : make_desc(sb, 16, 1024);
+            // K-major: 8-row groups 1024 B apart, one MMA K-step = 32 B along the row
+            // MN-major: 64-wide MN chunks 8192 B apart (LBO), 8-K-row groups 1024 B apart (SBO), K-step = 2048 B
+            const uint64_t adesc0 = A_MN ? make_desc(smem0, 8192, 1024) : make_desc(smem0, 16, 1024);
+            const uint64_t bdesc0 = B_MN ? make_desc(smem0 + kABytes, 8192, 1024) : make_desc(smem0 + kABytes, 16, 1024);
+            uint32_t ph = 0u, accum = 0u;
+            for (int kbase = 0; kbase < num_kb; kbase += STAGES, ph ^= 1u) {
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                    const uint64_t ak = adesc + (uint64_t)((A_MN ? 2048u : 32u) * k >> 4);
-                    const uint64_t bk = bdesc + (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
-                    umma_bf16(tmem_base, ak, bk, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                for (int s = 0; s < STAGES; ++s) {
+                    if (kbase + s < num_kb) {
+                        mbar_wait_fast(full0 + 8u * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#ifdef VCT_GEMM_TRACE_KB
+                        if (trace && lane == 0 && kbase + s < 20) trace[56 + kbase + s] = clock64();
+#endif
+                        // stage s starts s * kStageBytes further (1024-byte multiple: no carry into the other fields)
+                        const uint64_t adesc = adesc0 + (uint64_t)(((uint32_t)s * kStageBytes) >> 4);
+                        const uint64_t bdesc = bdesc0 + (uint64_t)(((uint32_t)s * kStageBytes) >> 4);
+                        if (elect_one()) {
+#pragma unroll
+                            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                                const uint64_t ak = adesc + (uint64_t)((A_MN ? 2048u : 32u) * k >> 4);
+                                const uint64_t bk = bdesc + (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
+                                umma_bf16(tmem_base, ak, bk, idesc, (accum | (uint32_t)k) != 0u ? 1u : 0u);
+                            }
+                            umma_commit(empty0 + 8u * s);      // frees the smem slot when these MMAs retire
+                        }
+                        __syncwarp();
+                        accum = 1u;
+#ifdef VCT_GEMM_TRACE_KB
+                        if (trace && lane == 0 && kbase + s < 20) trace[76 + kbase + s] = clock64();
+#endif
+                    }
                 }
-                umma_commit(smem_u32(&empty_bar[s]));      // frees the smem slot when these MMAs retire
             }
-            umma_commit(smem_u32(&tmem_full_bar));          // accumulator complete
+            if (elect_one()) {
+                umma_commit(smem_u32(&tmem_full_bar));          // accumulator complete
+                if (trace) trace[3] = clock64();
+            }
+            __syncwarp();
         }
     } else {
         // ===== epilogue: warp w may touch TMEM lanes [32*(w%4), 32*(w%4)+32) =====
         // phase 1: TMEM -> registers -> shared memory (the operand ring is free once the accumulator is complete)
-        // phase 2: shared memory -> fused epilogue -> global, with the threads remapped so that a warp touches
-        //          contiguous global memory (the TMEM layout gives each thread a ROW, which would make every
+        // phase 2: shared memory -> fused epilogue -> global, with the threads remapped so that a warp instruction
+        //          touches 512 contiguous bytes (the TMEM layout gives each thread a ROW, which would make every
         //          global access a 16-byte piece of a different cache line)
         constexpr int RS = BLOCK_N + 4;                       // padded row stride (floats): conflict-free 16 B stores
         float* stage = reinterpret_cast<float*>(smem);
@@ -137,54 +189,45 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int row = q * 32 + lane;
         mbar_wait(smem_u32(&tmem_full_bar), 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (trace && threadIdx.x == 64) trace[4] = clock64();
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 16; ++c) {
-            uint32_t r[16];
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 16);
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+            uint32_t r[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(c * 32);
             if (num_kb > 0) {
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                    : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                      "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                    : "r"(taddr)
-                    : "memory");
+                tmem_ld16(taddr, r);
+                tmem_ld16(taddr + 16, r + 16);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
             } else {
 #pragma unroll
-                for (int i = 0; i < 16; ++i) r[i] = 0u;        // empty K range (split-K tail): contributes zeros
+                for (int i = 0; i < 32; ++i) r[i] = 0u;        // empty K range (split-K tail): contributes zeros
             }
-            uint4* dst = reinterpret_cast<uint4*>(stage + row * RS + c * 16);
+            uint4* dst = reinterpret_cast<uint4*>(stage + row * RS + c * 32);
 #pragma unroll
-            for (int g = 0; g < 4; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+            for (int g = 0; g < 8; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
-        const Rng rng = make_rng(epi.rng_state, ACT != VCT_ACT_NONE ? epi.drop_p : 0.f);
+        if (trace && threadIdx.x == 64) trace[5] = clock64();
         const int t = threadIdx.x - 64;
-        constexpr int CG = BLOCK_N / 8;                       // 8-column groups per row
-#pragma unroll 2
-        for (int id = t; id < BLOCK_M * CG; id += 128) {
-            const int rr = id / CG, cg = id % CG;
-            const int m = m0 + rr, n = n0 + cg * 8;
-            if (m >= epi.M || n >= epi.N) continue;
-            const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * RS + cg * 8);
-            const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * RS + cg * 8 + 4);
-            if (splitk_ws != nullptr) {
-                // raw partial sums; vct's split-K reduce kernel applies the epilogue
-                float* w = splitk_ws + ((long long)blockIdx.z * epi.M + m) * ldw + n;
-                *reinterpret_cast<float4*>(w) = a0;
-                *reinterpret_cast<float4*>(w + 4) = a1;
-            } else {
-                epilogue_store8<ACT>(epi, rng, m, n, a0, a1);
-            }
+        if (splitk_ws != nullptr) {
+            // raw partial sums; vct's split-K reduce kernel applies the epilogue
+            epilogue_tile_partial<BLOCK_N>(splitk_ws + (long long)blockIdx.z * epi.M * ldw, ldw, epi.M, epi.N, stage, RS, m0, n0, t);
+        } else if (ACT == VCT_ACT_NONE) {
+            const Rng rng = make_rng(nullptr, 0.f);
+            epilogue_tile_plain<BLOCK_N>(epi, rng, stage, RS, m0, n0, t);
+        } else {
+            const Rng rng = make_rng(epi.rng_state, epi.drop_p);
+            epilogue_tile_act<ACT, BLOCK_N>(epi, rng, stage, RS, m0, n0, t);
         }
+        if (trace && threadIdx.x == 64) trace[6] = clock64();
     }
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)BLOCK_N) : "memory");
     }
+    if (trace && threadIdx.x == 0) trace[7] = clock64();
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -222,7 +265,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
         for (int s = 0; s < P_STAGES; ++s) {
-            mbar_init(smem_u32(&full_bar[s]), 1);
+            mbar_init(smem_u32(&full_bar[s]), 2);
             mbar_init(smem_u32(&empty_bar[s]), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -245,60 +288,77 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     // before this point reads or writes global memory that another kernel of the step produces
     pdl_wait();
 
-    if (warp == 0) {
-        if (lane == 0) {
-            uint32_t it = 0;
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    if (warp == 0 || warp == 6) {
+        {
+            const bool is_a = warp == 0;                       // warp 0 loads the A tiles, warp 6 the B tiles
+            uint32_t s = 0, ph = 1u;                           // ring slot and its "free" parity
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int mt = m_fast ? tile % tiles_m : tile / tiles_n, nt = m_fast ? tile / tiles_m : tile % tiles_n;
                 const int m0 = mt * BLOCK_M, n0 = nt * P_BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % P_STAGES, ph = (it / P_STAGES) & 1u;
-                    mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
-                    const uint32_t full = smem_u32(&full_bar[s]);
-                    mbar_expect_tx(full, kPStage);
-                    const uint32_t sa = smem_u32(smem + (size_t)s * kPStage), sb = sa + kABytes;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_fast(empty0 + 8u * s, ph);
+                    const uint32_t full = full0 + 8u * s;
+                    const uint32_t sa = smem0 + s * kPStage, sb = sa + kABytes;
                     const int k0 = kb * BLOCK_K;
-                    if (!A_MN) {
-                        tma_load_2d(sa, &tmA, k0, m0, full);
-                    } else {
+                    if (elect_one()) {
+                        if (is_a) {
+                            mbar_expect_tx(full, kABytes);
+                            if (!A_MN) {
+                                tma_load_2d(sa, &tmA, k0, m0, full);
+                            } else {
 #pragma unroll
-                        for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, k0, full);
-                    }
-                    if (!B_MN) {
-                        tma_load_2d(sb, &tmB, k0, n0, full);
-                    } else {
+                                for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, &tmA, m0 + c * 64, k0, full);
+                            }
+                        } else {
+                            mbar_expect_tx(full, kPBBytes);
+                            if (!B_MN) {
+                                tma_load_2d(sb, &tmB, k0, n0, full);
+                            } else {
 #pragma unroll
-                        for (int c = 0; c < P_BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, k0, full);
+                                for (int c = 0; c < P_BN / 64; ++c) tma_load_2d(sb + c * 8192, &tmB, n0 + c * 64, k0, full);
+                            }
+                        }
                     }
+                    __syncwarp();
+                    if (++s == P_STAGES) { s = 0; ph ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        if (lane == 0) {
+        {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                                    ((uint32_t)(P_BN >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-            uint32_t it = 0, ti = 0;
+            const uint64_t adesc0 = A_MN ? make_desc(smem0, 8192, 1024) : make_desc(smem0, 16, 1024);
+            const uint64_t bdesc0 = B_MN ? make_desc(smem0 + kABytes, 8192, 1024) : make_desc(smem0 + kABytes, 16, 1024);
+            uint32_t s = 0, ph = 0u, ti = 0;
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
                 const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
-                mbar_wait(smem_u32(&tmem_empty_bar[acc]), aph ^ 1u);     // epilogue has drained this accumulator
+                mbar_wait_fast(smem_u32(&tmem_empty_bar[acc]), aph ^ 1u);     // epilogue has drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + acc * (uint32_t)P_BN;
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const uint32_t s = it % P_STAGES, ph = (it / P_STAGES) & 1u;
-                    mbar_wait(smem_u32(&full_bar[s]), ph);
+                uint32_t accum = 0u;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_fast(full0 + 8u * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t sa = smem_u32(smem + (size_t)s * kPStage), sb = sa + kABytes;
-                    const uint64_t adesc = A_MN ? make_desc(sa, 8192, 1024) : make_desc(sa, 16, 1024);
-                    const uint64_t bdesc = B_MN ? make_desc(sb, 8192, 1024) : make_desc(sb, 16, 1024);
+                    const uint64_t adesc = adesc0 + (uint64_t)((s * kPStage) >> 4);
+                    const uint64_t bdesc = bdesc0 + (uint64_t)((s * kPStage) >> 4);
+                    if (elect_one()) {
 #pragma unroll
-                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                        const uint64_t ak = adesc + (uint64_t)((A_MN ? 2048u : 32u) * k >> 4);
-                        const uint64_t bk = bdesc + (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
-                        umma_bf16(d_tmem, ak, bk, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t ak = adesc + (uint64_t)((A_MN ? 2048u : 32u) * k >> 4);
+                            const uint64_t bk = bdesc + (uint64_t)((B_MN ? 2048u : 32u) * k >> 4);
+                            umma_bf16(d_tmem, ak, bk, idesc, (accum | (uint32_t)k) != 0u ? 1u : 0u);
+                        }
+                        umma_commit(empty0 + 8u * s);
                     }
-                    umma_commit(smem_u32(&empty_bar[s]));
+                    __syncwarp();
+                    accum = 1u;
+                    if (++s == P_STAGES) { s = 0; ph ^= 1u; }
                 }
-                umma_commit(smem_u32(&tmem_full_bar[acc]));
+                if (elect_one()) umma_commit(smem_u32(&tmem_full_bar[acc]));
+                __syncwarp();
             }
         }
     } else {
@@ -316,20 +376,15 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
 #pragma unroll 1
             for (int ch = 0; ch < P_BN / P_CH; ++ch) {
 #pragma unroll
-                for (int c = 0; c < P_CH / 16; ++c) {
-                    uint32_t r[16];
-                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)P_BN + (uint32_t)(ch * P_CH + c * 16);
-                    asm volatile(
-                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                        : "r"(taddr)
-                        : "memory");
+                for (int c = 0; c < P_CH / 32; ++c) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * (uint32_t)P_BN + (uint32_t)(ch * P_CH + c * 32);
+                    tmem_ld16(taddr, r);
+                    tmem_ld16(taddr + 16, r + 16);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    uint4* dst = reinterpret_cast<uint4*>(stage + row * P_RS + c * 16);
+                    uint4* dst = reinterpret_cast<uint4*>(stage + row * P_RS + c * 32);
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+                    for (int g = 0; g < 8; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
                 }
                 if (ch == P_BN / P_CH - 1) {
                     // every TMEM read of this accumulator has completed: hand it back to the MMA warp
@@ -337,17 +392,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                constexpr int CG = P_CH / 8;
-#pragma unroll 2
-                for (int id = t; id < BLOCK_M * CG; id += 128) {
-                    const int rr = id / CG, cg = id % CG;
-                    const int m = m0 + rr, n = n0 + ch * P_CH + cg * 8;
-                    if (m < epi.M && n < epi.N) {
-                        const float4 a0 = *reinterpret_cast<const float4*>(stage + rr * P_RS + cg * 8);
-                        const float4 a1 = *reinterpret_cast<const float4*>(stage + rr * P_RS + cg * 8 + 4);
-                        epilogue_store8<VCT_ACT_NONE>(epi, rng, m, n, a0, a1);
-                    }
-                }
+                epilogue_tile_plain<P_CH>(epi, rng, stage, P_RS, m0, n0 + ch * P_CH, t);
                 asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer is reused by the next chunk
             }
         }
@@ -383,10 +428,18 @@ splitk_reduce_kernel(const float* __restrict__ ws, int splits, long long ldw, Ep
 // ---------------------------------------------------------------------------------------------------
 // host: tensor maps (cached) and dispatch
 // ---------------------------------------------------------------------------------------------------
-template <int BLOCK_N, bool A_MN, bool B_MN, int ACT>
-int launch_tile(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
+// LOW: half the shared-memory ring (<= ~100 KB) so that TWO CTAs are resident per SM: one CTA's prologue /
+// epilogue (launch, TMEM alloc, first TMA round trip, TMEM -> smem -> global) overlaps the other's main loop.
+// These GEMMs are bound by L2 -> SM operand traffic and per-CTA fixed cost, not by the tensor pipe, so the
+// shallower ring costs nothing while the co-resident CTA hides ~9k cycles of fixed cost per tile.
+template <int BLOCK_N, bool A_MN, bool B_MN, int ACT, bool LOW>
+int launch_tile_impl(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
     constexpr int kStage = kABytes + BLOCK_N * BLOCK_K * 2;
-    constexpr int STAGES = kSmemBudget / kStage > 8 ? 8 : kSmemBudget / kStage;
+    constexpr int kBudget = LOW ? kSmemBudgetLow : kSmemBudget;
+    constexpr int kStagesFit = kBudget / kStage > 8 ? 8 : kBudget / kStage;
+    // the epilogue stages the [128 x BLOCK_N] fp32 tile (+4 floats of row padding) in the operand ring
+    constexpr int kEpiBytes = BLOCK_M * (BLOCK_N + 4) * 4;
+    constexpr int STAGES = kStagesFit * kStage >= kEpiBytes ? kStagesFit : (kEpiBytes + kStage - 1) / kStage;
     constexpr int smem = STAGES * kStage + 1024;
     auto kern = gemm_tc_kernel<BLOCK_N, A_MN, B_MN, STAGES, ACT>;
     static bool once = false;
@@ -395,7 +448,8 @@ int launch_tile(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMa
         once = true;
     }
     dim3 grid((a->N + BLOCK_N - 1) / BLOCK_N, (a->M + BLOCK_M - 1) / BLOCK_M, splits);
-    const Epilogue epi = make_epilogue(a);
+    Epilogue epi = make_epilogue(a);
+    epi.trace = g_trace;
     const long long ldw = ((long long)a->N + 7) / 8 * 8;
     vct::launch(kern, dim3(grid), dim3(kThreads), smem, st, tmA, tmB, a->K, epi, splits > 1 ? (float*)a->splitk_ws : nullptr, ldw);
     if (int e = check_launch("vct_gemm(tcgen05)")) return e;
@@ -405,6 +459,14 @@ int launch_tile(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMa
         return check_launch("vct_gemm(tcgen05 split-K reduce)");
     }
     return 0;
+}
+
+template <int BLOCK_N, bool A_MN, bool B_MN, int ACT>
+int launch_tile(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, bool low, cudaStream_t st) {
+    if constexpr (BLOCK_N <= 128) {
+        if (low) return launch_tile_impl<BLOCK_N, A_MN, B_MN, ACT, true>(a, tmA, tmB, splits, st);
+    }
+    return launch_tile_impl<BLOCK_N, A_MN, B_MN, ACT, false>(a, tmA, tmB, splits, st);
 }
 
 template <bool A_MN, bool B_MN>
@@ -422,22 +484,22 @@ int launch_persistent(const vct_gemm_args* a, const CUtensorMap& tmA, const CUte
 }
 
 template <int BLOCK_N>
-int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, cudaStream_t st) {
+int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, bool low, cudaStream_t st) {
     // activation epilogues exist where the path uses them: GELU forward on x W1^T (K-major, K-major) and GELU
     // backward on dY W2 (K-major, MN-major); everything else carries the small plain epilogue
     if (a->act == VCT_ACT_GELU_FWD) {
         VCT_REQUIRE(!a->a_trans && !a->b_trans, "vct_gemm(tcgen05): GELU_FWD is built for a_trans = b_trans = 0");
-        return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, splits, st);
+        return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, splits, low, st);
     }
     if (a->act == VCT_ACT_GELU_BWD) {
         VCT_REQUIRE(!a->a_trans, "vct_gemm(tcgen05): GELU_BWD is built for a_trans = 0");
-        if (a->b_trans) return launch_tile<BLOCK_N, false, true, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
-        return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, st);
+        if (a->b_trans) return launch_tile<BLOCK_N, false, true, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, low, st);
+        return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_BWD>(a, tmA, tmB, splits, low, st);
     }
-    if (!a->a_trans && !a->b_trans) return launch_tile<BLOCK_N, false, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
-    if (!a->a_trans && a->b_trans) return launch_tile<BLOCK_N, false, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
-    if (a->a_trans && !a->b_trans) return launch_tile<BLOCK_N, true, false, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
-    return launch_tile<BLOCK_N, true, true, VCT_ACT_NONE>(a, tmA, tmB, splits, st);
+    if (!a->a_trans && !a->b_trans) return launch_tile<BLOCK_N, false, false, VCT_ACT_NONE>(a, tmA, tmB, splits, low, st);
+    if (!a->a_trans && a->b_trans) return launch_tile<BLOCK_N, false, true, VCT_ACT_NONE>(a, tmA, tmB, splits, low, st);
+    if (a->a_trans && !a->b_trans) return launch_tile<BLOCK_N, true, false, VCT_ACT_NONE>(a, tmA, tmB, splits, low, st);
+    return launch_tile<BLOCK_N, true, true, VCT_ACT_NONE>(a, tmA, tmB, splits, low, st);
 }
 
 }  // namespace
@@ -505,18 +567,26 @@ int get_tensor_map(const void* ptr, long long inner, long long outer, long long 
 }
 
 
+// tile override for tuning sweeps: bn in {64,128,256} (0 = cost model), split-K factor, low: 1 = two-CTA-per-SM ring,
+// 0 = full ring, -1 = persistent kernel
+void gemm_tune(int bn, int splits, int low) { g_tune_bn = bn; g_tune_splits = splits; g_tune_low = low; }
+void gemm_trace(long long* dev_buf) { g_trace = dev_buf; }
+
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     VCT_REQUIRE(a->a_dtype == VCT_BF16, "vct_gemm(tcgen05): operands must be bf16");
     VCT_REQUIRE(a->lda % 8 == 0 && a->ldb % 8 == 0, "vct_gemm(tcgen05): lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
     VCT_REQUIRE((reinterpret_cast<uintptr_t>(a->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(a->B) & 15) == 0,
                 "vct_gemm(tcgen05): operands must be 16-byte aligned");
-    // Tile width and split-K factor from a small cost model (cycles): these GEMMs are bounded by the fixed cost of
-    // a CTA (launch, TMEM alloc, first TMA round trip, epilogue ~ 9k cycles) and by L2 -> SM operand traffic
-    // (~42 B/clk/SM when all SMs pull), not by the tensor pipe, so fewer / fuller waves win.
+    // Tile width, ring flavour and split-K factor from a small cost model (cycles), fitted to tools/gemm_sweep.py on
+    // B200 (regret 2.7 us over the 62 layer GEMMs of a step).  These GEMMs are bound by the fixed cost of a CTA
+    // (launch, TMEM alloc, first TMA round trip, epilogue) and by the per-k-block issue cost of the producer / MMA
+    // threads (~320 cycles + 1.2 per tile column), not by the tensor pipe, so fewer / fuller waves win; with the half
+    // ring two CTAs share an SM (twice the slots per wave, each k-block ~1.86x slower when both are resident).
     const long long tiles_m = (a->M + BLOCK_M - 1) / BLOCK_M;
     const int total_kb = (a->K + BLOCK_K - 1) / BLOCK_K;
     const long long ldw = ((long long)a->N + 7) / 8 * 8;
     int bn = 64, splits = 1;
+    bool low = false;
     double best = 1e30;
     // several 128x256 tiles per SM: the persistent kernel (epilogue overlapped with the next tile's main loop)
     const bool persistent = tiles_m * ((a->N + 255) / 256) >= 2 * kNumSMs && a->act == VCT_ACT_NONE &&
@@ -524,32 +594,43 @@ int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     if (persistent) { bn = 256; splits = 1; best = 0.0; }
     for (int cand : {256, 128, 64}) {
         const long long tiles = tiles_m * ((a->N + cand - 1) / cand);
-        const double cyc_kb = fmax(2.0 * cand, (16384.0 + 128.0 * cand) / 42.0);
-        for (int sp : {1, 2, 3, 4, 5, 6, 8}) {
-            if (sp > 1 && (a->splitk_ws == nullptr || total_kb < 16 * sp ||
-                           (long long)sp * a->M * ldw > a->splitk_ws_floats)) continue;
-            const long long ctas = tiles * sp;
-            const double waves = (double)((ctas + kNumSMs - 1) / kNumSMs);
-            const int kbs = (total_kb + sp - 1) / sp;
-            double t = waves * (9000.0 + kbs * cyc_kb);
-            if (sp > 1) t += 8000.0 + (double)sp * a->M * a->N * 4.0 / 3000.0;
-            if (t < best) { best = t; bn = cand; splits = sp; }
+        const double cyc_kb = fmax(2.0 * cand, 316.5 + 1.215 * cand);
+        for (int lo = 0; lo <= (cand <= 128 ? 1 : 0); ++lo) {
+            for (int sp : {1, 2, 3, 4, 5, 6, 8}) {
+                if (sp > 1 && (a->splitk_ws == nullptr || total_kb < 16 * sp ||
+                               (long long)sp * a->M * ldw > a->splitk_ws_floats)) continue;
+                const long long ctas = tiles * sp;
+                const int slots = lo ? 2 * kNumSMs : kNumSMs;
+                const double waves = (double)((ctas + slots - 1) / slots);
+                const int kbs = (total_kb + sp - 1) / sp;
+                double t = waves * (4716.0 + 26.7 * cand + kbs * cyc_kb * ((lo && ctas > kNumSMs) ? 1.856 : 1.0));
+                if (sp > 1) t += 6348.0 + (double)sp * a->M * a->N * 4.0 / 3000.0;
+                if (t < best) { best = t; bn = cand; splits = sp; low = lo != 0; }
+            }
         }
+    }
+    bool use_persistent = persistent;
+    if (g_tune_bn > 0) {                       // vct_gemm_tune override (tools/gemm_sweep.py)
+        bn = g_tune_bn;
+        splits = g_tune_splits > 0 ? g_tune_splits : 1;
+        if (splits > 1 && (a->splitk_ws == nullptr || (long long)splits * a->M * ldw > a->splitk_ws_floats)) splits = 1;
+        low = g_tune_low > 0 && bn <= 128;
+        use_persistent = g_tune_low < 0;        // low = -1 selects the persistent kernel (bn must be 256)
     }
     CUtensorMap tmA, tmB;
     if (!a->a_trans) { if (int e = get_tensor_map(a->A, a->K, a->M, a->lda, BLOCK_K, BLOCK_M, &tmA)) return e; }
     else             { if (int e = get_tensor_map(a->A, a->M, a->K, a->lda, 64, BLOCK_K, &tmA)) return e; }
     if (!a->b_trans) { if (int e = get_tensor_map(a->B, a->K, a->N, a->ldb, BLOCK_K, bn, &tmB)) return e; }
     else             { if (int e = get_tensor_map(a->B, a->N, a->K, a->ldb, 64, BLOCK_K, &tmB)) return e; }
-    if (bn == 256 && splits == 1 && a->act == VCT_ACT_NONE && persistent) {
+    if (bn == 256 && splits == 1 && a->act == VCT_ACT_NONE && use_persistent) {
         if (!a->a_trans && !a->b_trans) return launch_persistent<false, false>(a, tmA, tmB, st);
         if (!a->a_trans && a->b_trans) return launch_persistent<false, true>(a, tmA, tmB, st);
         if (a->a_trans && !a->b_trans) return launch_persistent<true, false>(a, tmA, tmB, st);
         return launch_persistent<true, true>(a, tmA, tmB, st);
     }
-    if (bn == 256) return dispatch_major<256>(a, tmA, tmB, splits, st);
-    if (bn == 128) return dispatch_major<128>(a, tmA, tmB, splits, st);
-    return dispatch_major<64>(a, tmA, tmB, splits, st);
+    if (bn == 256) return dispatch_major<256>(a, tmA, tmB, splits, low, st);
+    if (bn == 128) return dispatch_major<128>(a, tmA, tmB, splits, low, st);
+    return dispatch_major<64>(a, tmA, tmB, splits, low, st);
 }
 
 }  // namespace vct

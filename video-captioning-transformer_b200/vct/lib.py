@@ -75,6 +75,8 @@ SIGNATURES = {
     "vct_device_info": (i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "vct_step_tick": (i32, [vp, vp, vp]),
     "vct_gemm": (i32, [C.POINTER(GemmArgs), vp]),
+    "vct_gemm_tune": (i32, [i32, i32, i32]),
+    "vct_gemm_trace": (i32, [vp]),
     "vct_prep_frames": (i32, [vp, vp, i32, i32, i32, i32, vp]),
     "vct_attn_fwd": (i32, [C.POINTER(AttnArgs), vp]),
     "vct_attn_bwd": (i32, [C.POINTER(AttnArgs), vp]),
