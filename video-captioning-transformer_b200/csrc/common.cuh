@@ -223,4 +223,31 @@ __device__ __forceinline__ float dgelu_f(float x) {
     return cdf + x * pdf;
 }
 
+// Fast variants for the bf16 tensor-core epilogues (outputs are rounded to bf16, 2^-9 relative): the normal CDF from
+// Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7) in its complementary form, so that the left tail has no cancellation;
+// the exponential exp(-x^2/2) is shared between the CDF and the density.  ~15 instructions against ~45 for erff,
+// which matters because only the four epilogue warps of a CTA run this code.
+__device__ __forceinline__ void normal_cdf_pdf_fast(float x, float& cdf, float& pdf) {
+    const float ax = fabsf(x) * 0.70710678118654752f;
+    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float e = __expf(-ax * ax);                       // exp(-x^2 / 2)
+    const float half_erfc = 0.5f * p * t * e;               // 0.5 * erfc(|x| / sqrt 2)
+    cdf = x < 0.f ? half_erfc : 1.f - half_erfc;
+    pdf = 0.39894228040143268f * e;
+}
+__device__ __forceinline__ float gelu_fast(float x) {
+    float cdf, pdf;
+    normal_cdf_pdf_fast(x, cdf, pdf);
+    return x * cdf;
+}
+__device__ __forceinline__ float dgelu_fast(float x) {
+    float cdf, pdf;
+    normal_cdf_pdf_fast(x, cdf, pdf);
+    return fmaf(x, pdf, cdf);
+}
+
 }  // namespace vct

@@ -171,90 +171,127 @@ __device__ __forceinline__ void epilogue_store8(const Epilogue& e, const Rng& rn
 
 // ---------------------------------------------------------------------------------------------------------
 // Tile epilogues of the tcgen05 kernels.  128 threads (t = 0..127) store a [rows x BN] fp32 accumulator tile
-// that has been staged in shared memory (row stride RS floats).  Everything that does not depend on the row
-// (column offset, bias, output pointers, feature flags) is hoisted out of the row loop, so that the loop body is
-// one shared load, the adds, and one (two) fully coalesced global store(s): a warp instruction covers 512
-// contiguous bytes of a row.  The generic per-element functions above remain the path for ragged / unaligned tiles.
+// that has been staged in shared memory (row stride RS floats, `stage` = shared-space byte address).  Everything
+// that does not depend on the row (column offset, bias, output pointers, feature flags) is hoisted out of the row
+// loop; rows are processed four at a time -- four explicit ld.shared first, then the adds and the stores -- because
+// the compiler may not move a load above a store that might alias it, which would serialise every iteration on the
+// shared-memory latency.  A warp instruction covers 512 contiguous bytes of an output row.  The generic per-element
+// functions above remain the path for ragged / unaligned tiles.
 // ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+struct PlainCtx {           // row-invariant state of epilogue_tile_plain
+    float4 b;
+    const float* table; int period, N, n;
+    bool c_bf16, c2_bf16;
+    char* c; char* c2; const float* ad;
+    long long c_step, c2_step, ad_step;
+};
+
+__device__ __forceinline__ void plain_row(PlainCtx& x, float4 v, float4 a4, int m) {
+    v.x += x.b.x; v.y += x.b.y; v.z += x.b.z; v.w += x.b.w;
+    if (x.table) {
+        const float4 tb = ld4(x.table + (long long)(m % x.period) * x.N + x.n);
+        v.x += tb.x; v.y += tb.y; v.z += tb.z; v.w += tb.w;
+    }
+    v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
+    if (x.c_bf16) st4(reinterpret_cast<__nv_bfloat16*>(x.c), v);
+    else st4(reinterpret_cast<float*>(x.c), v);
+    x.c += x.c_step;
+    if (x.c2) {
+        if (x.c2_bf16) st4(reinterpret_cast<__nv_bfloat16*>(x.c2), v);
+        else st4(reinterpret_cast<float*>(x.c2), v);
+        x.c2 += x.c2_step;
+    }
+}
+
 template <int BN>
-__device__ __forceinline__ void epilogue_tile_plain(const Epilogue& e, const Rng& rng, const float* __restrict__ stage, int RS,
-                                                    int m0, int n0, int t) {
+__device__ __forceinline__ void epilogue_tile_plain(const Epilogue& e, const Rng& rng, uint32_t stage, int RS, int m0, int n0, int t) {
     constexpr int CG4 = BN / 4, RSTEP = 128 / CG4;          // 4-column groups per row; rows covered per pass
     const int c4 = t % CG4, n = n0 + c4 * 4;
     if (n >= e.N) return;
     const int rows = min(128, e.M - m0);
     int rr = t / CG4;
-    const float* src = stage + rr * RS + c4 * 4;
+    uint32_t src = stage + (uint32_t)(rr * RS + c4 * 4) * 4u;
+    const uint32_t src_step = (uint32_t)(RSTEP * RS) * 4u;
     if (!e.vec_ok || n + 4 > e.N) {
-        for (; rr < rows; rr += RSTEP, src += RSTEP * RS)
-            epilogue_scalar<VCT_ACT_NONE>(e, rng, m0 + rr, n, *reinterpret_cast<const float4*>(src));
+        for (; rr < rows; rr += RSTEP, src += src_step) epilogue_scalar<VCT_ACT_NONE>(e, rng, m0 + rr, n, lds128(src));
         return;
     }
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (e.bias) b = ld4(e.bias + n);
-    const float* table = e.row_table;
-    const int period = e.row_period, N = e.N;
-    const bool c_bf16 = e.c_dtype == VCT_BF16, c2_bf16 = e.c2_dtype == VCT_BF16;
-    const long long ldc = e.ldc, ldc2 = e.ldc2, lda = e.ld_addend;
-    long long m = m0 + rr;
-    char* c = reinterpret_cast<char*>(e.C) + (m * ldc + n) * (c_bf16 ? 2 : 4);
-    char* c2 = e.C2 ? reinterpret_cast<char*>(e.C2) + (m * ldc2 + n) * (c2_bf16 ? 2 : 4) : nullptr;
-    const float* ad = e.addend ? e.addend + m * lda + n : nullptr;
-    const long long c_step = (long long)RSTEP * ldc * (c_bf16 ? 2 : 4), c2_step = (long long)RSTEP * ldc2 * (c2_bf16 ? 2 : 4);
-#pragma unroll 4
-    for (; rr < rows; rr += RSTEP, src += RSTEP * RS, m += RSTEP) {
-        float4 v = *reinterpret_cast<const float4*>(src);
-        v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
-        if (table) {
-            const float4 tb = ld4(table + (long long)((int)m % period) * N + n);
-            v.x += tb.x; v.y += tb.y; v.z += tb.z; v.w += tb.w;
-        }
-        if (ad) {
-            const float4 a4 = ld4(ad);
-            v.x += a4.x; v.y += a4.y; v.z += a4.z; v.w += a4.w;
-            ad += (long long)RSTEP * lda;
-        }
-        if (c_bf16) st4(reinterpret_cast<__nv_bfloat16*>(c), v);
-        else st4(reinterpret_cast<float*>(c), v);
-        c += c_step;
-        if (c2) {
-            if (c2_bf16) st4(reinterpret_cast<__nv_bfloat16*>(c2), v);
-            else st4(reinterpret_cast<float*>(c2), v);
-            c2 += c2_step;
-        }
+    PlainCtx x;
+    x.b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (e.bias) x.b = ld4(e.bias + n);
+    x.table = e.row_table; x.period = e.row_period; x.N = e.N; x.n = n;
+    x.c_bf16 = e.c_dtype == VCT_BF16; x.c2_bf16 = e.c2_dtype == VCT_BF16;
+    const long long m = m0 + rr;
+    x.c = reinterpret_cast<char*>(e.C) + (m * e.ldc + n) * (x.c_bf16 ? 2 : 4);
+    x.c2 = e.C2 ? reinterpret_cast<char*>(e.C2) + (m * e.ldc2 + n) * (x.c2_bf16 ? 2 : 4) : nullptr;
+    x.ad = e.addend ? e.addend + m * e.ld_addend + n : nullptr;
+    x.c_step = (long long)RSTEP * e.ldc * (x.c_bf16 ? 2 : 4);
+    x.c2_step = (long long)RSTEP * e.ldc2 * (x.c2_bf16 ? 2 : 4);
+    x.ad_step = (long long)RSTEP * e.ld_addend;
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (; rr + 3 * RSTEP < rows; rr += 4 * RSTEP, src += 4 * src_step) {
+        float4 v[4], a4[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = lds128(src + u * src_step);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) a4[u] = x.ad ? ld4(x.ad + u * x.ad_step) : zero;
+        if (x.ad) x.ad += 4 * x.ad_step;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) plain_row(x, v[u], a4[u], m0 + rr + u * RSTEP);
+    }
+    for (; rr < rows; rr += RSTEP, src += src_step) {
+        const float4 v = lds128(src);
+        const float4 a4 = x.ad ? ld4(x.ad) : zero;
+        if (x.ad) x.ad += x.ad_step;
+        plain_row(x, v, a4, m0 + rr);
     }
 }
 
-// raw fp32 partial sums of a split-K slice: ws[(z * M + m) * ldw + n]
+// raw fp32 partial sums of a split-K slice: ws[m * ldw + n] (ws already offset to the slice)
 template <int BN>
-__device__ __forceinline__ void epilogue_tile_partial(float* __restrict__ ws, long long ldw, int M, int N, const float* __restrict__ stage,
-                                                      int RS, int m0, int n0, int t) {
+__device__ __forceinline__ void epilogue_tile_partial(float* __restrict__ ws, long long ldw, int M, int N, uint32_t stage, int RS,
+                                                      int m0, int n0, int t) {
     constexpr int CG4 = BN / 4, RSTEP = 128 / CG4;
     const int c4 = t % CG4, n = n0 + c4 * 4;
     if (n >= N) return;                                     // ldw is a multiple of 8 >= N: whole float4 groups are in bounds
     const int rows = min(128, M - m0);
     int rr = t / CG4;
-    const float* src = stage + rr * RS + c4 * 4;
+    uint32_t src = stage + (uint32_t)(rr * RS + c4 * 4) * 4u;
+    const uint32_t src_step = (uint32_t)(RSTEP * RS) * 4u;
     float* dst = ws + (long long)(m0 + rr) * ldw + n;
-#pragma unroll 4
-    for (; rr < rows; rr += RSTEP, src += RSTEP * RS, dst += (long long)RSTEP * ldw)
-        *reinterpret_cast<float4*>(dst) = *reinterpret_cast<const float4*>(src);
+    const long long dst_step = (long long)RSTEP * ldw;
+    for (; rr + 3 * RSTEP < rows; rr += 4 * RSTEP, src += 4 * src_step, dst += 4 * dst_step) {
+        float4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = lds128(src + u * src_step);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) *reinterpret_cast<float4*>(dst + u * dst_step) = v[u];
+    }
+    for (; rr < rows; rr += RSTEP, src += src_step, dst += dst_step) *reinterpret_cast<float4*>(dst) = lds128(src);
 }
 
 // activation epilogues (GELU forward / backward): 8-column groups per thread so that one Philox draw covers the
 // group's 8 dropout decisions and bf16 outputs are stored 16 bytes at a time
 template <int ACT, int BN>
-__device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& rng, const float* __restrict__ stage, int RS,
-                                                  int m0, int n0, int t) {
+__device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& rng, uint32_t stage, int RS, int m0, int n0, int t) {
     constexpr int CG = BN / 8, RSTEP = 128 / CG;
     const int cg = t % CG, n = n0 + cg * 8;
     if (n >= e.N) return;
     const int rows = min(128, e.M - m0);
     int rr = t / CG;
-    const float* src = stage + rr * RS + cg * 8;
+    uint32_t src = stage + (uint32_t)(rr * RS + cg * 8) * 4u;
+    const uint32_t src_step = (uint32_t)(RSTEP * RS) * 4u;
     if (!e.vec_ok || n + 8 > e.N) {
-        for (; rr < rows; rr += RSTEP, src += RSTEP * RS)
-            epilogue_store8<ACT>(e, rng, m0 + rr, n, *reinterpret_cast<const float4*>(src), *reinterpret_cast<const float4*>(src + 4));
+        for (; rr < rows; rr += RSTEP, src += src_step) epilogue_store8<ACT>(e, rng, m0 + rr, n, lds128(src), lds128(src + 16));
         return;
     }
     float b[8];
@@ -265,45 +302,62 @@ __device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& 
     const long long ldc = e.ldc, ldc2 = e.ldc2, ldx = e.ld_aux, lda = e.ld_addend;
     const unsigned long long N = (unsigned long long)e.N;
     const unsigned int site = e.site;
-#pragma unroll 2
-    for (; rr < rows; rr += RSTEP, src += RSTEP * RS) {
-        const long long m = m0 + rr;
-        const float4 a0 = *reinterpret_cast<const float4*>(src), a1 = *reinterpret_cast<const float4*>(src + 4);
-        float v[8] = {a0.x + b[0], a0.y + b[1], a0.z + b[2], a0.w + b[3], a1.x + b[4], a1.y + b[5], a1.z + b[6], a1.w + b[7]};
-        float sc[8];
-        dropout_scale8(rng, site, ((unsigned long long)m * N + (unsigned long long)n) >> 3, sc);
-        if (ACT == VCT_ACT_GELU_FWD) {
-            const long long o = m * ldc + n;
-            if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
-            else st8(reinterpret_cast<float*>(e.C) + o, v);
-            if (e.C2) {
-                float h[8];
+    for (; rr < rows; rr += 2 * RSTEP, src += 2 * src_step) {
+        // two rows per pass: all shared / global loads first, then the math and the stores
+        const bool two = rr + RSTEP < rows;
+        float4 a[2][2];
+        float z[2][8], ad[2][8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) h[q] = gelu_f(v[q]) * sc[q];
-                const long long o2 = m * ldc2 + n;
-                if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, h);
-                else st8(reinterpret_cast<float*>(e.C2) + o2, h);
+        for (int u = 0; u < 2; ++u) {
+            a[u][0] = lds128(src + u * src_step);
+            a[u][1] = lds128(src + u * src_step + 16);
+        }
+        if (ACT == VCT_ACT_GELU_BWD) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 0 || two) {
+                    const long long mm = m0 + rr + u * RSTEP;
+                    if (aux_bf16) ld8(reinterpret_cast<const __nv_bfloat16*>(e.aux) + mm * ldx + n, z[u]);
+                    else ld8(reinterpret_cast<const float*>(e.aux) + mm * ldx + n, z[u]);
+                    if (e.addend) ld8(e.addend + mm * lda + n, ad[u]);
+                }
             }
-        } else {
-            float z[8];
-            const long long ao = m * ldx + n;
-            if (aux_bf16) ld8(reinterpret_cast<const __nv_bfloat16*>(e.aux) + ao, z);
-            else ld8(reinterpret_cast<const float*>(e.aux) + ao, z);
+        }
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v[q] *= dgelu_f(z[q]) * sc[q];
-            if (e.addend) {
-                float ad[8];
-                ld8(e.addend + m * lda + n, ad);
+        for (int u = 0; u < 2; ++u) {
+            if (u == 1 && !two) break;
+            const long long m = m0 + rr + u * RSTEP;
+            float v[8] = {a[u][0].x + b[0], a[u][0].y + b[1], a[u][0].z + b[2], a[u][0].w + b[3],
+                          a[u][1].x + b[4], a[u][1].y + b[5], a[u][1].z + b[6], a[u][1].w + b[7]};
+            float sc[8];
+            dropout_scale8(rng, site, ((unsigned long long)m * N + (unsigned long long)n) >> 3, sc);
+            if (ACT == VCT_ACT_GELU_FWD) {
+                const long long o = m * ldc + n;
+                if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
+                else st8(reinterpret_cast<float*>(e.C) + o, v);
+                if (e.C2) {
+                    float h[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] += ad[q];
-            }
-            const long long o = m * ldc + n;
-            if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
-            else st8(reinterpret_cast<float*>(e.C) + o, v);
-            if (e.C2) {
-                const long long o2 = m * ldc2 + n;
-                if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, v);
-                else st8(reinterpret_cast<float*>(e.C2) + o2, v);
+                    for (int q = 0; q < 8; ++q) h[q] = gelu_fast(v[q]) * sc[q];
+                    const long long o2 = m * ldc2 + n;
+                    if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, h);
+                    else st8(reinterpret_cast<float*>(e.C2) + o2, h);
+                }
+            } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[q] *= dgelu_fast(z[u][q]) * sc[q];
+                if (e.addend) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q] += ad[u][q];
+                }
+                const long long o = m * ldc + n;
+                if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
+                else st8(reinterpret_cast<float*>(e.C) + o, v);
+                if (e.C2) {
+                    const long long o2 = m * ldc2 + n;
+                    if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, v);
+                    else st8(reinterpret_cast<float*>(e.C2) + o2, v);
+                }
             }
         }
     }

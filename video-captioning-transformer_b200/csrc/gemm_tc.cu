@@ -184,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         //          touches 512 contiguous bytes (the TMEM layout gives each thread a ROW, which would make every
         //          global access a 16-byte piece of a different cache line)
         constexpr int RS = BLOCK_N + 4;                       // padded row stride (floats): conflict-free 16 B stores
-        float* stage = reinterpret_cast<float*>(smem);
+        const uint32_t stage = smem0;                         // shared-space address: explicit ld/st.shared, not generic
         const int q = warp & 3;
         const int row = q * 32 + lane;
         mbar_wait(smem_u32(&tmem_full_bar), 0);
@@ -202,9 +202,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < 32; ++i) r[i] = 0u;        // empty K range (split-K tail): contributes zeros
             }
-            uint4* dst = reinterpret_cast<uint4*>(stage + row * RS + c * 32);
+            const uint32_t dst = stage + (uint32_t)(row * RS + c * 32) * 4u;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+            for (int g = 0; g < 8; ++g) sts128(dst + 16u * g, r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
@@ -246,7 +246,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                           Epilogue epi, int tiles_m, int tiles_n) {
     extern __shared__ __align__(1024) unsigned char smem_raw[];
     unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    float* stage = reinterpret_cast<float*>(smem + P_STAGES * kPStage);
+    const uint32_t stage = smem_u32(smem + P_STAGES * kPStage);   // epilogue staging, shared-space address
     __shared__ __align__(8) unsigned long long full_bar[P_STAGES];
     __shared__ __align__(8) unsigned long long empty_bar[P_STAGES];
     __shared__ __align__(8) unsigned long long tmem_full_bar[2];
@@ -382,9 +382,9 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                     tmem_ld16(taddr, r);
                     tmem_ld16(taddr + 16, r + 16);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    uint4* dst = reinterpret_cast<uint4*>(stage + row * P_RS + c * 32);
+                    const uint32_t dst = stage + (uint32_t)(row * P_RS + c * 32) * 4u;
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) dst[g] = make_uint4(r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
+                    for (int g = 0; g < 8; ++g) sts128(dst + 16u * g, r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
                 }
                 if (ch == P_BN / P_CH - 1) {
                     // every TMEM read of this accumulator has completed: hand it back to the MMA warp
@@ -592,10 +592,12 @@ int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     const bool persistent = tiles_m * ((a->N + 255) / 256) >= 2 * kNumSMs && a->act == VCT_ACT_NONE &&
                             getenv("VCT_NO_PERSISTENT") == nullptr;
     if (persistent) { bn = 256; splits = 1; best = 0.0; }
+    static const int force_low = getenv("VCT_GEMM_LOW") ? atoi(getenv("VCT_GEMM_LOW")) : 0;
     for (int cand : {256, 128, 64}) {
+        if (force_low && cand == 256 && !persistent) continue;
         const long long tiles = tiles_m * ((a->N + cand - 1) / cand);
         const double cyc_kb = fmax(2.0 * cand, 316.5 + 1.215 * cand);
-        for (int lo = 0; lo <= (cand <= 128 ? 1 : 0); ++lo) {
+        for (int lo = (force_low && cand <= 128) ? 1 : 0; lo <= (cand <= 128 ? 1 : 0); ++lo) {
             for (int sp : {1, 2, 3, 4, 5, 6, 8}) {
                 if (sp > 1 && (a->splitk_ws == nullptr || total_kb < 16 * sp ||
                                (long long)sp * a->M * ldw > a->splitk_ws_floats)) continue;

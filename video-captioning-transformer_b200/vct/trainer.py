@@ -75,6 +75,12 @@ class CaptionTrainer:
                                                                  if dist.is_available() and dist.is_initialized() else 1)
         self._graphs = {}
         self._warm = {}
+        # The step is captured on a HIGH-priority stream: its kernels (the latency-bound dependent chain of forward and
+        # backward) are the critical path, while the side lanes (weight gradients, column sums, Adam slices -- default,
+        # i.e. lowest, priority) only need to finish by the end of the step.  The block scheduler then hands freed SM
+        # slots to main-lane CTAs first instead of letting a 1184-CTA Adam launch stall the next GEMM of backward.
+        self._cap_stream = torch.cuda.Stream(device=self.engine.device, priority=-1) \
+            if os.environ.get("VCT_MAIN_PRIORITY", "0") == "1" else None
         self.buckets = None
         if self.world > 1:
             # backward finishes the decoder (generator first, embedding last) before the encoder
@@ -114,8 +120,13 @@ class CaptionTrainer:
                 return
             g = torch.cuda.CUDAGraph()
             before = eng.launches
-            with torch.cuda.graph(g):
-                fn()
+            if self._cap_stream is not None:
+                self._cap_stream.wait_stream(torch.cuda.current_stream(eng.device))
+                with torch.cuda.graph(g, stream=self._cap_stream):
+                    fn()
+            else:
+                with torch.cuda.graph(g):
+                    fn()
             self._graphs[key] = (g, eng.launches - before)
             eng.launches = before          # capture issued nothing; the replay below is this step
         g, n = self._graphs[key]
