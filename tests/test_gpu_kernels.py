@@ -474,8 +474,8 @@ L_check = L.check
 
 @pytest.mark.parametrize("B,Lq,d,H,causal", [(64, 13, 768, 8, 0), (64, 20, 768, 8, 1), (7, 20, 768, 8, 1), (16, 33, 768, 8, 0),
                                              (64, 13, 512, 8, 0), (5, 20, 512, 8, 1), (3, 64, 512, 8, 1)])
-def test_fused_self_attention_matches_composition(lib, B, Lq, d, H, causal, monkeypatch):
-    monkeypatch.setenv("VCT_FUSED_ATTN", "1")       # the fused kernel is opt-in (see attn_fused.cu)
+def test_fused_self_attention_matches_composition(lib, B, Lq, d, H, causal):
+    # impl = TCGEN05 runs the fused tensor-core kernel (attn_fused.cu; sequences up to 32), impl = SIMT the composition
     g = torch.Generator().manual_seed(B + Lq + d)
     x = torch.randn(B * Lq, d, generator=g).to(DEV, torch.bfloat16)
     w = (torch.randn(3 * d, d, generator=g) * 0.04).to(DEV, torch.bfloat16)
@@ -490,6 +490,45 @@ def test_fused_self_attention_matches_composition(lib, B, Lq, d, H, causal, monk
         qs, os_, ps = _run_self_flavour(lib, x, w, b, key_pad, B, Lq, d, H, causal, L.GEMM_SIMT, p, rng)
         assert torch.isfinite(of.float()).all() and torch.isfinite(qf.float()).all()
         torch.testing.assert_close(qf.float(), qs.float(), rtol=2e-2, atol=2e-2)      # both bf16-rounded projections
-        # the fused kernel attends over un-rounded fp32 q/k/v, the composition over their bf16 roundings
+        # both attend over bf16-rounded q/k/v; the fused kernel also rounds the probabilities to bf16 for the P V MMA
+        torch.testing.assert_close(pf, ps, rtol=5e-2, atol=5e-3)
+        torch.testing.assert_close(of.float(), os_.float(), rtol=5e-2, atol=3e-2)
+
+
+def _run_cross_flavour(lib, x, mem, w, b, B, Lq, Lk, d, H, impl, drop_p=0.0, rng=None):
+    from vct import lib as VL
+    # K/V of the memory pre-projected (kv_ready = 1), exactly like the training plan does for every decoder layer
+    kv = (mem.float() @ w[d:].float().t() + b[d:]).to(torch.bfloat16).contiguous()
+    m = VL.MhaArgs()
+    q = torch.full((B * Lq, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    o = torch.full((B * Lq, d), float("nan"), device=DEV, dtype=torch.bfloat16)
+    probs = torch.zeros(B, H, Lq, Lk, device=DEV)
+    m.B, m.L, m.Lk, m.d, m.H, m.dtype = B, Lq, Lk, d, H, L_BF16
+    m.x, m.mem, m.w_in, m.b_in = x.data_ptr(), mem.data_ptr(), w.data_ptr(), b.data_ptr()
+    m.qkv, m.kv, m.kv_ready, m.o = q.data_ptr(), kv.data_ptr(), 1, o.data_ptr()
+    m.drop_p, m.rng_state, m.site = drop_p, (rng.data_ptr() if rng is not None else None), 654
+    m.probs = probs.data_ptr()
+    m.gemm_impl = impl
+    L_check(lib.vct_attn_dec_cross_fwd(C.byref(m), stream()))
+    torch.cuda.synchronize()
+    return q, o, probs
+
+
+@pytest.mark.parametrize("B,Lq,Lk,d,H", [(64, 20, 13, 768, 8), (7, 20, 13, 768, 8), (16, 20, 33, 768, 8), (128, 20, 33, 768, 8),
+                                         (5, 20, 13, 512, 8), (9, 25, 20, 768, 8), (64, 12, 13, 768, 8)])
+def test_fused_cross_attention_matches_composition(lib, B, Lq, Lk, d, H):
+    """decoder cross flavour: q projection + attention in one tensor-core kernel (TCGEN05) against projection GEMM +
+    stand-alone core (SIMT); Lq <= 16 (last case) is outside the fused kernel's coverage and checks the fallback."""
+    g = torch.Generator().manual_seed(B + Lq + Lk + d)
+    x = torch.randn(B * Lq, d, generator=g).to(DEV, torch.bfloat16)
+    mem = torch.randn(B * Lk, d, generator=g).to(DEV, torch.bfloat16)
+    w = (torch.randn(3 * d, d, generator=g) * 0.04).to(DEV, torch.bfloat16)
+    b = (torch.randn(3 * d, generator=g) * 0.1).to(DEV)
+    for p in (0.0, 0.3):
+        rng = torch.tensor([78, 9], dtype=torch.int64, device=DEV)
+        qf, of, pf = _run_cross_flavour(lib, x, mem, w, b, B, Lq, Lk, d, H, L.GEMM_TCGEN05, p, rng)
+        qs, os_, ps = _run_cross_flavour(lib, x, mem, w, b, B, Lq, Lk, d, H, L.GEMM_SIMT, p, rng)
+        assert torch.isfinite(of.float()).all() and torch.isfinite(qf.float()).all()
+        torch.testing.assert_close(qf.float(), qs.float(), rtol=2e-2, atol=2e-2)
         torch.testing.assert_close(pf, ps, rtol=5e-2, atol=5e-3)
         torch.testing.assert_close(of.float(), os_.float(), rtol=5e-2, atol=3e-2)

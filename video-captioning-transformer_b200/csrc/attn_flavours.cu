@@ -1,12 +1,14 @@
-// The three attention flavours of the reference as single C-ABI calls.  Self-attention (encoder, decoder causal)
-// in bf16 runs as ONE fused kernel (attn_fused.cu); the remaining cases compose the packed in-projection GEMM with
-// the stand-alone attention core.
+// The three attention flavours of the reference as single C-ABI calls.  In bf16 with the tcgen05 GEMM each flavour runs
+// as ONE fused kernel (attn_fused.cu: projection, scores, softmax, dropout and value gather, all contractions on the
+// tensor cores); the remaining cases (fp32, sequences longer than 32, cross-attention whose K/V are not projected
+// yet) compose the packed in-projection GEMM with the stand-alone attention core.
 #include "common.cuh"
 
 using namespace vct;
 
 namespace vct {
 int attn_fused_self(const vct_mha_args* m, int causal, cudaStream_t st);   // attn_fused.cu
+int attn_fused_cross(const vct_mha_args* m, cudaStream_t st);              // attn_fused.cu
 }
 
 namespace {
@@ -69,6 +71,11 @@ extern "C" int vct_attn_dec_cross_fwd(const vct_mha_args* a, vct_stream_t stream
     VCT_REQUIRE(a->d % a->H == 0, "vct_attn_dec_cross_fwd: d %% H != 0");
     const int d = a->d;
     const size_t es = esize(a->dtype);
+    // bf16 + tcgen05 with the memory's K/V already projected: ONE kernel (q projection + attention, attn_fused.cu)
+    {
+        const int r = vct::attn_fused_cross(a, (cudaStream_t)stream);
+        if (r <= 0) return r;
+    }
     // q = x W_in[0:d]^T + b_in[0:d]
     if (int e = project(a->x, a->B * a->L, d, d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream)) return e;
     if (!a->kv_ready) {

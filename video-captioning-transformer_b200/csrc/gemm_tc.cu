@@ -571,6 +571,50 @@ int get_tensor_map(const void* ptr, long long inner, long long outer, long long 
 // 0 = full ring, -1 = persistent kernel
 void gemm_tune(int bn, int splits, int low) { g_tune_bn = bn; g_tune_splits = splits; g_tune_low = low; }
 void gemm_trace(long long* dev_buf) { g_trace = dev_buf; }
+long long* gemm_trace_ptr() { return g_trace; }
+
+// 3-D bf16 tensor (dims innermost first, strides of dims 1 and 2 in bytes), SWIZZLE_128B, zero fill out of bounds
+int get_tensor_map_3d(const void* ptr, const unsigned long long dims[3], const unsigned long long strides_bytes[2],
+                      const unsigned int box[3], CUtensorMap* out) {
+    struct Key3 {
+        const void* ptr; unsigned long long d[3], s[2]; unsigned int b[3];
+        bool operator==(const Key3& o) const {
+            return ptr == o.ptr && d[0] == o.d[0] && d[1] == o.d[1] && d[2] == o.d[2] && s[0] == o.s[0] && s[1] == o.s[1] &&
+                   b[0] == o.b[0] && b[1] == o.b[1] && b[2] == o.b[2];
+        }
+    };
+    struct Hash3 {
+        size_t operator()(const Key3& k) const {
+            size_t h = std::hash<const void*>()(k.ptr);
+            auto mix = [&h](unsigned long long v) { h ^= std::hash<unsigned long long>()(v) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2); };
+            for (int i = 0; i < 3; ++i) { mix(k.d[i]); mix(k.b[i]); }
+            mix(k.s[0]); mix(k.s[1]);
+            return h;
+        }
+    };
+    static std::unordered_map<Key3, CUtensorMap, Hash3> cache;
+    static std::mutex mu;
+    Key3 key{ptr, {dims[0], dims[1], dims[2]}, {strides_bytes[0], strides_bytes[1]}, {box[0], box[1], box[2]}};
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        auto it = cache.find(key);
+        if (it != cache.end()) { *out = it->second; return 0; }
+    }
+    EncodeTiledFn enc = get_encode();
+    VCT_REQUIRE(enc != nullptr, "tensor map: cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t gd[3] = {dims[0], dims[1], dims[2]};
+    cuuint64_t gs[2] = {strides_bytes[0], strides_bytes[1]};
+    cuuint32_t bx[3] = {box[0], box[1], box[2]};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), gd, gs, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    VCT_REQUIRE(r == CUDA_SUCCESS, "tensor map: cuTensorMapEncodeTiled(3d) failed (%d) ptr=%p dims=%llu,%llu,%llu box=%u,%u,%u", (int)r,
+                ptr, dims[0], dims[1], dims[2], box[0], box[1], box[2]);
+    std::lock_guard<std::mutex> lk(mu);
+    if (cache.size() > 4096) cache.clear();
+    cache[key] = *out;
+    return 0;
+}
 
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {
     VCT_REQUIRE(a->a_dtype == VCT_BF16, "vct_gemm(tcgen05): operands must be bf16");
