@@ -137,6 +137,11 @@ typedef struct {
     /* batch strides in elements; 0 = dense default (Lq * ld for q/o/dq/d_o, Lk * ld for k/v/dk/dv).
      * Non-default strides let incremental decoding attend over a [B, Lmax, 3d] K/V cache. */
     long long q_bs, k_bs, v_bs, o_bs, do_bs, dq_bs, dk_bs, dv_bs;
+    /* backward only, optional: gradient of the packed in-projection bias (nn.MultiheadAttention.in_proj_bias),
+     * i.e. the column sums of dq | dk | dv over all (batch, position) rows, fp32 [3 * H * dh] laid out q | k | v.
+     * dbias_partials: fp32 workspace [B, 3 * H * dh]; dbias_counters: H zero-initialised uint32 (self-resetting).
+     * Deterministic (per-CTA partials, fixed-order final sum by the last CTA of each head). */
+    float* dbias; float* dbias_partials; unsigned int* dbias_counters;
 } vct_attn_args;
 
 int vct_attn_fwd(const vct_attn_args* args, vct_stream_t stream);

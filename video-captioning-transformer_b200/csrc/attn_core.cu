@@ -107,16 +107,23 @@ attn_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
 }
 
 template <typename T, int DHP>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)      // <= 128 registers: four CTAs per SM, so that B * H = 512 CTAs are one wave
 attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ d_o,
                 T* __restrict__ dq, T* __restrict__ dk, T* __restrict__ dv, const unsigned char* __restrict__ key_pad,
-                Dims D, float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site) {
+                Dims D, float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site,
+                float* __restrict__ dbias, float* __restrict__ dbias_part, unsigned int* dbias_cnt) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ __align__(16) float sm[];
+    __shared__ float colpart[kWarps][3][DHP];      // per-warp column sums of this head's dq, dk, dv rows (in-proj bias gradient)
+    __shared__ bool is_last;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
     const int dh = D.dh, Lk = D.Lk, Lq = D.Lq;
+    // (accumulated in shared memory, not registers: the kernel sits exactly at the 128-register limit that lets four
+    // CTAs share an SM, and 512 CTAs need all 4 x 148 slots to run as one wave)
+#pragma unroll
+    for (int cc = 0; cc < DHP / 32; ++cc) colpart[warp][0][lane + 32 * cc] = colpart[warp][1][lane + 32 * cc] = colpart[warp][2][lane + 32 * cc] = 0.f;
     constexpr int KS = DHP + 1;
     const int LkP = (Lk + 3) & ~3, LqP = (Lq + 3) & ~3;
     float* Qs = sm;                        // [Lq][DHP]
@@ -180,6 +187,7 @@ attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
                     for (int cc = 0; cc < DHP / 32; ++cc) {
                         const int c = lane + 32 * cc;
                         if (c < dh) row[c] = from_f32<T>(acc[kk][cc]);
+                        if (dbias != nullptr) colpart[warp][0][c] += acc[kk][cc];
                     }
                 }
             }
@@ -222,9 +230,52 @@ attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
                 for (int cc = 0; cc < DHP / 32; ++cc) {
                     const int c = lane + 32 * cc;
                     if (c < dh) { krow[c] = from_f32<T>(ak[kk][cc]); vrow[c] = from_f32<T>(av[kk][cc]); }
+                    if (dbias != nullptr) {
+                        colpart[warp][1][c] += ak[kk][cc];
+                        colpart[warp][2][c] += av[kk][cc];
+                    }
                 }
             }
         }
+    }
+    // ---- in-projection bias gradient: column sums of dq | dk | dv over all (batch, position) rows, without a separate
+    //      pass over the gradient matrix.  CTA (b, h) writes its [3][dh] sums to dbias_part[b]; the last CTA of head h to
+    //      finish adds the B partials in batch order (deterministic) into dbias (layout q | k | v, each H * dh wide). ----
+    if (dbias == nullptr) return;
+    __syncthreads();
+    const int Hd = D.H * dh;
+    for (int t = threadIdx.x; t < 3 * dh; t += kThreads) {
+        const int sec = t / dh, c = t % dh;
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) a += colpart[w][sec][c];
+        dbias_part[(long long)b * 3 * Hd + sec * Hd + h * dh + c] = a;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(dbias_cnt + h, 1u);
+        is_last = (prev == (unsigned int)D.B - 1u);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        for (int t = threadIdx.x; t < 3 * dh; t += kThreads) {
+            const int sec = t / dh, c = t % dh;
+            const long long col = sec * Hd + h * dh + c;
+            float a = 0.f;
+            int bb = 0;
+            for (; bb + 16 <= D.B; bb += 16) {                  // 16 independent loads in flight, summed in batch order
+                float v[16];
+#pragma unroll
+                for (int u = 0; u < 16; ++u) v[u] = __ldcg(dbias_part + (long long)(bb + u) * 3 * Hd + col);
+#pragma unroll
+                for (int u = 0; u < 16; ++u) a += v[u];
+            }
+            for (; bb < D.B; ++bb) a += __ldcg(dbias_part + (long long)bb * 3 * Hd + col);
+            dbias[col] = a;
+        }
+        if (threadIdx.x == 0) dbias_cnt[h] = 0u;
     }
 }
 
@@ -279,7 +330,8 @@ int launch_bwd(const vct_attn_args* a, cudaStream_t st) {
     static bool once = false;
     if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
     vct::launch(kern, dim3(a->B * a->H), dim3(kThreads), smem, st, (const T*)a->q, (const T*)a->k, (const T*)a->v, (const T*)a->d_o, (T*)a->dq,
-                                              (T*)a->dk, (T*)a->dv, a->key_pad, make_dims(a), a->drop_p, a->rng_state, a->site);
+                                              (T*)a->dk, (T*)a->dv, a->key_pad, make_dims(a), a->drop_p, a->rng_state, a->site,
+                                              a->dbias, a->dbias_partials, a->dbias_counters);
     return check_launch("vct_attn_bwd");
 }
 
@@ -306,6 +358,8 @@ extern "C" int vct_attn_bwd(const vct_attn_args* a, vct_stream_t stream) {
     VCT_REQUIRE(a->q && a->k && a->v && a->d_o && a->dq && a->dk && a->dv, "vct_attn_bwd: null tensor");
     VCT_REQUIRE(a->do_ld % 4 == 0 && a->dq_ld % 4 == 0 && a->dk_ld % 4 == 0 && a->dv_ld % 4 == 0,
                 "vct_attn_bwd: gradient row strides must be multiples of 4 elements");
+    VCT_REQUIRE(a->dbias == nullptr || (a->dbias_partials != nullptr && a->dbias_counters != nullptr),
+                "vct_attn_bwd: dbias needs dbias_partials and dbias_counters");
     if (a->dtype == VCT_BF16) return dispatch<__nv_bfloat16>(a, (cudaStream_t)stream, true);
     return dispatch<float>(a, (cudaStream_t)stream, true);
 }

@@ -484,19 +484,46 @@ extern "C" long long vct_colsum_workspace_floats(int M, int N) {
     return (long long)((M + kCsRows - 1) / kCsRows) * N;
 }
 
+// A CTA owns kCsCols columns x kCsRows rows.  Each lane reads 8 consecutive columns (16 bytes of bf16) of a row, a warp
+// therefore 512 contiguous bytes; the 8 warps take rows w, w + 8, ... and their partial sums are combined through
+// shared memory in warp order (deterministic).  The last CTA of a column block adds the row-slice partials.
 template <typename T>
-__global__ void __launch_bounds__(kCsCols)
+__global__ void __launch_bounds__(256)
 colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, float* __restrict__ out,
-              float* __restrict__ partials, unsigned int* counters) {
+              float* __restrict__ partials, unsigned int* counters, int vec) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ bool is_last;
-    const int n = blockIdx.x * kCsCols + threadIdx.x;
+    __shared__ float part[8][kCsCols + 8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * kCsCols;
     const int m0 = blockIdx.y * kCsRows, m1 = min(M, m0 + kCsRows);
+    const int nl = n0 + lane * 8;
+    float a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+    if (vec && nl + 8 <= N) {
+        for (int m = m0 + warp; m < m1; m += 8) {
+            float v[8];
+            ld8(X + (long long)m * ld + nl, v);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) a[q] += v[q];
+        }
+    } else {
+        for (int m = m0 + warp; m < m1; m += 8)
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (nl + q < N) a[q] += to_f32(X[(long long)m * ld + nl + q]);
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) part[warp][lane * 8 + q] = a[q];
+    __syncthreads();
+    const int n = n0 + threadIdx.x;
     if (n < N) {
-        float a = 0.f;
-        for (int m = m0; m < m1; ++m) a += to_f32(X[(long long)m * ld + n]);
-        partials[(long long)blockIdx.y * N + n] = a;
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += part[w][threadIdx.x];
+        partials[(long long)blockIdx.y * N + n] = t;
     }
     __threadfence();
     __syncthreads();
@@ -508,9 +535,9 @@ colsum_kernel(const T* __restrict__ X, long long ld, int M, int N, float* __rest
     if (is_last) {
         __threadfence();
         if (n < N) {
-            float a = 0.f;
-            for (unsigned int b = 0; b < gridDim.y; ++b) a += __ldcg(partials + (long long)b * N + n);
-            out[n] = a;
+            float t = 0.f;
+            for (unsigned int b = 0; b < gridDim.y; ++b) t += __ldcg(partials + (long long)b * N + n);
+            out[n] = t;
         }
         if (threadIdx.x == 0) counters[blockIdx.x] = 0u;
     }
@@ -520,10 +547,12 @@ extern "C" int vct_colsum(const void* X, int dtype, long long ld, int M, int N, 
                           unsigned int* counter, vct_stream_t stream) {
     VCT_REQUIRE(M > 0 && N > 0 && N <= 65536, "vct_colsum: need 0 < N <= 65536 (counter array has 256 entries)");
     dim3 grid((N + kCsCols - 1) / kCsCols, (M + kCsRows - 1) / kCsRows);
+    // 16-byte (bf16) / 2 x 16-byte (fp32) row pieces need 8-element aligned rows
+    const int vec = (ld % 8 == 0) && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
     if (dtype == VCT_BF16)
-        vct::launch(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(kCsCols), 0, (cudaStream_t)stream, (const __nv_bfloat16*)X, ld, M, N, out, partials, counter);
+        vct::launch(colsum_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)X, ld, M, N, out, partials, counter, vec);
     else
-        vct::launch(colsum_kernel<float>, dim3(grid), dim3(kCsCols), 0, (cudaStream_t)stream, (const float*)X, ld, M, N, out, partials, counter);
+        vct::launch(colsum_kernel<float>, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const float*)X, ld, M, N, out, partials, counter, vec);
     return check_launch("vct_colsum");
 }
 

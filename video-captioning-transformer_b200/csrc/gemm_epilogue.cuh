@@ -212,9 +212,10 @@ __device__ __forceinline__ void plain_row(PlainCtx& x, float4 v, float4 a4, int 
     }
 }
 
-template <int BN>
+template <int BN, int NT>
 __device__ __forceinline__ void epilogue_tile_plain(const Epilogue& e, const Rng& rng, uint32_t stage, int RS, int m0, int n0, int t) {
-    constexpr int CG4 = BN / 4, RSTEP = 128 / CG4;          // 4-column groups per row; rows covered per pass
+    constexpr int CG4 = BN / 4, RSTEP = NT / CG4;           // 4-column groups per row; rows covered per pass of NT threads
+    if (t >= RSTEP * CG4) return;
     const int c4 = t % CG4, n = n0 + c4 * 4;
     if (n >= e.N) return;
     const int rows = min(128, e.M - m0);
@@ -257,10 +258,11 @@ __device__ __forceinline__ void epilogue_tile_plain(const Epilogue& e, const Rng
 }
 
 // raw fp32 partial sums of a split-K slice: ws[m * ldw + n] (ws already offset to the slice)
-template <int BN>
+template <int BN, int NT>
 __device__ __forceinline__ void epilogue_tile_partial(float* __restrict__ ws, long long ldw, int M, int N, uint32_t stage, int RS,
                                                       int m0, int n0, int t) {
-    constexpr int CG4 = BN / 4, RSTEP = 128 / CG4;
+    constexpr int CG4 = BN / 4, RSTEP = NT / CG4;
+    if (t >= RSTEP * CG4) return;
     const int c4 = t % CG4, n = n0 + c4 * 4;
     if (n >= N) return;                                     // ldw is a multiple of 8 >= N: whole float4 groups are in bounds
     const int rows = min(128, M - m0);
@@ -281,9 +283,10 @@ __device__ __forceinline__ void epilogue_tile_partial(float* __restrict__ ws, lo
 
 // activation epilogues (GELU forward / backward): 8-column groups per thread so that one Philox draw covers the
 // group's 8 dropout decisions and bf16 outputs are stored 16 bytes at a time
-template <int ACT, int BN>
+template <int ACT, int BN, int NT>
 __device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& rng, uint32_t stage, int RS, int m0, int n0, int t) {
-    constexpr int CG = BN / 8, RSTEP = 128 / CG;
+    constexpr int CG = BN / 8, RSTEP = NT / CG;
+    if (t >= RSTEP * CG) return;
     const int cg = t % CG, n = n0 + cg * 8;
     if (n >= e.N) return;
     const int rows = min(128, e.M - m0);
@@ -302,27 +305,32 @@ __device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& 
     const long long ldc = e.ldc, ldc2 = e.ldc2, ldx = e.ld_aux, lda = e.ld_addend;
     const unsigned long long N = (unsigned long long)e.N;
     const unsigned int site = e.site;
+    // two rows per pass; the global operands of the NEXT pass (z and the addend of the GELU backward) are requested before
+    // the math of the current one, so that their L2 latency is hidden behind ~500 instructions of work
+    float z[2][8], ad[2][8], zn[2][8], adn[2][8];
+    auto fetch = [&](int r0, float (&zz)[2][8], float (&aa)[2][8]) {
+        if (ACT != VCT_ACT_GELU_BWD) return;
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int rq = r0 + u * RSTEP;
+            if (rq < rows) {
+                const long long mm = m0 + rq;
+                if (aux_bf16) ld8(reinterpret_cast<const __nv_bfloat16*>(e.aux) + mm * ldx + n, zz[u]);
+                else ld8(reinterpret_cast<const float*>(e.aux) + mm * ldx + n, zz[u]);
+                if (e.addend) ld8(e.addend + mm * lda + n, aa[u]);
+            }
+        }
+    };
+    fetch(rr, z, ad);
     for (; rr < rows; rr += 2 * RSTEP, src += 2 * src_step) {
-        // two rows per pass: all shared / global loads first, then the math and the stores
         const bool two = rr + RSTEP < rows;
         float4 a[2][2];
-        float z[2][8], ad[2][8];
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             a[u][0] = lds128(src + u * src_step);
             a[u][1] = lds128(src + u * src_step + 16);
         }
-        if (ACT == VCT_ACT_GELU_BWD) {
-#pragma unroll
-            for (int u = 0; u < 2; ++u) {
-                if (u == 0 || two) {
-                    const long long mm = m0 + rr + u * RSTEP;
-                    if (aux_bf16) ld8(reinterpret_cast<const __nv_bfloat16*>(e.aux) + mm * ldx + n, z[u]);
-                    else ld8(reinterpret_cast<const float*>(e.aux) + mm * ldx + n, z[u]);
-                    if (e.addend) ld8(e.addend + mm * lda + n, ad[u]);
-                }
-            }
-        }
+        fetch(rr + 2 * RSTEP, zn, adn);
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             if (u == 1 && !two) break;
@@ -359,6 +367,12 @@ __device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& 
                     else st8(reinterpret_cast<float*>(e.C2) + o2, v);
                 }
             }
+        }
+        if (ACT == VCT_ACT_GELU_BWD) {
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) { z[u][q] = zn[u][q]; ad[u][q] = adn[u][q]; }
         }
     }
 }

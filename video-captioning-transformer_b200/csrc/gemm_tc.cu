@@ -207,18 +207,23 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int g = 0; g < 8; ++g) sts128(dst + 16u * g, r[4 * g], r[4 * g + 1], r[4 * g + 2], r[4 * g + 3]);
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");        // the 4 epilogue warps only
-        if (trace && threadIdx.x == 64) trace[5] = clock64();
-        const int t = threadIdx.x - 64;
+    }
+    // phase 2 is run by ALL warps: the producer and MMA warps have nothing left to do, and the elementwise part of the
+    // epilogue (GELU, Philox, conversions) is bound by instruction issue of the few warps that execute it
+    __syncthreads();
+    if (trace && threadIdx.x == 64) trace[5] = clock64();
+    {
+        constexpr int RS = BLOCK_N + 4;
+        const int t = threadIdx.x;
         if (splitk_ws != nullptr) {
             // raw partial sums; vct's split-K reduce kernel applies the epilogue
-            epilogue_tile_partial<BLOCK_N>(splitk_ws + (long long)blockIdx.z * epi.M * ldw, ldw, epi.M, epi.N, stage, RS, m0, n0, t);
+            epilogue_tile_partial<BLOCK_N, kThreads>(splitk_ws + (long long)blockIdx.z * epi.M * ldw, ldw, epi.M, epi.N, smem0, RS, m0, n0, t);
         } else if (ACT == VCT_ACT_NONE) {
             const Rng rng = make_rng(nullptr, 0.f);
-            epilogue_tile_plain<BLOCK_N>(epi, rng, stage, RS, m0, n0, t);
+            epilogue_tile_plain<BLOCK_N, kThreads>(epi, rng, smem0, RS, m0, n0, t);
         } else {
             const Rng rng = make_rng(epi.rng_state, epi.drop_p);
-            epilogue_tile_act<ACT, BLOCK_N>(epi, rng, stage, RS, m0, n0, t);
+            epilogue_tile_act<ACT, BLOCK_N, kThreads>(epi, rng, smem0, RS, m0, n0, t);
         }
         if (trace && threadIdx.x == 64) trace[6] = clock64();
     }
@@ -392,7 +397,7 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
                     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
-                epilogue_tile_plain<P_CH>(epi, rng, stage, P_RS, m0, n0 + ch * P_CH, t);
+                epilogue_tile_plain<P_CH, 128>(epi, rng, stage, P_RS, m0, n0 + ch * P_CH, t);
                 asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer is reused by the next chunk
             }
         }

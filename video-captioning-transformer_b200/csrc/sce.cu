@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 sce_kernel(const float* __restrict__ logits, long long ld_logits, const long long* __restrict__ ids, long long ids_ld,
            int B, int S, int V, float alpha, float beta, int pad_id, float* __restrict__ loss_out,
            float* __restrict__ row_parts, unsigned int* counter, TD* __restrict__ dlogits, long long ld_dl,
-           const float* __restrict__ upstream) {
+           const float* __restrict__ upstream, int vec) {
     pdl_launch_dependents();
     pdl_wait();
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -94,6 +94,95 @@ sce_kernel(const float* __restrict__ logits, long long ld_logits, const long lon
         }
     }
 
+    float ce_i = 0.f, rce_i = 0.f;
+    if (vec) {
+        // ---- vectorised path (row strides multiples of 8): 16-byte shared-memory accesses, exp through one MUFU
+        //      (exp2 of the log2(e)-scaled difference, relative error 2^-22), 16-byte gradient stores.  The kernel is
+        //      bound by instruction issue (one CTA per SM: the 122 KB row fills shared memory), so every pass is
+        //      written for the fewest instructions per element. ----
+        const int n4 = (int)(ld_logits >> 2);
+        float4* z4 = reinterpret_cast<float4*>(zs);
+        float m = -INFINITY;
+        for (int i = tid; i < n4; i += kThreads) {
+            float4 v = z4[i];
+            const int c = 4 * i;
+            if (c + 3 >= V) {                                   // padding columns of the logits buffer are undefined
+                if (c + 0 >= V) v.x = -INFINITY;
+                if (c + 1 >= V) v.y = -INFINITY;
+                if (c + 2 >= V) v.z = -INFINITY;
+                v.w = -INFINITY;
+                z4[i] = v;
+            }
+            m = fmaxf(m, fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)));
+        }
+        m = block_max(m, red);
+        const float zy = zs[y];
+        __syncthreads();
+        const float ml2 = m * 1.4426950408889634f;
+        float se = 0.f;
+        for (int i = tid; i < n4; i += kThreads) {
+            float4 v = z4[i];
+            v.x = exp2f(fmaf(v.x, 1.4426950408889634f, -ml2));
+            v.y = exp2f(fmaf(v.y, 1.4426950408889634f, -ml2));
+            v.z = exp2f(fmaf(v.z, 1.4426950408889634f, -ml2));
+            v.w = exp2f(fmaf(v.w, 1.4426950408889634f, -ml2));
+            z4[i] = v;
+            se += (v.x + v.y) + (v.z + v.w);
+        }
+        se = block_sum(se, red);
+        const float inv = 1.f / se;
+        ce_i = valid ? (m + logf(se) - zy) : 0.f;
+        float U = 0.f;
+        if (alpha != 1.0f) {
+            // U = sum_{c != y, p_c >= 1e-7} p_c; the clamped classes are counted instead
+            const float ethr = kPMin * se;                       // p >= pmin  <=>  e >= pmin * se
+            float u = 0.f, nclamp = 0.f;
+            for (int i = tid; i < n4; i += kThreads) {
+                const float4 v = z4[i];
+                u += (v.x >= ethr ? v.x : 0.f) + (v.y >= ethr ? v.y : 0.f) + (v.z >= ethr ? v.z : 0.f) + (v.w >= ethr ? v.w : 0.f);
+                nclamp += (v.x < ethr ? 1.f : 0.f) + (v.y < ethr ? 1.f : 0.f) + (v.z < ethr ? 1.f : 0.f) + (v.w < ethr ? 1.f : 0.f);
+            }
+            u = block_sum(u, red);
+            nclamp = block_sum(nclamp, red);
+            // remove the label class and the (zero-probability) padding columns from both tallies
+            const float ey = zs[y];
+            if (ey >= ethr) u -= ey; else nclamp -= 1.f;
+            nclamp -= (float)(4 * n4 - V);
+            U = u * inv;
+            rce_i = kRceA * (U + nclamp * kPMin);
+        }
+        if (dlogits != nullptr) {
+            const float up = upstream ? upstream[0] : 1.f;
+            const float a = (alpha == 1.0f ? 1.f : alpha) * (valid ? up / fmaxf(n_valid, 1.f) : 0.f);
+            const float bb = alpha == 1.0f ? 0.f : beta * kRceA * up / (float)N;
+            // g = a (p - [c == y]) + bb ([c != y, p >= pmin] p - p U) = e * (ka or kb) with the label fixed up afterwards
+            const float ethr = kPMin * se;
+            const float k_keep = (a + bb * (1.f - U)) * inv;      // classes at or above the clamp
+            const float k_clamp = (a - bb * U) * inv;             // clamped classes (their RCE term has no gradient)
+            TD* drow = dlogits + (long long)row * ld_dl;
+            const int n8 = (int)(ld_dl >> 3);
+            for (int i = tid; i < n8; i += kThreads) {
+                float g[8];
+                if (8 * i < 4 * n4) {
+                    const float4 v0 = z4[2 * i], v1 = (2 * i + 1 < n4) ? z4[2 * i + 1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                    const float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] = e[q] * (e[q] >= ethr ? k_keep : k_clamp);
+                    const int rel = y - 8 * i;
+                    if (rel >= 0 && rel < 8) {
+                        const float py = zs[y] * inv;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            if (q == rel) g[q] = a * (py - 1.f) - bb * py * U;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) g[q] = 0.f;
+                }
+                st8(drow + 8 * i, g);
+            }
+        }
+    } else {
     float m = -INFINITY;
     for (int c = tid; c < V; c += kThreads) m = fmaxf(m, zs[c]);
     m = block_max(m, red);
@@ -107,9 +196,9 @@ sce_kernel(const float* __restrict__ logits, long long ld_logits, const long lon
     }
     se = block_sum(se, red);
     const float inv = 1.f / se;
-    const float ce_i = valid ? (m + logf(se) - zy) : 0.f;
+    ce_i = valid ? (m + logf(se) - zy) : 0.f;
 
-    float U = 0.f, rce_i = 0.f;
+    float U = 0.f;
     if (alpha != 1.0f) {
         float u = 0.f, nclamp = 0.f;
         for (int c = tid; c < V; c += kThreads) {
@@ -137,6 +226,7 @@ sce_kernel(const float* __restrict__ logits, long long ld_logits, const long lon
             drow[c] = from_f32<TD>(g);
         }
     }
+    }   // scalar path
 
     if (loss_out != nullptr) {
         if (tid == 0) {
@@ -179,6 +269,8 @@ extern "C" int vct_sce(const float* logits, long long ld_logits, const long long
     VCT_REQUIRE(loss_out == nullptr || (row_parts && counter), "vct_sce: loss needs row_parts and counter");
     VCT_REQUIRE(dlogits == nullptr || ld_dl >= V, "vct_sce: ld_dl < V");
     cudaStream_t st = (cudaStream_t)stream;
+    const int vec = (ld_logits % 8 == 0) && (dlogits == nullptr || (ld_dl % 8 == 0 && ld_dl <= ld_logits + 8 &&
+                                                                    (reinterpret_cast<uintptr_t>(dlogits) & 15) == 0)) ? 1 : 0;
     static bool attr_done[2] = {false, false};
     if (dl_dtype == VCT_BF16) {
         auto kern = sce_kernel<__nv_bfloat16>;
@@ -187,7 +279,7 @@ extern "C" int vct_sce(const float* logits, long long ld_logits, const long long
             attr_done[1] = true;
         }
         vct::launch(kern, dim3(B * S), dim3(kThreads), smem, st, logits, ld_logits, ids, ids_ld, B, S, V, alpha, beta, pad_id, loss_out,
-                                            row_parts, counter, (__nv_bfloat16*)dlogits, ld_dl, upstream);
+                                            row_parts, counter, (__nv_bfloat16*)dlogits, ld_dl, upstream, vec);
     } else {
         auto kern = sce_kernel<float>;
         if (!attr_done[0]) {
@@ -195,7 +287,7 @@ extern "C" int vct_sce(const float* logits, long long ld_logits, const long long
             attr_done[0] = true;
         }
         vct::launch(kern, dim3(B * S), dim3(kThreads), smem, st, logits, ld_logits, ids, ids_ld, B, S, V, alpha, beta, pad_id, loss_out,
-                                            row_parts, counter, (float*)dlogits, ld_dl, upstream);
+                                            row_parts, counter, (float*)dlogits, ld_dl, upstream, vec);
     }
     return check_launch("vct_sce");
 }

@@ -316,7 +316,7 @@ class CaptionEngine:
 
     def _attn(self, plan: Plan, tag, bwd, *, B, H, Lq, Lk, q, q_ld, k, k_ld, v, v_ld, o, o_ld, key_pad=None, causal=0,
               p=0.0, site=0, probs=None, d_o=None, do_ld=0, dq=None, dq_ld=0, dk=None, dk_ld=0, dv=None, dv_ld=0,
-              q_bs=0, k_bs=0, v_bs=0, o_bs=0):
+              q_bs=0, k_bs=0, v_bs=0, o_bs=0, dbias=None, ws=None):
         a = L.AttnArgs()
         a.B, a.H, a.Lq, a.Lk, a.dh = B, H, Lq, Lk, self.dims.d // H
         a.dtype = self.cdt
@@ -326,6 +326,11 @@ class CaptionEngine:
         a.probs = probs
         a.d_o, a.do_ld, a.dq, a.dq_ld, a.dk, a.dk_ld, a.dv, a.dv_ld = d_o, do_ld, dq, dq_ld, dk, dk_ld, dv, dv_ld
         a.q_bs, a.k_bs, a.v_bs, a.o_bs = q_bs, k_bs, v_bs, o_bs
+        if dbias is not None:
+            # in-projection bias gradient (column sums of dq | dk | dv) produced by the backward kernel itself; the
+            # partials buffer is per call site, the counters are self-resetting
+            part = self._scratch(ws, "attn_dbias:" + tag, B, 3 * self.dims.d, torch.float32)
+            a.dbias, a.dbias_partials, a.dbias_counters = dbias, part.data_ptr(), self.counters.data_ptr() + 4 * 512
         plan.keep.append(a)
         plan.add(("vct_attn_bwd:" if bwd else "vct_attn_fwd:") + tag,
                  self.lib.vct_attn_bwd if bwd else self.lib.vct_attn_fwd, C.byref(a))
@@ -675,14 +680,13 @@ class CaptionEngine:
             self._attn(p, f"dec{l}.cross", True, B=B, H=D.H_dec, Lq=S, Lk=M, q=e.q.data_ptr(), q_ld=d,
                        k=e.kv.data_ptr(), k_ld=2 * d, v=e.kv.data_ptr() + d * es, v_ld=2 * d, o=None, o_ld=d,
                        p=pd, site=_dec_site(l, 2), d_o=g_o, do_ld=d, dq=g_q, dq_ld=d,
-                       dk=g_kv, dk_ld=2 * d, dv=g_kv + d * es, dv_ld=2 * d)
+                       dk=g_kv, dk_ld=2 * d, dv=g_kv + d * es, dv_ld=2 * d,
+                       dbias=self._g(pre + "multihead_attn.in_proj_bias"), ws=ws)
             wname, bname = pre + "multihead_attn.in_proj_weight", pre + "multihead_attn.in_proj_bias"
             with side(p):
                 self._gemm(p, f"dec{l}.cross.q.wgrad", d, d, Rd, g_q, d, 1, e.x1_c.data_ptr(), d, 1, self._g(wname), F32, d)
-                self._colsum(p, f"dec{l}.cross.q.bias", g_q, d, Rd, d, self._g(bname), ws)
                 self._gemm(p, f"dec{l}.cross.kv.wgrad", 2 * d, d, Re, g_kv, 2 * d, 1, ws.mem_c.data_ptr(), d, 1,
                            self._g(wname, d * d), F32, d)
-                self._colsum(p, f"dec{l}.cross.kv.bias", g_kv, 2 * d, Re, 2 * d, self._g(bname, d), ws)
             self._gemm(p, f"dec{l}.cross.q.dgrad", Rd, d, d, g_q, d, 0, self._w(wname), d, 1,
                        other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
             self._gemm(p, f"dec{l}.cross.kv.dgrad", Re, d, 2 * d, g_kv, 2 * d, 0, self._w(wname, d), d, 1,
@@ -702,12 +706,12 @@ class CaptionEngine:
             self._attn(p, f"dec{l}.self", True, B=B, H=D.H_dec, Lq=S, Lk=S, q=qkv, q_ld=3 * d, k=qkv + d * es, k_ld=3 * d,
                        v=qkv + 2 * d * es, v_ld=3 * d, o=None, o_ld=d, key_pad=ws.tok_pad.data_ptr(), causal=1, p=pd,
                        site=_dec_site(l, 0), d_o=g_o, do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
-                       dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d)
+                       dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d,
+                       dbias=self._g(pre + "self_attn.in_proj_bias"), ws=ws)
             wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
             with side(p):
                 self._gemm(p, f"dec{l}.self.in_proj.wgrad", 3 * d, d, Rd, gq, 3 * d, 1, xin_c.data_ptr(), d, 1,
                            self._g(wname), F32, d)
-                self._colsum(p, f"dec{l}.self.in_proj.bias", gq, 3 * d, Rd, 3 * d, self._g(bname), ws)
             self._gemm(p, f"dec{l}.self.in_proj.dgrad", Rd, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
                        addend=ws.g_s.data_ptr(), ld_addend=d)
             dx, other = other, dx           # dx = grad wrt the layer input
@@ -766,11 +770,11 @@ class CaptionEngine:
             self._attn(p, f"enc{l}.self", True, B=B, H=D.H_enc, Lq=M, Lk=M, q=qkv, q_ld=3 * d, k=qkv + d * es, k_ld=3 * d,
                        v=qkv + 2 * d * es, v_ld=3 * d, o=None, o_ld=d, key_pad=ws.vid_pad.data_ptr(), causal=0, p=pd,
                        site=_enc_site(l, 0), d_o=g_o, do_ld=d, dq=gq, dq_ld=3 * d, dk=gq + d * es,
-                       dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d)
+                       dk_ld=3 * d, dv=gq + 2 * d * es, dv_ld=3 * d,
+                       dbias=self._g(pre + "self_attn.in_proj_bias"), ws=ws)
             wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
             with side(p):
                 self._gemm(p, f"enc{l}.in_proj.wgrad", 3 * d, d, Re, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d)
-                self._colsum(p, f"enc{l}.in_proj.bias", gq, 3 * d, Re, 3 * d, self._g(bname), ws)
             last = l == 0
             self._gemm(p, f"enc{l}.in_proj.dgrad", Re, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
                        addend=ws.g_s.data_ptr(), ld_addend=d,
