@@ -532,3 +532,53 @@ def test_fused_cross_attention_matches_composition(lib, B, Lq, Lk, d, H):
         torch.testing.assert_close(qf.float(), qs.float(), rtol=2e-2, atol=2e-2)
         torch.testing.assert_close(pf, ps, rtol=5e-2, atol=5e-3)
         torch.testing.assert_close(of.float(), os_.float(), rtol=5e-2, atol=3e-2)
+
+
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,causal", [(64, 8, 20, 20, 96, 1), (64, 8, 13, 13, 96, 0), (64, 8, 20, 13, 96, 0), (7, 8, 20, 20, 96, 1),
+                                                 (16, 8, 20, 33, 96, 0), (5, 8, 20, 13, 64, 0), (9, 8, 25, 25, 64, 1)])
+def test_attention_backward_tcgen05_matches_simt(lib, B, H, Lq, Lk, dh, causal):
+    """bf16 attention backward: the tensor-core kernel (attn_fused.cu) against the SIMT kernel (forced by passing explicit
+    gradient batch strides, which the tensor-core path does not take), with key padding, dropout and the fused
+    in-projection bias gradient."""
+    g = torch.Generator().manual_seed(B + 7 * Lq + Lk)
+    d = H * dh
+    q = torch.randn(B, Lq, H, dh, generator=g).to(DEV, torch.bfloat16)
+    k = torch.randn(B, Lk, H, dh, generator=g).to(DEV, torch.bfloat16)
+    v = torch.randn(B, Lk, H, dh, generator=g).to(DEV, torch.bfloat16)
+    do = torch.randn(B, Lq, H, dh, generator=g).to(DEV, torch.bfloat16)
+    key_pad = None
+    if Lq == Lk:
+        key_pad = torch.zeros(B, Lk, dtype=torch.uint8)
+        for b in range(1, B):
+            key_pad[b, Lk - (b % 6):] = 1 if b % 6 else 0
+        key_pad = key_pad.to(DEV)
+    rng = torch.tensor([91, 3], dtype=torch.int64, device=DEV)
+    outs = []
+    for force_simt in (False, True):
+        dq, dk, dv = (torch.full_like(t, float("nan")) for t in (q, k, v))
+        dbias = torch.full((3 * d,), float("nan"), device=DEV)
+        part = torch.empty(B, 3 * d, device=DEV)
+        cnt = torch.zeros(H, dtype=torch.int32, device=DEV)
+        a = L.AttnArgs()
+        a.B, a.H, a.Lq, a.Lk, a.dh, a.dtype = B, H, Lq, Lk, dh, L.BF16
+        a.q, a.q_ld, a.k, a.k_ld, a.v, a.v_ld = q.data_ptr(), d, k.data_ptr(), d, v.data_ptr(), d
+        a.key_pad = key_pad.data_ptr() if key_pad is not None else None
+        a.causal, a.scale = causal, 1.0 / math.sqrt(dh)
+        a.drop_p, a.rng_state, a.site = 0.3, rng.data_ptr(), 17
+        a.d_o, a.do_ld, a.dq, a.dq_ld, a.dk, a.dk_ld, a.dv, a.dv_ld = do.data_ptr(), d, dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d
+        a.dbias, a.dbias_partials, a.dbias_counters = dbias.data_ptr(), part.data_ptr(), cnt.data_ptr()
+        if force_simt:
+            a.dq_bs, a.dk_bs, a.dv_bs = Lq * d, Lk * d, Lk * d
+        L.check(lib.vct_attn_bwd(C.byref(a), stream()), "bwd")
+        torch.cuda.synchronize()
+        assert int(cnt.abs().sum()) == 0                       # counters reset themselves
+        outs.append((dq.float(), dk.float(), dv.float(), dbias.clone()))
+    (dq_t, dk_t, dv_t, db_t), (dq_s, dk_s, dv_s, db_s) = outs
+    for t_, s_ in ((dq_t, dq_s), (dk_t, dk_s), (dv_t, dv_s)):
+        assert torch.isfinite(t_).all()
+        torch.testing.assert_close(t_, s_, rtol=3e-2, atol=3e-2)
+        assert float((t_ - s_).norm() / s_.norm()) < 1e-2
+    assert float((db_t - db_s).norm() / db_s.norm()) < 5e-3
+    # the bias gradient is the column sum of the (unrounded) gradients
+    ref = torch.cat([dq_s.reshape(-1, d).sum(0), dk_s.reshape(-1, d).sum(0), dv_s.reshape(-1, d).sum(0)])
+    assert float((db_s - ref).norm() / ref.norm()) < 2e-2

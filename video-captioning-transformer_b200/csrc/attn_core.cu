@@ -353,6 +353,10 @@ extern "C" int vct_attn_fwd(const vct_attn_args* a, vct_stream_t stream) {
     return dispatch<float>(a, (cudaStream_t)stream, false);
 }
 
+namespace vct {
+int attn_bwd_tc(const vct_attn_args* m, cudaStream_t st);   // attn_fused.cu
+}
+
 extern "C" int vct_attn_bwd(const vct_attn_args* a, vct_stream_t stream) {
     if (int e = validate(a, "vct_attn_bwd")) return e;
     VCT_REQUIRE(a->q && a->k && a->v && a->d_o && a->dq && a->dk && a->dv, "vct_attn_bwd: null tensor");
@@ -360,6 +364,11 @@ extern "C" int vct_attn_bwd(const vct_attn_args* a, vct_stream_t stream) {
                 "vct_attn_bwd: gradient row strides must be multiples of 4 elements");
     VCT_REQUIRE(a->dbias == nullptr || (a->dbias_partials != nullptr && a->dbias_counters != nullptr),
                 "vct_attn_bwd: dbias needs dbias_partials and dbias_counters");
+    // bf16, sequences up to 32 queries / 64 keys: every contraction on tcgen05 (attn_fused.cu); otherwise the SIMT kernel
+    {
+        const int r = vct::attn_bwd_tc(a, (cudaStream_t)stream);
+        if (r <= 0) return r;
+    }
     if (a->dtype == VCT_BF16) return dispatch<__nv_bfloat16>(a, (cudaStream_t)stream, true);
     return dispatch<float>(a, (cudaStream_t)stream, true);
 }

@@ -405,6 +405,332 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     if (trace && threadIdx.x == 0) trace[109] = clock64();
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention backward on tcgen05.  One CTA per (group of NB sequences, head); Q, K, V, dO tiles of the head come in by
+// TMA (3-D boxes pad every sequence to LQP / LKP rows), then
+//   S  = Q K^T,  dP = dO V^T                      (K-major operands)         -> TMEM
+//   thread per query row: P (same masks, same exp2 softmax, same Philox keep mask as forward), dropped P and
+//   dS = P o (dP_dropped - rowsum(P o dP_dropped)) * scale, both as bf16 operand tiles (zero outside the sequence block)
+//   dQ = dS K          (A K-major, B = the K tile read MN-major)
+//   dK = dS^T Q,  dV = Pd^T dO   (A = the dS / Pd tile read MN-major, i.e. transposed for free)
+//   thread per row: dq / dk / dv rows -> bf16 global; per-CTA column sums -> in-projection bias gradient partials
+// A tile written with tile_addr() can be consumed K-major (rows = M/N index) or MN-major (rows = K index): the
+// SWIZZLE_128B pattern is the same, only the descriptor differs.
+// ---------------------------------------------------------------------------------------------------------------------
+struct BwdArgs {
+    int B, H, Lq, Lk;
+    const unsigned char* key_pad;
+    int causal;
+    float scale;
+    __nv_bfloat16* dq; long long dq_ld;
+    __nv_bfloat16* dk; long long dk_ld;
+    __nv_bfloat16* dv; long long dv_ld;
+    float drop_p; const unsigned long long* rng_state; unsigned int site;
+    float* dbias; float* dbias_part; unsigned int* dbias_cnt;
+};
+
+template <int DH, int LQP, int LKP>
+__global__ void __launch_bounds__(192, 1)
+attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmDO, BwdArgs a) {
+    constexpr int NB = (128 / LQP) < (128 / LKP) ? (128 / LQP) : (128 / LKP);
+    constexpr int NK = NB * LKP, NQ = NB * LQP;
+    constexpr int KSTEPS = DH / 16, NBLK = (DH + 63) / 64;
+    constexpr uint32_t kColS = 0, kColDP = 128, kColDQ = 256, kColDK = 352, kColDV = 0;
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) unsigned long long bars[4];      // 0 tiles landed, 1 S/dP done, 2 P/dS tiles written, 3 gradients done
+    __shared__ uint32_t tmem_base_slot;
+    __shared__ bool is_last;
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, b0 = blockIdx.x * NB;
+    const uint32_t smem0 = smem_u32(smem), bar0 = smem_u32(&bars[0]);
+    const uint32_t q_tile = smem0, k_tile = smem0 + kTile, v_tile = smem0 + 2 * kTile, do_tile = smem0 + 3 * kTile;
+    const uint32_t pd_tile = smem0 + 4 * kTile, ds_tile = smem0 + 5 * kTile;
+
+    if (warp == 0 && lane == 0) {
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmQ) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmK) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmV) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&tmDO) : "memory");
+        mbar_init(bar0 + 0, 1);
+        mbar_init(bar0 + 8, 1);
+        mbar_init(bar0 + 16, 128);
+        mbar_init(bar0 + 24, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    pdl_wait();
+
+    if (warp == 0) {
+        if (elect_one()) {
+            mbar_expect_tx(bar0 + 0, (uint32_t)NBLK * 2u * ((uint32_t)NQ + (uint32_t)NK) * 128u);
+#pragma unroll
+            for (int blk = 0; blk < NBLK; ++blk) {
+                tma_load_3d(q_tile + blk * kBlk, &tmQ, h * DH + blk * 64, 0, b0, bar0 + 0);
+                tma_load_3d(k_tile + blk * kBlk, &tmK, h * DH + blk * 64, 0, b0, bar0 + 0);
+                tma_load_3d(do_tile + blk * kBlk, &tmDO, h * DH + blk * 64, 0, b0, bar0 + 0);
+                tma_load_3d(v_tile + blk * kBlk, &tmV, h * DH + blk * 64, 0, b0, bar0 + 0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        const uint32_t base_idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BLOCK_M >> 4) << 24);
+        mbar_wait(bar0 + 0, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint32_t idesc_s = base_idesc | ((uint32_t)(NK >> 3) << 17);
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint32_t off = (uint32_t)(ks >> 2) * kBlk + (uint32_t)(ks & 3) * 32u;
+                umma_bf16(tmem_base + kColS, make_desc(q_tile + off, 16, 1024), make_desc(k_tile + off, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+            }
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ++ks) {
+                const uint32_t off = (uint32_t)(ks >> 2) * kBlk + (uint32_t)(ks & 3) * 32u;
+                umma_bf16(tmem_base + kColDP, make_desc(do_tile + off, 16, 1024), make_desc(v_tile + off, 16, 1024), idesc_s, ks > 0 ? 1u : 0u);
+            }
+            umma_commit(bar0 + 8);
+        }
+        __syncwarp();
+        mbar_wait(bar0 + 16, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (elect_one()) {
+            const uint32_t idesc_n = base_idesc | ((uint32_t)(DH >> 3) << 17);
+            // dQ = dS K : A K-major over the keys, B = K tile MN-major (k-rows = keys)
+#pragma unroll
+            for (int ks = 0; ks < NK / 16; ++ks) {
+                const uint32_t aoff = (uint32_t)(ks >> 2) * kBlk + (uint32_t)(ks & 3) * 32u;
+                umma_bf16(tmem_base + kColDQ, make_desc(ds_tile + aoff, 16, 1024), make_desc(k_tile + (uint32_t)ks * 2048u, kBlk, 1024),
+                          idesc_n | (1u << 16), ks > 0 ? 1u : 0u);
+            }
+            // dK = dS^T Q, dV = Pd^T dO : A = the tile read MN-major (k-rows = query rows), B = Q / dO tile MN-major.
+            // Only the NQ query rows the TMA boxes filled take part (rows beyond them hold stale shared memory).
+#pragma unroll
+            for (int ks = 0; ks < NQ / 16; ++ks)
+                umma_bf16(tmem_base + kColDK, make_desc(ds_tile + (uint32_t)ks * 2048u, kBlk, 1024), make_desc(q_tile + (uint32_t)ks * 2048u, kBlk, 1024),
+                          idesc_n | (1u << 15) | (1u << 16), ks > 0 ? 1u : 0u);
+#pragma unroll
+            for (int ks = 0; ks < NQ / 16; ++ks)
+                umma_bf16(tmem_base + kColDV, make_desc(pd_tile + (uint32_t)ks * 2048u, kBlk, 1024), make_desc(do_tile + (uint32_t)ks * 2048u, kBlk, 1024),
+                          idesc_n | (1u << 15) | (1u << 16), ks > 0 ? 1u : 0u);
+            umma_commit(bar0 + 24);
+        }
+        __syncwarp();
+    } else {
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const int j = r / LQP, i = r % LQP;
+        const int b = b0 + j;
+        const bool valid = j < NB && b < a.B && i < a.Lq;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const long long prow = ((long long)b * a.H + h) * a.Lq + i;
+        unsigned long long okmask = 0ull, keepmask = ~0ull;
+        if (valid) {
+            const unsigned char* pad_row = a.key_pad ? a.key_pad + (long long)b * a.Lk : nullptr;
+#pragma unroll
+            for (int kk = 0; kk < LKP; ++kk) {
+                const bool ok = kk < a.Lk && !(a.causal && kk > i) && !(pad_row != nullptr && pad_row[kk]);
+                okmask |= (unsigned long long)(ok ? 1u : 0u) << kk;
+            }
+        }
+        const Rng rng = make_rng(a.rng_state, a.drop_p);
+        if (rng.p > 0.f && valid) {
+            keepmask = 0ull;
+#pragma unroll
+            for (int g = 0; g < LKP / 8; ++g)
+                if (g * 8 < a.Lk)
+                    keepmask |= (unsigned long long)dropout_bits8(rng, a.site, (unsigned long long)prow * 8ull + (unsigned long long)g) << (8 * g);
+        }
+        mbar_wait(bar0 + 8, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        constexpr int SPW = 32 / LQP, NLD = SPW * LKP;
+        float sc[LKP], dp[LKP];
+        {
+            uint32_t rg[NLD], rd[NLD];
+            const int jq = q * SPW < NB ? q * SPW : 0;
+#pragma unroll
+            for (int c = 0; c < NLD / 16; ++c) {
+                tmem_ld16(lane_addr + kColS + (uint32_t)(jq * LKP) + 16u * c, rg + 16 * c);
+                tmem_ld16(lane_addr + kColDP + (uint32_t)(jq * LKP) + 16u * c, rd + 16 * c);
+            }
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            const bool upper = SPW == 2 && lane >= 16;
+#pragma unroll
+            for (int kk = 0; kk < LKP; ++kk) {
+                sc[kk] = __uint_as_float(SPW == 2 ? (upper ? rg[(NLD / 2 + kk) % NLD] : rg[kk]) : rg[kk]);
+                dp[kk] = __uint_as_float(SPW == 2 ? (upper ? rd[(NLD / 2 + kk) % NLD] : rd[kk]) : rd[kk]);
+            }
+        }
+        const float sl2 = a.scale * 1.4426950408889634f;
+        float mx = -INFINITY;
+#pragma unroll
+        for (int kk = 0; kk < LKP; ++kk) {
+            sc[kk] = ((okmask >> kk) & 1ull) ? sc[kk] * sl2 : -INFINITY;
+            mx = fmaxf(mx, sc[kk]);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < LKP; ++kk) {
+            sc[kk] = ((okmask >> kk) & 1ull) ? exp2f(sc[kk] - mx) : 0.f;
+            sum += sc[kk];
+        }
+        const float inv = sum > 0.f ? 1.f / sum : 0.f;
+        float dsum = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < LKP; ++kk) {
+            const float keep = ((keepmask >> kk) & 1ull) ? rng.inv_keep : 0.f;
+            sc[kk] *= inv;                                   // p
+            dp[kk] = ((okmask >> kk) & 1ull) ? dp[kk] * keep : 0.f;   // gradient wrt p (through the dropout)
+            dsum = fmaf(sc[kk], dp[kk], dsum);
+        }
+#pragma unroll
+        for (int kk = 0; kk < LKP; ++kk) {
+            const float keep = ((keepmask >> kk) & 1ull) ? rng.inv_keep : 0.f;
+            dp[kk] = sc[kk] * (dp[kk] - dsum) * a.scale;     // dS
+            sc[kk] *= keep;                                  // dropped probabilities
+        }
+#pragma unroll
+        for (int cidx = 0; cidx < NK / 8; ++cidx) {
+            sts128(tile_addr(pd_tile, r, cidx), 0u, 0u, 0u, 0u);
+            sts128(tile_addr(ds_tile, r, cidx), 0u, 0u, 0u, 0u);
+        }
+        if (valid) {
+#pragma unroll
+            for (int g = 0; g < LKP / 8; ++g) {
+                sts128(tile_addr(pd_tile, r, j * (LKP / 8) + g), pack_bf16(sc[g * 8], sc[g * 8 + 1]), pack_bf16(sc[g * 8 + 2], sc[g * 8 + 3]),
+                       pack_bf16(sc[g * 8 + 4], sc[g * 8 + 5]), pack_bf16(sc[g * 8 + 6], sc[g * 8 + 7]));
+                sts128(tile_addr(ds_tile, r, j * (LKP / 8) + g), pack_bf16(dp[g * 8], dp[g * 8 + 1]), pack_bf16(dp[g * 8 + 2], dp[g * 8 + 3]),
+                       pack_bf16(dp[g * 8 + 4], dp[g * 8 + 5]), pack_bf16(dp[g * 8 + 6], dp[g * 8 + 7]));
+            }
+        }
+        fence_async_smem();
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        mbar_arrive(bar0 + 16);
+        // ---- gradients: thread = query row for dq, = key row for dk / dv ----
+        mbar_wait(bar0 + 24, 0);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const int jk = r / LKP, kk = r % LKP;
+        const int bk = b0 + jk;
+        const bool kvalid = r < NK && bk < a.B && kk < a.Lk;
+        __nv_bfloat16* rows[3] = {
+            valid ? a.dq + ((long long)b * a.Lq + i) * a.dq_ld + h * DH : nullptr,
+            kvalid ? a.dk + ((long long)bk * a.Lk + kk) * a.dk_ld + h * DH : nullptr,
+            kvalid ? a.dv + ((long long)bk * a.Lk + kk) * a.dv_ld + h * DH : nullptr};
+        const uint32_t cols[3] = {kColDQ, kColDK, kColDV};
+        float* stagef = reinterpret_cast<float*>(smem);      // [128][DH + 1] fp32 column-sum staging (tiles are dead by now)
+        const int t = threadIdx.x - 64;
+        const int Hd = a.H * DH;
+#pragma unroll 1
+        for (int sec = 0; sec < 3; ++sec) {
+            const bool rowok = sec == 0 ? valid : kvalid;
+#pragma unroll 1
+            for (int c32 = 0; c32 < DH / 32; ++c32) {
+                uint32_t rg[32];
+                tmem_ld16(lane_addr + cols[sec] + (uint32_t)(c32 * 32), rg);
+                tmem_ld16(lane_addr + cols[sec] + (uint32_t)(c32 * 32 + 16), rg + 16);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (rows[sec]) {
+#pragma unroll
+                    for (int ch = 0; ch < 4; ++ch) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) w[u] = pack_bf16(__uint_as_float(rg[ch * 8 + 2 * u]), __uint_as_float(rg[ch * 8 + 2 * u + 1]));
+                        *reinterpret_cast<uint4*>(rows[sec] + c32 * 32 + ch * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                if (a.dbias) {
+#pragma unroll
+                    for (int u = 0; u < 32; ++u) stagef[r * (DH + 1) + c32 * 32 + u] = rowok ? __uint_as_float(rg[u]) : 0.f;
+                }
+            }
+            if (a.dbias) {
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (t < DH) {
+                    float s = 0.f;
+#pragma unroll 8
+                    for (int rr = 0; rr < 128; ++rr) s += stagef[rr * (DH + 1) + t];
+                    a.dbias_part[(long long)blockIdx.x * 3 * Hd + sec * Hd + h * DH + t] = s;
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+            }
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (a.dbias) {
+            __threadfence();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (t == 0) {
+                const unsigned int prev = atomicAdd(a.dbias_cnt + h, 1u);
+                is_last = (prev == gridDim.x - 1);
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (is_last) {
+                __threadfence();
+                for (int c = t; c < 3 * DH; c += 128) {
+                    const long long col = (long long)(c / DH) * Hd + h * DH + (c % DH);
+                    float s = 0.f;
+                    for (unsigned int g = 0; g < gridDim.x; ++g) s += __ldcg(a.dbias_part + (long long)g * 3 * Hd + col);
+                    a.dbias[col] = s;
+                }
+                if (t == 0) a.dbias_cnt[h] = 0u;
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+template <int DH, int LQP, int LKP>
+int launch_bwd_tc(const vct_attn_args* m, cudaStream_t st) {
+    constexpr int NB = (128 / LQP) < (128 / LKP) ? (128 / LQP) : (128 / LKP);
+    constexpr int smem = 6 * (int)kTile + 1024;
+    static_assert(128 * (DH + 1) * 4 <= 6 * (int)kTile, "column-sum staging must fit in the dead tiles");
+    const int d = m->H * DH;
+    CUtensorMap tmQ, tmK, tmV, tmDO;
+    auto make = [&](const void* ptr, long long ld, long long bs, int L, int LP, CUtensorMap* out) {
+        const unsigned long long dims[3] = {(unsigned long long)d, (unsigned long long)L, (unsigned long long)m->B};
+        const unsigned long long strides[2] = {(unsigned long long)ld * 2ull, (unsigned long long)bs * 2ull};
+        const unsigned int box[3] = {64u, (unsigned)LP, (unsigned)NB};
+        return get_tensor_map_3d(ptr, dims, strides, box, out);
+    };
+    const long long q_bs = m->q_bs ? m->q_bs : (long long)m->Lq * m->q_ld, k_bs = m->k_bs ? m->k_bs : (long long)m->Lk * m->k_ld;
+    const long long v_bs = m->v_bs ? m->v_bs : (long long)m->Lk * m->v_ld, do_bs = m->do_bs ? m->do_bs : (long long)m->Lq * m->do_ld;
+    if (int e = make(m->q, m->q_ld, q_bs, m->Lq, LQP, &tmQ)) return e;
+    if (int e = make(m->k, m->k_ld, k_bs, m->Lk, LKP, &tmK)) return e;
+    if (int e = make(m->v, m->v_ld, v_bs, m->Lk, LKP, &tmV)) return e;
+    if (int e = make(m->d_o, m->do_ld, do_bs, m->Lq, LQP, &tmDO)) return e;
+    auto kern = attn_bwd_tc_kernel<DH, LQP, LKP>;
+    static bool once = false;
+    if (!once) {
+        VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        once = true;
+    }
+    BwdArgs a;
+    a.B = m->B; a.H = m->H; a.Lq = m->Lq; a.Lk = m->Lk;
+    a.key_pad = m->key_pad; a.causal = m->causal; a.scale = m->scale;
+    a.dq = (__nv_bfloat16*)m->dq; a.dq_ld = m->dq_ld;
+    a.dk = (__nv_bfloat16*)m->dk; a.dk_ld = m->dk_ld;
+    a.dv = (__nv_bfloat16*)m->dv; a.dv_ld = m->dv_ld;
+    a.drop_p = m->drop_p; a.rng_state = m->rng_state; a.site = m->site;
+    a.dbias = m->dbias; a.dbias_part = m->dbias_partials; a.dbias_cnt = m->dbias_counters;
+    dim3 grid((m->B + NB - 1) / NB, m->H);
+    vct::launch(kern, grid, dim3(192), smem, st, tmQ, tmK, tmV, tmDO, a);
+    return check_launch("vct_attn_bwd(tcgen05)");
+}
+
 bool fused_enabled() {
     static const bool on = [] {
         const char* e = getenv("VCT_FUSED_ATTN");
@@ -482,6 +808,23 @@ int attn_fused_self(const vct_mha_args* m, int causal, cudaStream_t st) {
     const int dh = m->d / m->H;
     if (dh == 96) return m->L <= 16 ? launch_fused<96, 16, 16, false>(m, causal, st) : launch_fused<96, 32, 32, false>(m, causal, st);
     if (dh == 64) return m->L <= 16 ? launch_fused<64, 16, 16, false>(m, causal, st) : launch_fused<64, 32, 32, false>(m, causal, st);
+    return 1;
+}
+
+// attention backward on the tensor cores: 0 = launched, > 0 = shape not covered (caller runs the SIMT kernel), < 0 = error
+int attn_bwd_tc(const vct_attn_args* m, cudaStream_t st) {
+    static const bool on = [] { const char* e = getenv("VCT_ATTN_BWD_TC"); return e == nullptr || e[0] != '0'; }();
+    if (!on || m->dtype != VCT_BF16 || m->Lq > 32 || m->Lk > 64 || (m->causal && m->Lq != m->Lk)) return 1;
+    if (m->dq_bs || m->dk_bs || m->dv_bs) return 1;                                  // gradients are written densely
+    auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    if (!al(m->q) || !al(m->k) || !al(m->v) || !al(m->d_o) || !al(m->dq) || !al(m->dk) || !al(m->dv)) return 1;
+    if (m->q_ld % 8 || m->k_ld % 8 || m->v_ld % 8 || m->do_ld % 8 || m->dq_ld % 8 || m->dk_ld % 8 || m->dv_ld % 8) return 1;
+    if (m->q_bs % 8 || m->k_bs % 8 || m->v_bs % 8 || m->do_bs % 8) return 1;
+    const int lqp = m->Lq <= 16 ? 16 : 32, lkp = m->Lk <= 16 ? 16 : (m->Lk <= 32 ? 32 : 64);
+#define VCT_BWD_CASE(DH, A, B) if (m->dh == DH && lqp == A && lkp == B) return launch_bwd_tc<DH, A, B>(m, st);
+    VCT_BWD_CASE(96, 16, 16) VCT_BWD_CASE(96, 32, 32) VCT_BWD_CASE(96, 32, 16) VCT_BWD_CASE(96, 32, 64)
+    VCT_BWD_CASE(64, 16, 16) VCT_BWD_CASE(64, 32, 32) VCT_BWD_CASE(64, 32, 16) VCT_BWD_CASE(64, 32, 64)
+#undef VCT_BWD_CASE
     return 1;
 }
 
