@@ -191,6 +191,49 @@ def gemm_flops(a):
     return 2.0 * g.M * g.N * g.K
 
 
+def attention_rooflines(names, med, calls, peaks):
+    """Roofline of the fused attention kernels (BASELINE metric: "attn kernel HBM GB/s vs peak"; SURVEY section 8d
+    formulas, bf16 = 2 bytes): per flavour the median per-launch device time of the step's launches, the kernel's
+    ALGORITHMIC bytes and FLOPs, both bounds, and the fraction of the tighter (larger ideal time) one.
+      self fwd : reads x, W_in[3d,d], b; writes o and the saved q|k|v rows;   FLOPs = B (6 L d^2 + 4 L^2 d)
+      cross fwd: reads x, pre-projected K|V of the memory, W_q, b_q; writes o, q; FLOPs = B (2 S d^2 + 4 S M d)
+      bwd      : reads q, k, v, dO; writes dq, dk, dv;                         FLOPs = 10 B Lq Lk d"""
+    groups = {}
+    for n, m, a in zip(names, med, calls):
+        if n.startswith(("vct_attn_enc_self_fwd", "vct_attn_dec_self_fwd")):
+            o = a[0]._obj
+            B, L, d = o.B, o.L, o.d
+            by = 2.0 * (B * L * d + 3 * d * d + 3 * d + B * L * d + 3 * B * L * d) + B * L
+            fl = B * (6.0 * L * d * d + 4.0 * L * L * d)
+            key = n.split(":")[0]
+        elif n.startswith("vct_attn_dec_cross_fwd"):
+            o = a[0]._obj
+            B, S, M, d = o.B, o.L, o.Lk, o.d
+            by = 2.0 * (B * S * d + B * M * 2 * d + d * d + d + 2 * B * S * d)
+            fl = B * (2.0 * S * d * d + 4.0 * S * M * d)
+            key = "vct_attn_dec_cross_fwd"
+        elif n.startswith("vct_attn_bwd"):
+            o = a[0]._obj
+            B, Lq, Lk, d = o.B, o.Lq, o.Lk, o.H * o.dh
+            by = 2.0 * B * d * (3 * Lq + 4 * Lk)
+            fl = 10.0 * B * Lq * Lk * d
+            key = "vct_attn_bwd:" + ("cross" if Lq != Lk else ("enc_self" if "enc" in n else "dec_self"))
+        else:
+            continue
+        groups.setdefault(key, []).append((m, by, fl))
+    out = []
+    for key, rows in groups.items():
+        ms = statistics.median(r[0] for r in rows)
+        by, fl = rows[0][1], rows[0][2]
+        t_hbm, t_tc = by / (peaks["hbm_gbs"] * 1e9), fl / (peaks["tflops"] * 1e12)
+        bound = "hbm" if t_hbm >= t_tc else "tensor"
+        out.append({"kernel": key, "launches_per_step": len(rows), "ms": round(ms, 5), "bytes": by, "flops": fl,
+                    "achieved_gbs": by / (ms * 1e-3) / 1e9, "achieved_tflops": fl / (ms * 1e-3) / 1e12,
+                    "ideal_us_hbm": t_hbm * 1e6, "ideal_us_tensor": t_tc * 1e6, "bound": bound,
+                    "frac": max(t_hbm, t_tc) / (ms * 1e-3)})
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -290,7 +333,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     h2d = x.numel() * 4 + vm.numel() + tok.numel() * 8
     # ---- roofline of the dominant kernel (rank 0): per-launch CUDA-event times of one eager step ------
-    roofline, breakdown = None, None
+    roofline, breakdown, attn_roof = None, None, None
     if rank == 0:
         ws = eng.workspace(B, T, S1 - 1, True)
         plans = [eng.plan_forward(ws, fused_grad=True, part="all"), eng.plan_backward(ws, sce_first=False, part="all")]
@@ -311,6 +354,7 @@ def main():
         groups["vct_adam"] = adam_ms
         breakdown = {k: round(v, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1])}
         peaks = measured_peaks()
+        attn_roof = attention_rooflines(names, med, calls, peaks)
         top = max(range(len(names)), key=lambda i: med[i])
         if adam_ms >= med[top]:
             nbytes = a.numel * (16 + 12 + (2 if eng.precision == "bf16" else 0))
@@ -362,7 +406,7 @@ def main():
                 "e2e": {"value": B * world * args.steps / float(e2e_s.item()), "unit": "captions/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
                 "gpu_launches": launches, "loss": final_loss, "clocks": clocks, "roofline": roofline,
-                "cpu_baseline": cpu, "kernel_ms": breakdown, "phase_ms": phase_ms}
+                "attn_rooflines": attn_roof, "cpu_baseline": cpu, "kernel_ms": breakdown, "phase_ms": phase_ms}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -17,6 +17,14 @@ for r in csv.DictReader(lines):
     name = re.sub(r"\(.*", "", r["Kernel Name"])
     name = re.sub(r"<unnamed>::|\(anonymous namespace\)::|void ", "", name)
     rows.append((name, ns))
+# optional window: keep the launches of train steps [first, last) counted by step_tick_kernel (one per step)
+if len(sys.argv) >= 4:
+    first, last = int(sys.argv[2]), int(sys.argv[3])
+    ticks = [i for i, (n, _) in enumerate(rows) if "step_tick_kernel" in n]
+    lo = ticks[first] if first < len(ticks) else 0
+    hi = ticks[last] if last < len(ticks) else len(rows)
+    rows = rows[lo:hi]
+    print(f"window: train steps {first}..{last - 1} ({last - first} steps)")
 tot = sum(ns for _, ns in rows)
 agg = defaultdict(lambda: [0, 0.0])
 for n, ns in rows:
