@@ -59,6 +59,9 @@ int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, vct_stream_t
  *   act = VCT_ACT_NONE
  *   act = VCT_ACT_GELU_FWD : C  = z (pre-activation), C2 = dropout(gelu(z))   [FFN linear1]
  *   act = VCT_ACT_GELU_BWD : C  = acc * gelu'(aux[m,n]) * dropmask[m,n]        [FFN backward]
+ *   act = VCT_ACT_GELU_FWD_F / VCT_ACT_MUL_AUX: the same pair with the backward factor gelu'(z) * dropmask computed
+ *         once in the forward epilogue (where z, the CDF and the density are at hand) and stored instead of z, so that
+ *         the backward epilogue is one multiply (the training plans use this pair)
  * Replaces nn.Linear / F.linear calls: model/MMEncoder.py:246 (unify), model/CapDecoder.py:55
  * (generator), torch/nn/functional.py _in_projection_packed + out_proj inside
  * multi_head_attention_forward, torch/nn/modules/transformer.py:980-982,1197-1199 (FFN), and the
@@ -68,6 +71,8 @@ int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, vct_stream_t
 #define VCT_ACT_NONE 0
 #define VCT_ACT_GELU_FWD 1
 #define VCT_ACT_GELU_BWD 2
+#define VCT_ACT_GELU_FWD_F 3 /* C = f = gelu'(z) * dropmask (the factor backward needs), C2 = dropout(gelu(z)) */
+#define VCT_ACT_MUL_AUX 4    /* C = acc * aux[m,n] (+ addend): FFN backward with the saved factor f, no erf / RNG */
 #define VCT_GEMM_SIMT 0
 #define VCT_GEMM_TCGEN05 1
 

@@ -582,3 +582,30 @@ def test_attention_backward_tcgen05_matches_simt(lib, B, H, Lq, Lk, dh, causal):
     # the bias gradient is the column sum of the (unrounded) gradients
     ref = torch.cat([dq_s.reshape(-1, d).sum(0), dk_s.reshape(-1, d).sum(0), dv_s.reshape(-1, d).sum(0)])
     assert float((db_s - ref).norm() / ref.norm()) < 2e-2
+
+
+@pytest.mark.parametrize("impl", [L.GEMM_SIMT, L.GEMM_TCGEN05])
+def test_gemm_saved_gelu_factor_pair_matches_recompute_pair(lib, impl):
+    """ACT_GELU_FWD_F stores f = gelu'(z) * dropmask in the forward epilogue and ACT_MUL_AUX multiplies by it in backward
+    (what the training plans use); the result must equal the ACT_GELU_FWD / ACT_GELU_BWD pair that recomputes gelu'
+    and the mask from z."""
+    M, N, K = 1280, 2048, 256
+    g = torch.Generator().manual_seed(5)
+    A = (torch.randn(M, K, generator=g) * 0.2).to(DEV, torch.bfloat16)
+    B = torch.randn(N, K, generator=g).to(DEV, torch.bfloat16)
+    bias = torch.randn(N, generator=g).to(DEV)
+    G = (torch.randn(M, K, generator=g) * 0.2).to(DEV, torch.bfloat16)          # upstream operand of the backward GEMM
+    W = torch.randn(N, K, generator=g).to(DEV, torch.bfloat16)
+    rng = torch.tensor([11, 4], dtype=torch.int64, device=DEV)
+    kw = dict(bias=bias, c2_dtype=L.BF16, drop_p=0.3, rng_state=rng, site=9, c_dtype=L.BF16, impl=impl)
+    z, h1 = run_gemm(lib, A, B, 0, 0, M, N, K, act=L.ACT_GELU_FWD, **kw)
+    f, h2 = run_gemm(lib, A, B, 0, 0, M, N, K, act=L.ACT_GELU_FWD_F, **kw)
+    torch.testing.assert_close(h2.float(), h1.float(), rtol=1e-2, atol=1e-2)
+    zz = z.float().clone().requires_grad_(True)
+    torch.nn.functional.gelu(zz).sum().backward()
+    keep = (h1.float() != 0) | (z.float().abs() < 1e-3)                          # dropped <=> h == 0 (up to z ~ 0)
+    torch.testing.assert_close(f.float() * keep, zz.grad / 0.7 * keep * (f.float() != 0), rtol=3e-2, atol=3e-2)
+    d1, _ = run_gemm(lib, G, W, 0, 0, M, N, K, act=L.ACT_GELU_BWD, aux=z, drop_p=0.3, rng_state=rng, site=9, c_dtype=L.BF16, impl=impl)
+    d2, _ = run_gemm(lib, G, W, 0, 0, M, N, K, act=L.ACT_MUL_AUX, aux=f, c_dtype=L.BF16, impl=impl)
+    assert torch.isfinite(d2.float()).all()
+    assert float((d2.float() - d1.float()).norm() / d1.float().norm()) < 1e-2

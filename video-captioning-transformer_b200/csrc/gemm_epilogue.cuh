@@ -69,13 +69,14 @@ __device__ __noinline__ void epilogue_scalar(const Epilogue& e, const Rng& rng, 
         if (e.bias) v += e.bias[nn];
         if (e.row_table) v += e.row_table[(long long)(m % e.row_period) * e.N + nn];
         float sc = 1.f;
-        if (ACT != VCT_ACT_NONE) sc = dropout_scale1(rng, e.site, (unsigned long long)m * (unsigned long long)e.N + nn);
-        if (ACT == VCT_ACT_GELU_FWD) {
-            store1(e.C, e.c_dtype, (long long)m * e.ldc + nn, v);
+        if (ACT != VCT_ACT_NONE && ACT != VCT_ACT_MUL_AUX) sc = dropout_scale1(rng, e.site, (unsigned long long)m * (unsigned long long)e.N + nn);
+        if (ACT == VCT_ACT_GELU_FWD || ACT == VCT_ACT_GELU_FWD_F) {
+            store1(e.C, e.c_dtype, (long long)m * e.ldc + nn, ACT == VCT_ACT_GELU_FWD ? v : dgelu_f(v) * sc);
             if (e.C2) store1(e.C2, e.c2_dtype, (long long)m * e.ldc2 + nn, gelu_f(v) * sc);
             continue;
         }
         if (ACT == VCT_ACT_GELU_BWD) v *= dgelu_f(load1(e.aux, e.aux_dtype, (long long)m * e.ld_aux + nn)) * sc;
+        if (ACT == VCT_ACT_MUL_AUX) v *= load1(e.aux, e.aux_dtype, (long long)m * e.ld_aux + nn);
         if (e.addend) v += e.addend[(long long)m * e.ld_addend + nn];
         store1(e.C, e.c_dtype, (long long)m * e.ldc + nn, v);
         if (e.C2) store1(e.C2, e.c2_dtype, (long long)m * e.ldc2 + nn, v);
@@ -130,11 +131,14 @@ __device__ __forceinline__ void epilogue_store8(const Epilogue& e, const Rng& rn
         for (int q = 0; q < 8; ++q) v[q] += t[q];
     }
     float sc[8];
-    dropout_scale8(rng, e.site, ((unsigned long long)m * (unsigned long long)e.N + (unsigned long long)n) >> 3, sc);
-    if (ACT == VCT_ACT_GELU_FWD) {
+    if (ACT != VCT_ACT_MUL_AUX) dropout_scale8(rng, e.site, ((unsigned long long)m * (unsigned long long)e.N + (unsigned long long)n) >> 3, sc);
+    if (ACT == VCT_ACT_GELU_FWD || ACT == VCT_ACT_GELU_FWD_F) {
         const long long o = (long long)m * e.ldc + n;
-        if (e.c_dtype == VCT_BF16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
-        else st8(reinterpret_cast<float*>(e.C) + o, v);
+        float f[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) f[q] = ACT == VCT_ACT_GELU_FWD ? v[q] : dgelu_f(v[q]) * sc[q];
+        if (e.c_dtype == VCT_BF16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, f);
+        else st8(reinterpret_cast<float*>(e.C) + o, f);
         if (e.C2) {
             float h[8];
 #pragma unroll
@@ -151,7 +155,7 @@ __device__ __forceinline__ void epilogue_store8(const Epilogue& e, const Rng& rn
         if (e.aux_dtype == VCT_BF16) ld8(reinterpret_cast<const __nv_bfloat16*>(e.aux) + ao, z);
         else ld8(reinterpret_cast<const float*>(e.aux) + ao, z);
 #pragma unroll
-        for (int q = 0; q < 8; ++q) v[q] *= dgelu_f(z[q]) * sc[q];
+        for (int q = 0; q < 8; ++q) v[q] *= ACT == VCT_ACT_MUL_AUX ? z[q] : dgelu_f(z[q]) * sc[q];
     }
     if (e.addend) {
         float ad[8];
@@ -308,8 +312,10 @@ __device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& 
     // two rows per pass; the global operands of the NEXT pass (z and the addend of the GELU backward) are requested before
     // the math of the current one, so that their L2 latency is hidden behind ~500 instructions of work
     float z[2][8], ad[2][8], zn[2][8], adn[2][8];
+    constexpr bool kBwd = ACT == VCT_ACT_GELU_BWD || ACT == VCT_ACT_MUL_AUX;
+    constexpr bool kFwd = ACT == VCT_ACT_GELU_FWD || ACT == VCT_ACT_GELU_FWD_F;
     auto fetch = [&](int r0, float (&zz)[2][8], float (&aa)[2][8]) {
-        if (ACT != VCT_ACT_GELU_BWD) return;
+        if (!kBwd) return;
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
             const int rq = r0 + u * RSTEP;
@@ -338,22 +344,27 @@ __device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& 
             float v[8] = {a[u][0].x + b[0], a[u][0].y + b[1], a[u][0].z + b[2], a[u][0].w + b[3],
                           a[u][1].x + b[4], a[u][1].y + b[5], a[u][1].z + b[6], a[u][1].w + b[7]};
             float sc[8];
-            dropout_scale8(rng, site, ((unsigned long long)m * N + (unsigned long long)n) >> 3, sc);
-            if (ACT == VCT_ACT_GELU_FWD) {
-                const long long o = m * ldc + n;
-                if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, v);
-                else st8(reinterpret_cast<float*>(e.C) + o, v);
-                if (e.C2) {
-                    float h[8];
+            if (ACT != VCT_ACT_MUL_AUX) dropout_scale8(rng, site, ((unsigned long long)m * N + (unsigned long long)n) >> 3, sc);
+            if (kFwd) {
+                float hh[8], ff[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) h[q] = gelu_fast(v[q]) * sc[q];
+                for (int q = 0; q < 8; ++q) {
+                    float cdf, pdf;
+                    normal_cdf_pdf_fast(v[q], cdf, pdf);
+                    hh[q] = v[q] * cdf * sc[q];
+                    ff[q] = ACT == VCT_ACT_GELU_FWD ? v[q] : fmaf(v[q], pdf, cdf) * sc[q];
+                }
+                const long long o = m * ldc + n;
+                if (c_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C) + o, ff);
+                else st8(reinterpret_cast<float*>(e.C) + o, ff);
+                if (e.C2) {
                     const long long o2 = m * ldc2 + n;
-                    if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, h);
-                    else st8(reinterpret_cast<float*>(e.C2) + o2, h);
+                    if (c2_bf16) st8(reinterpret_cast<__nv_bfloat16*>(e.C2) + o2, hh);
+                    else st8(reinterpret_cast<float*>(e.C2) + o2, hh);
                 }
             } else {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[q] *= dgelu_fast(z[u][q]) * sc[q];
+                for (int q = 0; q < 8; ++q) v[q] *= ACT == VCT_ACT_MUL_AUX ? z[u][q] : dgelu_fast(z[u][q]) * sc[q];
                 if (e.addend) {
 #pragma unroll
                     for (int q = 0; q < 8; ++q) v[q] += ad[u][q];
@@ -368,7 +379,7 @@ __device__ __forceinline__ void epilogue_tile_act(const Epilogue& e, const Rng& 
                 }
             }
         }
-        if (ACT == VCT_ACT_GELU_BWD) {
+        if (kBwd) {
 #pragma unroll
             for (int u = 0; u < 2; ++u)
 #pragma unroll

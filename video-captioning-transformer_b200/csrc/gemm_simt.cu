@@ -122,6 +122,8 @@ int launch_simt(const vct_gemm_args* a, cudaStream_t st) {
 #define GO_ACT(AT, BT)                                      \
     if (a->act == VCT_ACT_GELU_FWD) GO(AT, BT, VCT_ACT_GELU_FWD);   \
     else if (a->act == VCT_ACT_GELU_BWD) GO(AT, BT, VCT_ACT_GELU_BWD); \
+    else if (a->act == VCT_ACT_GELU_FWD_F) GO(AT, BT, VCT_ACT_GELU_FWD_F); \
+    else if (a->act == VCT_ACT_MUL_AUX) GO(AT, BT, VCT_ACT_MUL_AUX); \
     else GO(AT, BT, VCT_ACT_NONE)
     if (!a->a_trans && !a->b_trans) { GO_ACT(false, false); }
     else if (!a->a_trans && a->b_trans) { GO_ACT(false, true); }
@@ -167,7 +169,9 @@ extern "C" int vct_gemm(const vct_gemm_args* a, vct_stream_t stream) {
                 "vct_gemm: leading dimension too small");
     VCT_REQUIRE((reinterpret_cast<uintptr_t>(a->C) & 15) == 0 && (a->C2 == nullptr || (reinterpret_cast<uintptr_t>(a->C2) & 15) == 0),
                 "vct_gemm: outputs must be 16-byte aligned");
-    VCT_REQUIRE(a->act != VCT_ACT_GELU_BWD || a->aux != nullptr, "vct_gemm: GELU_BWD needs aux (the pre-activation)");
+    VCT_REQUIRE(a->act >= VCT_ACT_NONE && a->act <= VCT_ACT_MUL_AUX, "vct_gemm: unknown activation %d", a->act);
+    VCT_REQUIRE((a->act != VCT_ACT_GELU_BWD && a->act != VCT_ACT_MUL_AUX) || a->aux != nullptr,
+                "vct_gemm: GELU_BWD / MUL_AUX need aux (the pre-activation / the saved factor)");
     VCT_REQUIRE(a->act == VCT_ACT_NONE || !a->a_trans, "vct_gemm: activation epilogues are built for a_trans = 0 only");
     VCT_REQUIRE(a->row_table == nullptr || a->row_period > 0, "vct_gemm: row_table needs row_period > 0");
     VCT_REQUIRE(a->addend == nullptr || a->ld_addend >= a->N, "vct_gemm: ld_addend too small");

@@ -492,9 +492,15 @@ template <int BLOCK_N>
 int dispatch_major(const vct_gemm_args* a, const CUtensorMap& tmA, const CUtensorMap& tmB, int splits, bool low, cudaStream_t st) {
     // activation epilogues exist where the path uses them: GELU forward on x W1^T (K-major, K-major) and GELU
     // backward on dY W2 (K-major, MN-major); everything else carries the small plain epilogue
-    if (a->act == VCT_ACT_GELU_FWD) {
+    if (a->act == VCT_ACT_GELU_FWD || a->act == VCT_ACT_GELU_FWD_F) {
         VCT_REQUIRE(!a->a_trans && !a->b_trans, "vct_gemm(tcgen05): GELU_FWD is built for a_trans = b_trans = 0");
+        if (a->act == VCT_ACT_GELU_FWD_F) return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_FWD_F>(a, tmA, tmB, splits, low, st);
         return launch_tile<BLOCK_N, false, false, VCT_ACT_GELU_FWD>(a, tmA, tmB, splits, low, st);
+    }
+    if (a->act == VCT_ACT_MUL_AUX) {
+        VCT_REQUIRE(!a->a_trans, "vct_gemm(tcgen05): MUL_AUX is built for a_trans = 0");
+        if (a->b_trans) return launch_tile<BLOCK_N, false, true, VCT_ACT_MUL_AUX>(a, tmA, tmB, splits, low, st);
+        return launch_tile<BLOCK_N, false, false, VCT_ACT_MUL_AUX>(a, tmA, tmB, splits, low, st);
     }
     if (a->act == VCT_ACT_GELU_BWD) {
         VCT_REQUIRE(!a->a_trans, "vct_gemm(tcgen05): GELU_BWD is built for a_trans = 0");

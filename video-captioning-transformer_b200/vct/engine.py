@@ -473,7 +473,7 @@ class CaptionEngine:
                          e.stats[0].data_ptr(), e.stats[1].data_ptr(), Re, p_drop, _enc_site(l, 1))
             self._gemm(plan, f"enc{l}.linear1", Re, D.F_enc, d, e.x1_c.data_ptr(), d, 0, self._w(pre + "linear1.weight"), d, 0,
                        e.z.data_ptr(), cd, D.F_enc, bias=self._p(pre + "linear1.bias"), C2=e.h.data_ptr(), c2_dtype=cd,
-                       ldc2=D.F_enc, act=L.ACT_GELU_FWD, drop_p=p_drop, site=_enc_site(l, 2))
+                       ldc2=D.F_enc, act=L.ACT_GELU_FWD_F if ws.training else L.ACT_GELU_FWD, drop_p=p_drop, site=_enc_site(l, 2))
             self._gemm(plan, f"enc{l}.linear2", Re, d, D.F_enc, e.h.data_ptr(), D.F_enc, 0, self._w(pre + "linear2.weight"),
                        D.F_enc, 0, e.s2.data_ptr(), F32, d, bias=self._p(pre + "linear2.bias"))
             self._ln_fwd(plan, f"enc{l}.norm2", e.x1.data_ptr(), e.s2.data_ptr(), pre + "norm2.weight", pre + "norm2.bias",
@@ -539,7 +539,7 @@ class CaptionEngine:
                          e.stats[2].data_ptr(), e.stats[3].data_ptr(), Rd, p_drop, _dec_site(l, 3))
             self._gemm(plan, f"dec{l}.linear1", Rd, D.F_dec, d, e.x2_c.data_ptr(), d, 0, self._w(pre + "linear1.weight"), d, 0,
                        e.z.data_ptr(), cd, D.F_dec, bias=self._p(pre + "linear1.bias"), C2=e.h.data_ptr(), c2_dtype=cd,
-                       ldc2=D.F_dec, act=L.ACT_GELU_FWD, drop_p=p_drop, site=_dec_site(l, 4))
+                       ldc2=D.F_dec, act=L.ACT_GELU_FWD_F if ws.training else L.ACT_GELU_FWD, drop_p=p_drop, site=_dec_site(l, 4))
             self._gemm(plan, f"dec{l}.linear2", Rd, d, D.F_dec, e.h.data_ptr(), D.F_dec, 0, self._w(pre + "linear2.weight"),
                        D.F_dec, 0, e.s3.data_ptr(), F32, d, bias=self._p(pre + "linear2.bias"))
             self._ln_fwd(plan, f"dec{l}.norm3", e.x2.data_ptr(), e.s3.data_ptr(), pre + "norm3.weight", pre + "norm3.bias",
@@ -659,7 +659,7 @@ class CaptionEngine:
                 self._gemm(p, f"dec{l}.linear2.wgrad", d, D.F_dec, Rd, g_r3, d, 1, e.h.data_ptr(), D.F_dec, 1,
                            self._g(pre + "linear2.weight"), F32, D.F_dec)
             self._gemm(p, f"dec{l}.linear2.dgrad", Rd, D.F_dec, d, g_r3, d, 0, self._w(pre + "linear2.weight"),
-                       D.F_dec, 1, g_z, cd, D.F_dec, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_dec,
+                       D.F_dec, 1, g_z, cd, D.F_dec, act=L.ACT_MUL_AUX, aux=e.z.data_ptr(), ld_aux=D.F_dec,
                        drop_p=pd, site=_dec_site(l, 4))
             with side(p):
                 self._gemm(p, f"dec{l}.linear1.wgrad", D.F_dec, d, Rd, g_z, D.F_dec, 1, e.x2_c.data_ptr(), d, 1,
@@ -749,7 +749,7 @@ class CaptionEngine:
                 self._gemm(p, f"enc{l}.linear2.wgrad", d, D.F_enc, Re, g_r2, d, 1, e.h.data_ptr(), D.F_enc, 1,
                            self._g(pre + "linear2.weight"), F32, D.F_enc)
             self._gemm(p, f"enc{l}.linear2.dgrad", Re, D.F_enc, d, g_r2, d, 0, self._w(pre + "linear2.weight"),
-                       D.F_enc, 1, g_z, cd, D.F_enc, act=L.ACT_GELU_BWD, aux=e.z.data_ptr(), ld_aux=D.F_enc,
+                       D.F_enc, 1, g_z, cd, D.F_enc, act=L.ACT_MUL_AUX, aux=e.z.data_ptr(), ld_aux=D.F_enc,
                        drop_p=pd, site=_enc_site(l, 2))
             with side(p):
                 self._gemm(p, f"enc{l}.linear1.wgrad", D.F_enc, d, Re, g_z, D.F_enc, 1, e.x1_c.data_ptr(), d, 1,

@@ -13,7 +13,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(os.path.dirname(HERE), "libvct_b200.so")
 
 F32, BF16 = 0, 1
-ACT_NONE, ACT_GELU_FWD, ACT_GELU_BWD = 0, 1, 2
+ACT_NONE, ACT_GELU_FWD, ACT_GELU_BWD, ACT_GELU_FWD_F, ACT_MUL_AUX = 0, 1, 2, 3, 4
 GEMM_SIMT, GEMM_TCGEN05 = 0, 1
 
 vp, ll, i32, u32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_uint, C.c_float
