@@ -75,6 +75,9 @@ class CaptionTrainer:
                                                                  if dist.is_available() and dist.is_initialized() else 1)
         self._graphs = {}
         self._warm = {}
+        # experimental, OFF: capturing the per-slice NCCL all-reduces in the step graph hung on this stack (torch 2.11 +
+        # NCCL 2.28.9, 2 x B200: both ranks stall in the first replay), so N > 1 keeps the eager backward below
+        self.graph_nccl = os.environ.get("VCT_GRAPH_NCCL", "0") == "1"
         # The step is captured on a HIGH-priority stream: its kernels (the latency-bound dependent chain of forward and
         # backward) are the critical path, while the side lanes (weight gradients, column sums, Adam slices -- default,
         # i.e. lowest, priority) only need to finish by the end of the step.  The block scheduler then hands freed SM
@@ -91,12 +94,12 @@ class CaptionTrainer:
         self.engine.set_lr(lr)
 
     # ---- one step -----------------------------------------------------------------------------------
-    def _compute(self, ws, fuse_adam: bool = False) -> None:
+    def _compute(self, ws, fuse_adam: bool = False, allreduce=None) -> None:
         eng = self.engine
         eng.tick()
         eng.zero_scatter_grads()
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
-        eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=fuse_adam))
+        eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=fuse_adam, allreduce=allreduce))
 
     def _forward(self, ws) -> None:
         eng = self.engine
@@ -153,10 +156,25 @@ class CaptionTrainer:
             self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True))
         elif self.world == 1:
             self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()))
+        elif self.fuse_adam and self.graph_nccl:
+            # data parallel, ONE CUDA graph per step: the per-slice NCCL all-reduces are captured on the optimizer lane
+            # together with the Adam slices (NCCL >= 2.9.6 collectives are capturable), so an N-GPU step costs no more
+            # host time than a 1-GPU step.  If the capture is refused the trainer falls back to the eager backward.
+            try:
+                self._graphed((B, T, S, "step+adam+nccl"),
+                              lambda: self._compute(ws, fuse_adam=True, allreduce=(self.group, self.world)))
+            except Exception as e:            # noqa: BLE001 -- capture failures surface as RuntimeError / CUDA errors
+                if (B, T, S, "step+adam+nccl") in self._graphs:
+                    raise
+                import warnings
+                warnings.warn(f"vct_b200: NCCL collectives could not be captured in a CUDA graph ({e}); using the eager backward")
+                self.graph_nccl = False
+                self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
+                eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=(self.group, self.world)))
         elif self.fuse_adam:
-            # data parallel with overlap: forward is a CUDA graph; backward runs eagerly because NCCL collectives stay
-            # outside graph capture -- each arena slice is all-reduced and then updated on the optimizer lane while
-            # the rest of backward continues on the main lane
+            # data parallel with overlap: forward is a CUDA graph; backward runs eagerly (NCCL collectives outside graph
+            # capture) -- each arena slice is all-reduced and then updated on the optimizer lane while the rest of
+            # backward continues on the main lane
             self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
             eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=(self.group, self.world)))
         else:
