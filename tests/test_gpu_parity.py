@@ -214,3 +214,28 @@ def test_native_trainer_matches_autograd_plus_torch_adam(full_model):
         assert abs(float(la) - float(lb)) <= 1e-5 * abs(float(la)), (step, float(la), float(lb))
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         torch.testing.assert_close(pa, pb, rtol=1e-4, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
+
+
+def test_segmented_graph_backward_matches_single_graph(full_model, monkeypatch):
+    """The N > 1 execution scheme of CaptionTrainer (forward graph + backward CUDA-graph segments + optimizer lane issued
+    eagerly between them; forced on one GPU with VCT_FORCE_SEGMENTED=1) must reproduce the single-graph step: same kernels,
+    same per-stream order."""
+    from vct.trainer import CaptionTrainer
+    x, vm, tok = synth_inputs(8, 12, 512, 21, 30522, 4321, padded=True)
+    xd, vd, td = x.to(DEV), vm.to(DEV), tok.to(DEV)
+    ma = full_model("json", "bf16", "tcgen05")
+    mb = full_model("json", "bf16", "tcgen05")
+    ma.train(), mb.train()
+    ta = CaptionTrainer(ma, lr=1e-4, betas=(0.9, 0.999))
+    tb = CaptionTrainer(mb, lr=1e-4, betas=(0.9, 0.999))
+    for step in range(5):                                    # 2 eager warm-up steps, capture on the 3rd, 2 replays
+        monkeypatch.delenv("VCT_FORCE_SEGMENTED", raising=False)
+        la = float(ta.step(xd, vd, td))
+        monkeypatch.setenv("VCT_FORCE_SEGMENTED", "1")
+        lb = float(tb.step(xd, vd, td))
+        assert abs(la - lb) <= 1e-6 * abs(la), (step, la, lb)      # (the embedding scatter uses fp32 atomics: not bit-exact)
+    monkeypatch.delenv("VCT_FORCE_SEGMENTED", raising=False)
+    assert len(tb._segments) == 1 and sum(1 for g, *_ in next(iter(tb._segments.values()))[0] if g is not None) >= 5
+    torch.cuda.synchronize()
+    for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
+        torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")

@@ -75,9 +75,11 @@ class CaptionTrainer:
                                                                  if dist.is_available() and dist.is_initialized() else 1)
         self._graphs = {}
         self._warm = {}
-        # experimental, OFF: capturing the per-slice NCCL all-reduces in the step graph hung on this stack (torch 2.11 +
-        # NCCL 2.28.9, 2 x B200: both ranks stall in the first replay), so N > 1 keeps the eager backward below
-        self.graph_nccl = os.environ.get("VCT_GRAPH_NCCL", "0") == "1"
+        # N > 1: backward as CUDA-graph segments between the optimizer slices (VCT_SEGMENTED=0: fully eager backward).
+        # (Capturing the NCCL all-reduces themselves inside one step graph hung on this stack -- torch 2.11 + NCCL 2.28.9,
+        # 2 x B200, both ranks stall in the first replay -- so the collectives stay outside the graphs.)
+        self.segmented = os.environ.get("VCT_SEGMENTED", "1") != "0"
+        self._segments = {}
         # The step is captured on a HIGH-priority stream: its kernels (the latency-bound dependent chain of forward and
         # backward) are the critical path, while the side lanes (weight gradients, column sums, Adam slices -- default,
         # i.e. lowest, priority) only need to finish by the end of the step.  The block scheduler then hands freed SM
@@ -136,14 +138,70 @@ class CaptionTrainer:
         g.replay()
         eng.launches += n
 
+    def _backward_segments(self, ws, key) -> None:
+        """Backward + per-slice (all-reduce, Adam) as a chain of CUDA-graph segments (see ``step``).  The backward plan is
+        split at every run of optimizer-lane calls; segment k holds the main-lane and weight-gradient-lane launches that
+        precede slice k (the side lane re-joins the main lane at the end of a segment, as graph capture requires)."""
+        from .engine import Plan
+        eng = self.engine
+        main = torch.cuda.current_stream(eng.device)
+        opt = eng.side_streams[1]
+        ar = (self.group, self.world) if self.world > 1 else None
+        plan = eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=ar)
+        if self._warm.get(key + ("segments",), 0) < 2 or not self.use_graph:
+            self._warm[key + ("segments",)] = self._warm.get(key + ("segments",), 0) + 1
+            eng.run(plan)
+            return
+        if key not in self._segments:
+            segs, cur = [], []
+            for c in plan.calls:
+                if c[3] == 2:                                    # optimizer lane: py:all_reduce / vct_adam
+                    if not segs or cur or segs[-1][1] is None:
+                        segs.append([cur, []])
+                        cur = []
+                    segs[-1][1].append(c)
+                else:
+                    cur.append(c)
+            if cur:
+                segs.append([cur, []])
+            built = []
+            for gpu_calls, opt_calls in segs:
+                g, n = None, 0
+                real = [c for c in gpu_calls if c[0] != "join"]
+                if real:
+                    sub = Plan()
+                    sub.calls, sub.keep = list(gpu_calls), plan.keep
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        n = sub.run(torch.cuda.current_stream(eng.device), eng.side_streams)
+                built.append((g, n, opt_calls, torch.cuda.Event(), sub if real else None))
+            self._segments[key] = (built, torch.cuda.Event())
+        built, done = self._segments[key]
+        from . import lib as L
+        for g, n, opt_calls, ev, _sub in built:
+            if g is not None:
+                g.replay()
+                eng.launches += n
+            if opt_calls:
+                ev.record(main)
+                opt.wait_event(ev)
+                for name, fn, args, _lane in opt_calls:
+                    rc = fn(opt) if name.startswith("py:") else fn(*args, opt.cuda_stream)
+                    if rc:
+                        L.check(rc, name)
+                    if not name.startswith("py:"):
+                        eng.launches += 1
+        done.record(opt)
+        main.wait_event(done)
+
     def step(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: torch.Tensor) -> torch.Tensor:
         """feats fp32 [B,T,Din], vid_pad bool [B,T] | None, ids int64 [B,S+1] (host -- ideally pinned -- or
         device tensors).  Returns the step's loss as a device scalar (no host sync).
 
         world == 1: [tick, forward, backward, Adam] is ONE CUDA graph.
-        world  > 1: graph [tick, forward]; eager backward whose optimizer lane all-reduces (NCCL SUM) and then
-        updates each arena slice as soon as its gradient is final (VCT_FUSE_ADAM=0: graph [tick, forward,
-        backward] -> bucketed all-reduce -> graph [Adam])."""
+        world  > 1: graph [tick, forward]; backward as graph segments whose optimizer lane all-reduces (NCCL SUM) and
+        then updates each arena slice as soon as its gradient is final (VCT_SEGMENTED=0: eager backward;
+        VCT_FUSE_ADAM=0: graph [tick, forward, backward] -> bucketed all-reduce -> graph [Adam])."""
         eng = self.engine
         B, T, _ = feats.shape
         S = ids.shape[1] - 1
@@ -151,26 +209,22 @@ class CaptionTrainer:
         eng.check_arena()
         eng.refresh_shadow()               # no-op unless the masters were edited outside vct_adam
         eng.stage_inputs(ws, feats, vid_pad, ids)
-        if self.world == 1 and self.fuse_adam:
+        if self.world == 1 and self.fuse_adam and os.environ.get("VCT_FORCE_SEGMENTED") == "1":
+            # test hook: the N > 1 execution scheme (forward graph + backward graph segments + eager optimizer lane) on one GPU
+            self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
+            self._backward_segments(ws, (B, T, S))
+        elif self.world == 1 and self.fuse_adam:
             # optimizer-in-backward: vct_adam runs slice by slice on a side lane while backward continues
             self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True))
         elif self.world == 1:
             self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()))
-        elif self.fuse_adam and self.graph_nccl:
-            # data parallel, ONE CUDA graph per step: the per-slice NCCL all-reduces are captured on the optimizer lane
-            # together with the Adam slices (NCCL >= 2.9.6 collectives are capturable), so an N-GPU step costs no more
-            # host time than a 1-GPU step.  If the capture is refused the trainer falls back to the eager backward.
-            try:
-                self._graphed((B, T, S, "step+adam+nccl"),
-                              lambda: self._compute(ws, fuse_adam=True, allreduce=(self.group, self.world)))
-            except Exception as e:            # noqa: BLE001 -- capture failures surface as RuntimeError / CUDA errors
-                if (B, T, S, "step+adam+nccl") in self._graphs:
-                    raise
-                import warnings
-                warnings.warn(f"vct_b200: NCCL collectives could not be captured in a CUDA graph ({e}); using the eager backward")
-                self.graph_nccl = False
-                self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
-                eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=(self.group, self.world)))
+        elif self.fuse_adam and self.segmented:
+            # data parallel: forward is one CUDA graph and backward a chain of graph SEGMENTS -- the launches between two
+            # optimizer slices are captured together -- with the per-slice NCCL all-reduce + Adam issued eagerly on the
+            # optimizer lane after each segment.  ~25 host operations per step instead of ~110 ctypes launches, so the
+            # N-GPU step is no longer bound by the host.
+            self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
+            self._backward_segments(ws, (B, T, S))
         elif self.fuse_adam:
             # data parallel with overlap: forward is a CUDA graph; backward runs eagerly (NCCL collectives outside graph
             # capture) -- each arena slice is all-reduced and then updated on the optimizer lane while the rest of
