@@ -158,3 +158,21 @@ def test_synthetic_batch_shapes_and_tokens():
     for row in tok.tolist():
         n = row.index(102)
         assert all(t == 0 for t in row[n + 1:]) and all(t >= 1000 for t in row[1:n])
+
+
+def test_backward_plan_is_split_at_optimizer_lane_runs():
+    """vct.trainer.split_segments: the N > 1 trainer captures the launches between two optimizer slices as one CUDA graph
+    and issues the slice's (all-reduce, Adam) eagerly; every call must land in exactly one segment, in order."""
+    from vct.trainer import split_segments
+    c = lambda name, lane: (name, None, (), lane)          # noqa: E731
+    calls = [c("a", 0), c("w1", 1), c("b", 0), c("py:all_reduce:x", 2), c("vct_adam:x", 2), c("c", 0), c("join", 0), c("w2", 1),
+             c("py:all_reduce:y", 2), c("vct_adam:y", 2), c("vct_adam:z", 2), c("d", 0)]
+    segs = split_segments(calls)
+    assert [[x[0] for x in g] for g, _ in segs] == [["a", "w1", "b"], ["c", "join", "w2"], ["d"]]
+    assert [[x[0] for x in o] for _, o in segs] == [["py:all_reduce:x", "vct_adam:x"], ["py:all_reduce:y", "vct_adam:y", "vct_adam:z"], []]
+    flat = [x for g, o in segs for x in (g + o)]
+    assert flat == calls
+    # optimizer calls first (nothing to capture before them) and no trailing main-lane work
+    segs = split_segments([c("vct_adam:p", 2), c("a", 0), c("vct_adam:q", 2)])
+    assert [[x[0] for x in g] for g, _ in segs] == [[], ["a"]] and [[x[0] for x in o] for _, o in segs] == [["vct_adam:p"], ["vct_adam:q"]]
+    assert split_segments([]) == []

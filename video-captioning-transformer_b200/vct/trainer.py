@@ -51,6 +51,27 @@ def gradient_buckets(arena, order: List[str], max_bytes: int = 64 << 20) -> List
     return out
 
 
+def split_segments(calls) -> List[Tuple[list, list]]:
+    """Split a backward plan (``Plan.calls`` entries ``(name, fn, args, lane)``) at every run of optimizer-lane (lane 2)
+    calls: returns ``[(gpu_calls, optimizer_calls), ...]`` in issue order, where ``gpu_calls`` are the main-lane /
+    weight-gradient-lane entries that precede the run (possibly empty) and the last pair may have no optimizer calls."""
+    segs, cur = [], []
+    in_opt = False
+    for c in calls:
+        if c[3] == 2:
+            if not in_opt:
+                segs.append((cur, []))
+                cur = []
+                in_opt = True
+            segs[-1][1].append(c)
+        else:
+            cur.append(c)
+            in_opt = False
+    if cur:
+        segs.append((cur, []))
+    return segs
+
+
 def all_reduce_flat(flat: torch.Tensor, buckets: List[Tuple[int, int]], group=None) -> None:
     """SUM all-reduce of each bucket slice (any backend: nccl on GPU, gloo in the CPU tests)."""
     import torch.distributed as dist
@@ -153,19 +174,8 @@ class CaptionTrainer:
             eng.run(plan)
             return
         if key not in self._segments:
-            segs, cur = [], []
-            for c in plan.calls:
-                if c[3] == 2:                                    # optimizer lane: py:all_reduce / vct_adam
-                    if not segs or cur or segs[-1][1] is None:
-                        segs.append([cur, []])
-                        cur = []
-                    segs[-1][1].append(c)
-                else:
-                    cur.append(c)
-            if cur:
-                segs.append([cur, []])
             built = []
-            for gpu_calls, opt_calls in segs:
+            for gpu_calls, opt_calls in split_segments(plan.calls):      # optimizer lane: py:all_reduce / vct_adam
                 g, n = None, 0
                 real = [c for c in gpu_calls if c[0] != "join"]
                 if real:
