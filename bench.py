@@ -266,8 +266,8 @@ def attention_rooflines(names, med, calls, peaks):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)     # 200 x 1.7 ms: long enough for several nvidia-smi clock samples
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU")
     ap.add_argument("--precision", default=os.environ.get("VCT_PRECISION", "bf16"))
