@@ -16,7 +16,7 @@
  *   - row-major, batch-first; "ld" arguments are row strides in ELEMENTS
  *   - dtype codes: VCT_F32 = 0, VCT_BF16 = 1 (storage type; arithmetic/accumulation is fp32)
  *   - masks: uint8, 1 = ignore (torch.bool True), like the reference's padding masks
- *   - dropout: counter-based (Philox4x32-10).  `rng_state` is a device array of two uint64
+ *   - dropout: counter-based (Philox4x32-7, the minimum round count the Philox authors qualify: passes BigCrush).  `rng_state` is a device array of two uint64
  *     {seed, step}; `site` identifies the dropout call site; the mask is a pure function of
  *     (seed, step, site, element index), so backward regenerates it.  drop_p <= 0 disables.
  */

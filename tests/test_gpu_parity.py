@@ -235,7 +235,8 @@ def test_segmented_graph_backward_matches_single_graph(full_model, monkeypatch):
         lb = float(tb.step(xd, vd, td))
         assert abs(la - lb) <= 1e-6 * abs(la), (step, la, lb)      # (the embedding scatter uses fp32 atomics: not bit-exact)
     monkeypatch.delenv("VCT_FORCE_SEGMENTED", raising=False)
-    assert len(tb._segments) == 1 and sum(1 for g, *_ in next(iter(tb._segments.values()))[0] if g is not None) >= 5
+    segs = tb.engine.workspace(8, 12, 20, True).graphs["_segments"]
+    assert len(segs) == 1 and sum(1 for g, *_ in next(iter(segs.values()))[0] if g is not None) >= 5
     torch.cuda.synchronize()
     for (k, pa), (_, pb) in zip(ma.named_parameters(), mb.named_parameters()):
         torch.testing.assert_close(pa, pb, rtol=1e-5, atol=1e-7, msg=lambda m, k=k: f"{k}: {m}")

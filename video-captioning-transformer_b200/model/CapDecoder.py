@@ -68,14 +68,21 @@ class CapDecoder(nn.Module):
         return any('forward' in layer.__dict__ for layer in self.decoder.layers)
 
     # ---- reference API ------------------------------------------------------------------------------
-    def forward(self, memories: Tensor, tgt: Tensor, tgt_padding_mask: Tensor):
+    def forward(self, memories: Tensor, tgt: Tensor, tgt_padding_mask: Optional[Tensor], _want_logits: bool = True):
         """memories [B,M,E], tgt ids [B,S+1], tgt_padding_mask [B,S+1] (True = pad) -> (logits [B,S,V], loss).
-        The padding mask the kernels use is recomputed as ``tgt == pad_id``, which is what the reference's
-        CapPreprocessor produces (model/CapPreprocessor.py:35)."""
+        As in the reference (model/CapDecoder.py:43-52) the decoder's key-padding mask is ``tgt_padding_mask[:, :-1]``
+        -- the mask that is PASSED, not one recomputed from the ids -- while the loss ignores positions whose target
+        id is ``pad_id`` (model/CapDecoder.py:28-32).  ``None`` means ``tgt == pad_id``.  Both outputs are freshly
+        allocated."""
         from vct.functional import DecoderFn
         eng = self._engine()
         params = [p for _, p in self.named_parameters()]
-        return DecoderFn.apply(eng, self, memories, tgt, *params)
+        tok_pad = None
+        if tgt_padding_mask is not None:
+            if tgt_padding_mask.shape != tgt.shape:
+                raise ValueError(f"tgt_padding_mask {tuple(tgt_padding_mask.shape)} must match tgt {tuple(tgt.shape)}")
+            tok_pad = tgt_padding_mask[:, :-1].to(torch.bool)
+        return DecoderFn.apply(eng, self, memories, tgt, tok_pad, bool(_want_logits), *params)
 
     def decode_word(self, memories: Tensor, tgt: Tensor, tgt_padding_mask: Optional[Tensor]):
         """Next-word logits [B,V] for the prefix ``tgt`` [B,t] (model/CapDecoder.py:62-79).  Runs the

@@ -115,11 +115,19 @@ class MMT4Caption(nn.Module):
 
     def caption_forward(self, video_feats, video_masks, captions):
         """loss of the captioning task (reference :114-121; returns the loss only)."""
-        self._engine()
+        eng = self._engine()
         text_ts, text_mask_ts = self._tokenise(captions)
         self.video_encoder._vct_S_hint = text_ts.shape[1] - 1
-        memory, _, _ = self.video_encoder(video_feats, video_masks)
-        logits, loss = self.cap_decoder(memory, text_ts, text_mask_ts)
+        # one fresh dropout step per training forward, shared by the encoder and the decoder (distinct call sites)
+        eng._pinned_step = None
+        if self.training:
+            eng._pinned_step = eng.next_rng_step()
+        try:
+            memory, _, _ = self.video_encoder(video_feats, video_masks)
+            # the logits are discarded here (reference :120-121), so the decoder does not copy them out
+            _, loss = self.cap_decoder(memory, text_ts, text_mask_ts, _want_logits=False)
+        finally:
+            eng._pinned_step = None
         return loss
 
     def match_forward(self, video_feats, video_masks, captions):

@@ -157,7 +157,13 @@ class CaptionEngine:
         self.pos = cap_decoder.positional_encoding.pos_embedding if cap_decoder is not None else None   # [5000, d]
         self.pe = video_encoder.temp_emb.pe if video_encoder is not None else None                      # [1, 512, d]
         # per-step device state
-        self.rng_state = torch.tensor([seed, 0], dtype=torch.int64, device=device)
+        # dropout stream: {seed, step}.  Every data-parallel rank draws different masks (the reference's ranks do too:
+        # each process owns its own torch RNG stream), so the rank is mixed into the seed.
+        self.seed = int(seed)
+        self.rng_state = torch.tensor([self._rank_seed(seed), 0], dtype=torch.int64, device=device)
+        self._host_step = 0          # last step value handed out on the autograd path (next_rng_step)
+        self._dev_step = 0           # value known to be in rng_state[1]; None after a device-side tick
+        self._pinned_step = None     # set by MMT4Caption.caption_forward: encoder and decoder share one step
         self.hyper = torch.zeros(8, dtype=torch.float32, device=device)
         self.counters = torch.zeros(1024, dtype=torch.int32, device=device)
         self.upstream = torch.ones(1, dtype=torch.float32, device=device)
@@ -167,6 +173,40 @@ class CaptionEngine:
         self._ws: Dict[Tuple, SimpleNamespace] = {}
         self._shadow_version = None
         self.launches = 0
+
+    # ------------------------------------------------------------------------------------------
+    # dropout RNG bookkeeping
+    # ------------------------------------------------------------------------------------------
+    @staticmethod
+    def _rank_seed(seed: int) -> int:
+        rank = 0
+        try:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized():
+                rank = dist.get_rank()
+        except Exception:
+            rank = 0
+        return (int(seed) + 0x9E3779B97F4A7C15 * rank) & 0x7FFFFFFFFFFFFFFF
+
+    def set_seed(self, seed: int, rank_mix: bool = True) -> None:
+        self.seed = int(seed)
+        self.rng_state[0:1].fill_(self._rank_seed(seed) if rank_mix else int(seed))
+
+    def set_rng_step(self, step: int) -> None:
+        """Make ``step`` the training-step component of every dropout mask drawn from now on (autograd path: the
+        backward of a forward must regenerate that forward's masks, whatever ran in between)."""
+        if self._dev_step != step:
+            self.rng_state[1:2].fill_(int(step))
+            self._dev_step = int(step)
+
+    def next_rng_step(self) -> int:
+        """A fresh step value for one training forward on the autograd path (the native trainer advances the device
+        counter itself through vct_step_tick inside its CUDA graph)."""
+        if self._pinned_step is not None:
+            return self._pinned_step
+        self._host_step += 1
+        self.set_rng_step(self._host_step)
+        return self._host_step
 
     # ------------------------------------------------------------------------------------------
     # parameter access
@@ -346,7 +386,10 @@ class CaptionEngine:
     def workspace(self, B: int, T: int, S: int, training: bool) -> SimpleNamespace:
         key = (B, T, S, training)
         if key in self._ws:
-            return self._ws[key]
+            ws = self._ws.pop(key)
+            self._ws[key] = ws            # most recently used last
+            return ws
+        self._evict_workspaces()
         D = self.dims
         ws = SimpleNamespace(B=B, T=T, S=S, M=T + 1, training=training)
         d, M = D.d, T + 1
@@ -437,8 +480,21 @@ class CaptionEngine:
         ws.splitk = [torch.empty(8 * max(Re, Rd) * max(d, 8), dtype=f32, device=self.device) for _ in range(2)] \
             if self.gemm_impl == L.GEMM_TCGEN05 else None
         ws.plans = {}
+        ws.graphs = {}            # CUDA graphs captured over this workspace's pointers (vct.trainer): same lifetime
+        ws.enc_version = 0        # bumped by every encoder / decoder forward over this workspace: backward checks that
+        ws.dec_version = 0        # the activations it is about to read are still those of its own forward
+        ws.mem_token = None
         self._ws[key] = ws
         return ws
+
+    def _evict_workspaces(self) -> None:
+        """Bound the per-shape workspace cache (batches built by caption length have a new S almost every step): keep the
+        VCT_WS_CACHE most recently used training / eval workspaces.  An evicted workspace (with its plans and CUDA
+        graphs) is freed once nothing else -- e.g. a pending autograd graph -- references it."""
+        limit = max(1, int(os.environ.get("VCT_WS_CACHE", "6")))
+        keys = [k for k in self._ws if k and k[0] != "decode"]
+        while len(keys) >= limit:
+            self._ws.pop(keys.pop(0))
 
     # ------------------------------------------------------------------------------------------
     # forward plan
@@ -791,8 +847,11 @@ class CaptionEngine:
     # ------------------------------------------------------------------------------------------
     # running
     # ------------------------------------------------------------------------------------------
-    def stage_inputs(self, ws, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: Optional[torch.Tensor]):
-        """Copy the step's inputs into the workspace (host or device sources; async on the current stream)."""
+    def stage_inputs(self, ws, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: Optional[torch.Tensor],
+                     tok_pad: Optional[torch.Tensor] = None):
+        """Copy the step's inputs into the workspace (host or device sources; async on the current stream).
+        tok_pad: optional bool [B, S] key-padding mask of the decoder inputs (default: ids[:, :-1] == pad_id, which is
+        what the reference's CapPreprocessor produces, model/CapPreprocessor.py:35)."""
         ws.feats.copy_(feats.reshape(ws.feats.shape), non_blocking=True)
         ws.vid_pad[:, 0] = 0
         if vid_pad is None:
@@ -800,8 +859,14 @@ class CaptionEngine:
         else:
             ws.vid_pad[:, 1:].copy_(vid_pad, non_blocking=True)
         if ids is not None:
-            ws.ids.copy_(ids, non_blocking=True)
+            self.stage_ids(ws, ids, tok_pad)
+
+    def stage_ids(self, ws, ids: torch.Tensor, tok_pad: Optional[torch.Tensor] = None) -> None:
+        ws.ids.copy_(ids, non_blocking=True)
+        if tok_pad is None:
             torch.eq(ws.ids[:, :-1], self.dims.pad_id, out=ws.tok_pad.view(torch.bool))
+        else:
+            ws.tok_pad.view(torch.bool).copy_(tok_pad.reshape(ws.tok_pad.shape), non_blocking=True)
 
     def run(self, plan: Plan) -> None:
         self.launches += plan.run(torch.cuda.current_stream(self.device), self.side_streams)
@@ -823,6 +888,7 @@ class CaptionEngine:
     def tick(self) -> None:
         L.check(self.lib.vct_step_tick(self.rng_state.data_ptr(), self.hyper.data_ptr(), self._stream()), "vct_step_tick")
         self.launches += 1
+        self._dev_step = None        # advanced on the device (possibly inside a CUDA graph): host mirror unknown
 
     def adam(self, grad_scale: float = 1.0) -> None:
         a = self.arena
@@ -879,7 +945,10 @@ class CaptionEngine:
 
     def plan_decode_init(self, dws, enc_ws) -> Plan:
         """cross-attention K/V of every decoder layer from the encoder memory (once per batch)."""
-        key = ("init", id(enc_ws))
+        key = ("init",)
+        if getattr(dws, "init_ws", None) is not enc_ws:
+            dws.plans.pop(key, None)      # the encoder workspace was re-allocated (LRU eviction): its pointers changed
+            dws.init_ws = enc_ws          # (the reference also keeps that workspace alive as long as this plan exists)
         if key not in dws.plans:
             D = self.dims
             d = D.d

@@ -1,7 +1,15 @@
 """torch.autograd bridges: they let the reference's own training loop
 (``loss = model(...); loss.backward(); optimizer.step()``, train.py:123-126) and
 DistributedDataParallel drive the B200 kernels.  Forward and backward are launch plans of
-``CaptionEngine``; these classes only move gradients in and out of the arena."""
+``CaptionEngine``; these classes only move gradients in and out of the arena.
+
+Contract of this path (the reference returns freshly allocated tensors):
+  * outputs handed to the caller (memory, logits, loss) are COPIES of the workspace buffers, so a later forward of the
+    same shape cannot change tensors the caller still holds;
+  * activations saved for backward stay in the per-shape workspace: running another forward of the same shape
+    before ``backward()`` invalidates them, which is detected and raised (never silently wrong gradients);
+  * every training forward draws a fresh dropout step (``engine.next_rng_step``) and its backward re-installs that
+    step first, so forward and backward masks are identical and consecutive calls differ."""
 from __future__ import annotations
 
 from typing import Optional
@@ -11,9 +19,22 @@ import torch
 from .engine import CaptionEngine
 
 
+def _detach_aliased_grads(engine: CaptionEngine, prefix: str, params) -> None:
+    """Gradient accumulation (a second ``backward()`` without ``zero_grad(set_to_none=True)``): a ``p.grad`` that
+    AccumulateGrad stole from a previous backward is a VIEW of the gradient arena, which the plan about to run
+    overwrites.  Move such gradients to their own storage first so that autograd adds old + new correctly."""
+    a = engine.arena
+    base, end = a.grad.data_ptr(), a.grad.data_ptr() + 4 * a.numel
+    for _name, p in params:
+        g = p.grad
+        if g is not None and base <= g.data_ptr() < end:
+            p.grad = g.clone()
+
+
 def _grads_for(engine: CaptionEngine, prefix: str, params):
-    """Arena gradient views for the given parameters (zero-copy when ``p.grad`` is unset, which is
-    what ``optimizer.zero_grad()`` leaves; a clone otherwise so accumulation never self-aliases)."""
+    """Arena gradient views for the given parameters: zero-copy when ``p.grad`` is unset (what
+    ``optimizer.zero_grad()`` leaves -- AccumulateGrad then adopts the view), a clone when autograd is going to
+    accumulate into an existing ``p.grad``."""
     out = []
     a = engine.arena
     for name, p in params:
@@ -23,6 +44,12 @@ def _grads_for(engine: CaptionEngine, prefix: str, params):
         g = a.grad_view(prefix + name)
         out.append(g if p.grad is None else g.clone())
     return out
+
+
+def _stale(what: str):
+    return RuntimeError(f"vct: the {what} workspace was reused by another forward of the same shape before this "
+                        f"backward ran; call backward() before the next forward of that shape (activations are saved "
+                        f"in a per-shape workspace, not per call)")
 
 
 class EncoderFn(torch.autograd.Function):
@@ -35,10 +62,15 @@ class EncoderFn(torch.autograd.Function):
         ws = engine.workspace(B, T, S_hint, training)
         engine.check_arena()
         engine.refresh_shadow()
+        ctx.rng_step = engine.next_rng_step() if training else None
         engine.stage_inputs(ws, feats, vid_pad, None)
         engine.run(engine.plan_encode(ws))
-        ctx.engine, ctx.ws, ctx.module = engine, ws, module
-        return ws.mem.view(B, T + 1, engine.dims.d)
+        ws.enc_version += 1
+        ctx.engine, ctx.ws, ctx.module, ctx.version = engine, ws, module, ws.enc_version
+        out = ws.mem.view(B, T + 1, engine.dims.d).clone()
+        # lets DecoderFn recognise "this is the memory my workspace already holds" without comparing contents
+        ws.mem_token = (out.data_ptr(), out._version, ws.enc_version)
+        return out
 
     @staticmethod
     def backward(ctx, dmem):
@@ -46,10 +78,15 @@ class EncoderFn(torch.autograd.Function):
         if not ws.training:
             raise RuntimeError("vct: backward through an eval-mode encoder forward is not supported "
                                "(call model.train(); dropout p can be 0)")
+        if ws.enc_version != ctx.version:
+            raise _stale("encoder")
+        named = list(ctx.module.named_parameters())
+        _detach_aliased_grads(engine, "video_encoder.", named)
+        engine.set_rng_step(ctx.rng_step)
         if dmem.data_ptr() != ws.g_mem.data_ptr():
             ws.g_mem.copy_(dmem.reshape(ws.g_mem.shape))
         engine.run(engine.plan_backward(ws, sce_first=False, part="enc"))
-        grads = _grads_for(engine, "video_encoder.", list(ctx.module.named_parameters()))
+        grads = _grads_for(engine, "video_encoder.", named)
         return (None, None, None, None, None, *grads)
 
 
@@ -57,24 +94,30 @@ class DecoderFn(torch.autograd.Function):
     """CapDecoder.forward (model/CapDecoder.py:34-60) -> (logits [B,S,V], loss)."""
 
     @staticmethod
-    def forward(ctx, engine: CaptionEngine, module, memory, ids, *params):
+    def forward(ctx, engine: CaptionEngine, module, memory, ids, tok_pad, want_logits: bool, *params):
         B, M, d = memory.shape
         S = ids.shape[1] - 1
         training = module.training
         ws = engine.workspace(B, M - 1, S, training)
         engine.check_arena()
         engine.refresh_shadow()
-        if memory.data_ptr() != ws.mem.data_ptr():
-            # memory produced elsewhere (stand-alone use of the decoder): stage it
+        ctx.rng_step = engine.next_rng_step() if training else None
+        tok = ws.mem_token
+        if tok is None or tok != (memory.data_ptr(), memory._version, ws.enc_version):
+            # memory produced elsewhere (stand-alone use of the decoder, or edited by the caller): stage it
             ws.mem.copy_(memory.reshape(ws.mem.shape))
             if ws.mem_c is not ws.mem:
                 ws.mem_c.copy_(ws.mem)
-        ws.ids.copy_(ids, non_blocking=True)
-        torch.eq(ws.ids[:, :-1], engine.dims.pad_id, out=ws.tok_pad.view(torch.bool))
+            ws.mem_token = None
+        engine.stage_ids(ws, ids, tok_pad)
         engine.run(engine.plan_forward(ws, fused_grad=False, part="dec"))
-        ctx.engine, ctx.ws, ctx.module = engine, ws, module
+        ws.dec_version += 1
+        ctx.engine, ctx.ws, ctx.module, ctx.version = engine, ws, module, ws.dec_version
         V = engine.dims.V
-        logits = ws.logits.view(B, S, ws.Vp)[:, :, :V]
+        if want_logits:
+            logits = ws.logits.view(B, S, ws.Vp)[:, :, :V].clone()
+        else:
+            logits = ws.logits.new_empty(0)         # caption_forward discards the logits (model/MMT4Caption.py:120-121)
         loss = ws.loss[0].clone()
         ctx.mark_non_differentiable(logits)
         return logits, loss
@@ -85,12 +128,18 @@ class DecoderFn(torch.autograd.Function):
         if not ws.training:
             raise RuntimeError("vct: backward through an eval-mode decoder forward is not supported "
                                "(call model.train(); dropout p can be 0)")
+        if ws.dec_version != ctx.version:
+            raise _stale("decoder")
+        named = list(ctx.module.named_parameters())
+        _detach_aliased_grads(engine, "cap_decoder.", named)
+        engine.set_rng_step(ctx.rng_step)
         engine.upstream.copy_(dloss.reshape(1))
         engine.zero_scatter_grads()
         engine.run(engine.plan_backward(ws, sce_first=True, part="dec"))
-        grads = _grads_for(engine, "cap_decoder.", list(ctx.module.named_parameters()))
+        grads = _grads_for(engine, "cap_decoder.", named)
+        # (a view: the encoder's backward consumes it at once; nothing else of this path keeps it)
         dmem = ws.g_mem.view(ws.B, ws.M, engine.dims.d) if ctx.needs_input_grad[2] else None
-        return (None, None, dmem, None, *grads)
+        return (None, None, dmem, None, None, None, *grads)
 
 
 def sce_loss(engine_lib, logits: torch.Tensor, labels: torch.Tensor, alpha: float, beta: float, pad_id: int):

@@ -94,13 +94,12 @@ class CaptionTrainer:
         self.group = process_group
         self.world = world_size if world_size is not None else (dist.get_world_size(process_group)
                                                                  if dist.is_available() and dist.is_initialized() else 1)
-        self._graphs = {}
-        self._warm = {}
+        self._graphs_global = {}       # graphs that touch no per-shape workspace (the stand-alone Adam launch)
+        self._graphs, self._warm = self._graphs_global, {}
         # N > 1: backward as CUDA-graph segments between the optimizer slices (VCT_SEGMENTED=0: fully eager backward).
         # (Capturing the NCCL all-reduces themselves inside one step graph hung on this stack -- torch 2.11 + NCCL 2.28.9,
         # 2 x B200, both ranks stall in the first replay -- so the collectives stay outside the graphs.)
         self.segmented = os.environ.get("VCT_SEGMENTED", "1") != "0"
-        self._segments = {}
         # The step is captured on a HIGH-priority stream: its kernels (the latency-bound dependent chain of forward and
         # backward) are the critical path, while the side lanes (weight gradients, column sums, Adam slices -- default,
         # i.e. lowest, priority) only need to finish by the end of the step.  The block scheduler then hands freed SM
@@ -133,12 +132,16 @@ class CaptionTrainer:
     def _update(self) -> None:
         self.engine.adam(grad_scale=1.0 / self.world)
 
-    def _graphed(self, key, fn):
-        """Run ``fn`` eagerly twice (plan building, kernel attributes), then capture it once and replay."""
+    def _graphed(self, key, fn, ws=None):
+        """Run ``fn`` eagerly twice (plan building, kernel attributes), then capture it once and replay.  Graphs over a
+        workspace's pointers are stored IN that workspace (``ws.graphs``), so evicting the workspace from the engine's
+        LRU cache drops them with it."""
         eng = self.engine
         if not self.use_graph:
             fn()
             return
+        store = ws.graphs if ws is not None else self._graphs_global
+        self._graphs, self._warm = store, store.setdefault("_warm", {})
         if key not in self._graphs:
             if self._warm.get(key, 0) < 2:
                 self._warm[key] = self._warm.get(key, 0) + 1
@@ -169,11 +172,13 @@ class CaptionTrainer:
         opt = eng.side_streams[1]
         ar = (self.group, self.world) if self.world > 1 else None
         plan = eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=ar)
-        if self._warm.get(key + ("segments",), 0) < 2 or not self.use_graph:
-            self._warm[key + ("segments",)] = self._warm.get(key + ("segments",), 0) + 1
+        warm = ws.graphs.setdefault("_warm", {})
+        segments = ws.graphs.setdefault("_segments", {})
+        if warm.get(key + ("segments",), 0) < 2 or not self.use_graph:
+            warm[key + ("segments",)] = warm.get(key + ("segments",), 0) + 1
             eng.run(plan)
             return
-        if key not in self._segments:
+        if key not in segments:
             built = []
             for gpu_calls, opt_calls in split_segments(plan.calls):      # optimizer lane: py:all_reduce / vct_adam
                 g, n = None, 0
@@ -185,8 +190,8 @@ class CaptionTrainer:
                     with torch.cuda.graph(g):
                         n = sub.run(torch.cuda.current_stream(eng.device), eng.side_streams)
                 built.append((g, n, opt_calls, torch.cuda.Event(), sub if real else None))
-            self._segments[key] = (built, torch.cuda.Event())
-        built, done = self._segments[key]
+            segments[key] = (built, torch.cuda.Event())
+        built, done = segments[key]
         from . import lib as L
         for g, n, opt_calls, ev, _sub in built:
             if g is not None:
@@ -221,28 +226,28 @@ class CaptionTrainer:
         eng.stage_inputs(ws, feats, vid_pad, ids)
         if self.world == 1 and self.fuse_adam and os.environ.get("VCT_FORCE_SEGMENTED") == "1":
             # test hook: the N > 1 execution scheme (forward graph + backward graph segments + eager optimizer lane) on one GPU
-            self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
+            self._graphed((B, T, S, "forward"), lambda: self._forward(ws), ws=ws)
             self._backward_segments(ws, (B, T, S))
         elif self.world == 1 and self.fuse_adam:
             # optimizer-in-backward: vct_adam runs slice by slice on a side lane while backward continues
-            self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True))
+            self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True), ws=ws)
         elif self.world == 1:
-            self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()))
+            self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()), ws=ws)
         elif self.fuse_adam and self.segmented:
             # data parallel: forward is one CUDA graph and backward a chain of graph SEGMENTS -- the launches between two
             # optimizer slices are captured together -- with the per-slice NCCL all-reduce + Adam issued eagerly on the
             # optimizer lane after each segment.  ~25 host operations per step instead of ~110 ctypes launches, so the
             # N-GPU step is no longer bound by the host.
-            self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
+            self._graphed((B, T, S, "forward"), lambda: self._forward(ws), ws=ws)
             self._backward_segments(ws, (B, T, S))
         elif self.fuse_adam:
             # data parallel with overlap: forward is a CUDA graph; backward runs eagerly (NCCL collectives outside graph
             # capture) -- each arena slice is all-reduced and then updated on the optimizer lane while the rest of
             # backward continues on the main lane
-            self._graphed((B, T, S, "forward"), lambda: self._forward(ws))
+            self._graphed((B, T, S, "forward"), lambda: self._forward(ws), ws=ws)
             eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=(self.group, self.world)))
         else:
-            self._graphed((B, T, S, "compute"), lambda: self._compute(ws))
+            self._graphed((B, T, S, "compute"), lambda: self._compute(ws), ws=ws)
             all_reduce_flat(eng.arena.grad, self.buckets, self.group)
             self._graphed(("update",), self._update)
         return ws.loss[0]
