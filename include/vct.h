@@ -208,6 +208,14 @@ int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, cons
                         int R, int d, float drop_p, const unsigned long long* rng_state, unsigned int site,
                         vct_stream_t stream);
 
+/* ---- eval-mode encoder fast path ------------------------------------------------------------
+ * x[r, :] = 0 for every row r with mask[r] != 0 (x fp32 [R, d], d % 4 == 0).  Under eval() + no_grad with a
+ * key-padding mask -- what val_epoch (train.py:151-168) and eval.py:140 run -- nn.TransformerEncoder takes torch's
+ * nested-tensor path (torch/nn/modules/transformer.py:452-548), which zero-fills the padded positions before the
+ * final LayerNorm: memory rows of padded frames become norm.bias.  The eval plan calls this on the last
+ * encoder layer's output right before vct_ln_residual_fwd. */
+int vct_zero_rows(float* x, const unsigned char* mask, int R, int d, vct_stream_t stream);
+
 /* ---- token embedding + positional table ------------------------------------------------------
  * x[b,s,:] = dropout(E[ids[b*ids_ld + s], :] + pos[s, :])   (no sqrt(d) scaling)
  * model/CapDecoder.py:48 + model/Embedding.py:23-25.  ids int64.  Writes x fp32 and optional x_c.

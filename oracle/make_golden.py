@@ -6,6 +6,9 @@ present on the GPU box):
 
 Writes
   tests/golden/tiny_a.npz, tiny_b.npz     tiny dims, every weight/input/output/gradient
+  tests/golden/extra_anchors.json, extra_samples.npz   (``--extra``) round-2 anchors: the bench workload (B = 64),
+                                           cfg 5 dims (6+6, T = 32), the eval fast path with padded frames and the cfg 3
+                                           greedy decode (B = 256, max_len 30) -- see make_extra
   tests/golden/fullsize_anchors.json       shipped-JSON dims (1 enc + 3 dec, d 768) and the
                                            BASELINE cfg-1 literal reading (2+2, d 512):
                                            seeds -> checksums / slices / loss / grad norms /
@@ -179,11 +182,127 @@ def make_fullsize(ref, tokdir):
         json.dump(anchors, f, indent=1)
 
 
+def sample_grid(t, n0=40, n1=12):
+    """~n0 x n1 strided sample of a 2-D tensor (per-element checks at full size without committing 94 MB)."""
+    s0, s1 = max(1, t.shape[0] // n0), max(1, t.shape[1] // n1)
+    return t[::s0, ::s1].contiguous(), (s0, s1)
+
+
+SAMPLED = ("cap_decoder.generator.weight", "cap_decoder.tgt_to_emb.weight",
+           "cap_decoder.decoder.layers.0.self_attn.in_proj_weight", "cap_decoder.decoder.layers.{last}.multihead_attn.in_proj_weight",
+           "cap_decoder.decoder.layers.{last}.linear1.weight", "video_encoder.transformer_encoder.layers.0.self_attn.in_proj_weight",
+           "video_encoder.transformer_encoder.layers.{elast}.linear2.weight", "video_encoder.unify.0.weight")
+
+
+def make_extra(ref, tokdir):
+    """Round-2 anchors (VERDICT r1 "What's missing" 1-3), all from the REAL reference on CPU:
+      bench64   the bench workload itself: shipped JSON dims, B = 64, un-padded, fwd + bwd (loss, slices, gradient norms and
+                strided per-element gradient samples)
+      cfg5      BASELINE cfg 5 dims: 6 enc + 6 dec layers, d 768, T = 32 (M = 33), B = 16
+      evalfast  the reference AS RUN by val_epoch / eval.py: eval() + no_grad + padded video batch with the torch
+                nested-tensor fast path ENABLED (padded memory rows become LayerNorm(0) = norm.bias)
+      decode256 BASELINE cfg 3: greedy decode, B = 256, max_len 30, token ids + per-step top-1/top-2 logit margins
+    """
+    anchors = {"torch": torch.__version__, "seed_model": 666, "seed_inputs": 1234}
+    samples = {}
+
+    def build(enc_layers, dec_layers):
+        cfg = ref_shims.shipped_model_config(tokdir)
+        cfg["video_encoder"]["layer"] = enc_layers
+        cfg["caption_decoder"]["layer"] = dec_layers
+        torch.manual_seed(666)
+        m = ref.MMT4Caption.MMT4Caption(cfg, device=CPU)
+        m.mode("caption")
+        m.eval()
+        return m
+
+    def fwd_bwd(model, tag, B, T, padded):
+        x, vm, tok = synth_inputs(B, T, 512, 21, 30522, 1234, padded=padded)
+        model.zero_grad(set_to_none=True)
+        mem, _, _ = model.video_encoder([x], [vm])
+        logits, loss = model.cap_decoder(mem, tok, tok == 0)
+        loss.backward()
+        grads = {k: p.grad for k, p in model.named_parameters() if p.grad is not None}
+        Ld = len(model.cap_decoder.decoder.layers)
+        Le = len(model.video_encoder.transformer_encoder.layers)
+        for name in SAMPLED:
+            k = name.format(last=Ld - 1, elast=Le - 1)
+            g, stride = sample_grid(grads[k])
+            samples[f"{tag}/grad/{k}"] = g.numpy()
+            samples[f"{tag}/stride/{k}"] = np.array(stride)
+        samples[f"{tag}/memory_rows"] = mem.detach()[::max(1, B // 4), ::4, ::16].contiguous().numpy()
+        samples[f"{tag}/logits_rows"] = logits.detach()[::max(1, B // 4), ::5, ::509].contiguous().numpy()
+        return {"B": B, "T": T, "padded": padded, "loss": float(loss), "mean_abs_logits": float(logits.abs().mean()),
+                "memory_0_0_0:6": mem[0, 0, :6].tolist(), "logits_0_0_0:6": logits[0, 0, :6].tolist(),
+                "logits_last_-6:": logits[-1, -1, -6:].tolist(),
+                "grad_norms": {k: float(g.double().norm()) for k, g in grads.items()}}
+
+    torch.backends.mha.set_fastpath_enabled(False)
+    model = build(1, 3)
+    anchors["bench64"] = fwd_bwd(model, "bench64", 64, 12, padded=False)
+    print("bench64 loss", anchors["bench64"]["loss"])
+
+    # ---- evalfast: what val_epoch (train.py:151-168) / eval.py:140 actually execute -------------------------------------
+    x, vm, tok = synth_inputs(8, 12, 512, 21, 30522, 1234, padded=True, vid_padded=True)
+    rec = {}
+    for fast in (False, True):
+        torch.backends.mha.set_fastpath_enabled(fast)
+        with torch.no_grad():
+            mem, gm, _ = model.video_encoder([x], [vm])
+            logits, loss = model.cap_decoder(mem, tok, tok == 0)
+        ys, strings = ref_greedy(ref, model.video_encoder, model.cap_decoder, x, vm, max_len=6)
+        key = "fast" if fast else "slow"
+        rec[key] = {"loss": float(loss), "greedy_ys": ys.tolist(), "mean_abs_logits": float(logits.abs().mean())}
+        samples[f"evalfast/{key}/memory"] = mem[:, :, ::16].contiguous().numpy()
+        samples[f"evalfast/{key}/logits_rows"] = logits[:, ::5, ::509].contiguous().numpy()
+    samples["evalfast/vid_pad"] = vm.numpy()
+    samples["evalfast/norm_bias"] = model.video_encoder.transformer_encoder.norm.bias.detach()[::16].numpy()
+    anchors["evalfast"] = rec
+    torch.backends.mha.set_fastpath_enabled(False)
+    print("evalfast loss slow/fast", rec["slow"]["loss"], rec["fast"]["loss"])
+
+    # ---- decode256: BASELINE cfg 3 ------------------------------------------------------------------------------------------
+    xb, vmb, _ = synth_inputs(256, 12, 512, 21, 30522, 1234, padded=False)
+    margins, tops = [], []
+    orig_dw = model.cap_decoder.decode_word
+
+    def spy(memories, tgt, mask):
+        lg = orig_dw(memories, tgt, mask)
+        t2 = lg.topk(2, dim=1).values
+        margins.append((t2[:, 0] - t2[:, 1]).clone())
+        tops.append(t2[:, 0].clone())
+        return lg
+    model.cap_decoder.decode_word = spy
+    ys, strings = ref_greedy(ref, model.video_encoder, model.cap_decoder, xb, vmb, max_len=30)
+    model.cap_decoder.decode_word = orig_dw
+    samples["decode256/ys"] = ys.numpy().astype(np.int32)
+    samples["decode256/margins"] = torch.stack(margins, 1).numpy()          # [256, 29]
+    samples["decode256/top1"] = torch.stack(tops, 1).numpy()
+    anchors["decode256"] = {"B": 256, "max_len": 30, "steps": len(margins), "min_margin": float(torch.stack(margins).min()),
+                            "strings_0:2": strings[:2]}
+    print("decode256", ys.shape, "min margin", anchors["decode256"]["min_margin"])
+    del model
+
+    model5 = build(6, 6)
+    anchors["cfg5"] = fwd_bwd(model5, "cfg5", 16, 32, padded=True)
+    xs, vms, _ = synth_inputs(16, 32, 512, 21, 30522, 1234, padded=True)
+    ys5, _ = ref_greedy(ref, model5.video_encoder, model5.cap_decoder, xs, vms, max_len=6)
+    anchors["cfg5"]["greedy_ys"] = ys5.tolist()
+    anchors["cfg5"]["state_checksum_sample"] = {k: v for k, v in list(checksum(model5.state_dict()).items())[:12]}
+    print("cfg5 loss", anchors["cfg5"]["loss"])
+    with open(os.path.join(GOLD, "extra_anchors.json"), "w") as f:
+        json.dump(anchors, f, indent=1)
+    np.savez_compressed(os.path.join(GOLD, "extra_samples.npz"), **samples)
+
+
 def main():
     os.makedirs(GOLD, exist_ok=True)
     torch.backends.mha.set_fastpath_enabled(False)
     torch.set_num_threads(os.cpu_count())
     ref = ref_shims.import_reference_model()
+    if "--extra" in sys.argv:
+        make_extra(ref, ref_shims.make_tokenizer_dir(os.path.join(ROOT, "gpurun_out", "_tok")))
+        return
     make_tiny(ref, "tiny_a", Din=24, d=32, h=2, F=48, Le=2, Ld=2, V=211, T=5, S1=8, B=4, alpha=0.5, seed=11)
     make_tiny(ref, "tiny_b", Din=16, d=48, h=2, F=64, Le=1, Ld=3, V=157, T=7, S1=6, B=3, alpha=1.0, seed=23)
     tokdir = ref_shims.make_tokenizer_dir(os.path.join(ROOT, "gpurun_out", "_tok"))

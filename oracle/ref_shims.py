@@ -15,7 +15,22 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("VCT_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _find_reference() -> str:
+    """/root/reference in the build container; on the GPU box the unmodified copy that baseline/install_reference.py
+    placed under the git-ignored baseline/_ref/ (it travels with the gpurun snapshot)."""
+    env = os.environ.get("VCT_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", os.path.join(_REPO, "baseline", "_ref")):
+        if os.path.isfile(os.path.join(cand, "model", "MMT4Caption.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 VOCAB_SIZE = 30522
 
 

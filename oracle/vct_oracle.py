@@ -144,8 +144,13 @@ def _count_layers(sd: Dict[str, Tensor], prefix: str) -> int:
 #           aggregation "avg", do_norm False -- the branch the shipped JSON selects)
 # --------------------------------------------------------------------------
 def encoder_forward(sd: Dict[str, Tensor], feats: Tensor, pad_mask: Optional[Tensor], nhead: int,
-                    prefix: str = "video_encoder.") -> Tensor:
-    """feats [B,T,Din] fp32, pad_mask bool [B,T] (True = ignore) or None -> memory [B,T+1,d]."""
+                    prefix: str = "video_encoder.", eval_fastpath: bool = False) -> Tensor:
+    """feats [B,T,Din] fp32, pad_mask bool [B,T] (True = ignore) or None -> memory [B,T+1,d].
+
+    eval_fastpath: what ``val_epoch`` (train.py:151-168) and ``eval.py:140`` actually execute -- ``eval()`` +
+    ``no_grad`` + a key-padding mask make ``nn.TransformerEncoder`` take torch's nested-tensor fast path
+    (torch/nn/modules/transformer.py:452-548), which zero-fills the padded positions before the final LayerNorm:
+    memory rows of padded frames become ``LayerNorm(0) = norm.bias``; valid rows are unchanged."""
     B, T, _ = feats.shape
     u = feats @ sd[prefix + "unify.0.weight"].T + sd[prefix + "unify.0.bias"]          # :246
     g = u.mean(dim=1, keepdim=True)            # :248-250, avg over ALL T incl. padded frames (Q4)
@@ -162,6 +167,8 @@ def encoder_forward(sd: Dict[str, Tensor], feats: Tensor, pad_mask: Optional[Ten
                    sd[p + "self_attn.out_proj.weight"], sd[p + "self_attn.out_proj.bias"], nhead, add_mask)
         x = layer_norm(x + a, sd[p + "norm1.weight"], sd[p + "norm1.bias"])
         x = layer_norm(x + _ffn(x, sd, p), sd[p + "norm2.weight"], sd[p + "norm2.bias"])
+    if eval_fastpath and pad_mask is not None:
+        x = x.masked_fill(full[:, :, None], 0.0)
     return layer_norm(x, sd[prefix + "transformer_encoder.norm.weight"], sd[prefix + "transformer_encoder.norm.bias"])
 
 
@@ -230,14 +237,14 @@ def sce_loss(logits: Tensor, labels: Tensor, alpha: float, beta: float, pad_id: 
 # whole path
 # --------------------------------------------------------------------------
 def caption_forward(sd: Dict[str, Tensor], feats: Tensor, vid_pad: Optional[Tensor], ids: Tensor,
-                    enc_nhead: int, dec_nhead: int, alpha: float, pad_id: int = 0
+                    enc_nhead: int, dec_nhead: int, alpha: float, pad_id: int = 0, eval_fastpath: bool = False
                     ) -> Tuple[Tensor, Tensor, Tensor]:
     """model/MMT4Caption.py:114-121 with pre-tokenised ids [B,S+1].
 
     Returns (memory, logits [B,S,V], loss).  tgt_in = ids[:, :-1], tgt_out =
     ids[:, 1:], pad = (ids == pad_id)[:, :-1]  (model/CapDecoder.py:43-45).
     """
-    memory = encoder_forward(sd, feats, vid_pad, enc_nhead)
+    memory = encoder_forward(sd, feats, vid_pad, enc_nhead, eval_fastpath=eval_fastpath)
     tgt_in, tgt_out = ids[:, :-1], ids[:, 1:]
     pad_in = (ids == pad_id)[:, :-1]
     h = decoder_hidden(sd, memory, tgt_in, pad_in, dec_nhead)
@@ -275,23 +282,29 @@ def decode_word(sd: Dict[str, Tensor], memory: Tensor, ys: Tensor, dec_nhead: in
 
 
 def greedy_decode_ids(sd: Dict[str, Tensor], feats: Tensor, vid_pad: Optional[Tensor], enc_nhead: int,
-                      dec_nhead: int, max_len: int = 30, start_id: int = 101, end_id: int = 102) -> Tensor:
+                      dec_nhead: int, max_len: int = 30, start_id: int = 101, end_id: int = 102,
+                      eval_fastpath: bool = False, return_margins: bool = False):
     """model/MMT4Caption.py:146-172: returns ys [B, <=max_len] (incl. the start token).
 
     All rows keep generating until every row has produced ``end_id`` at least
     once (Q11); argmax ties resolve to the lowest index (torch.max).
     """
     B = feats.shape[0]
-    memory = encoder_forward(sd, feats, vid_pad, enc_nhead)
+    memory = encoder_forward(sd, feats, vid_pad, enc_nhead, eval_fastpath=eval_fastpath)
     ys = torch.full((B, 1), start_id, dtype=torch.long)
     ended = torch.zeros(B, dtype=torch.bool)
+    margins = []
     for _ in range(max_len - 1):
-        nxt = decode_word(sd, memory, ys, dec_nhead).argmax(dim=1)
+        lg = decode_word(sd, memory, ys, dec_nhead)
+        nxt = lg.argmax(dim=1)
+        if return_margins:
+            t2 = lg.topk(2, dim=1).values
+            margins.append(t2[:, 0] - t2[:, 1])
         ys = torch.cat([ys, nxt[:, None]], dim=1)
         ended |= nxt == end_id
         if bool(ended.all()):
             break
-    return ys
+    return (ys, torch.stack(margins, 1)) if return_margins else ys
 
 
 def cut_caption_ids(row: List[int], end_id: int = 102) -> List[int]:

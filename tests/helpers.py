@@ -66,3 +66,26 @@ def synth_inputs(B, T, Din, S1, V, seed=1234, padded=True, vid_padded=False):
             vm[b, vlen[b]:] = True
             x[b, vlen[b]:] = 0.0
     return x, vm, tok
+
+
+def load_extra():
+    """Round-2 anchors made by ``oracle/make_golden.py --extra`` -> (anchors dict, samples npz)."""
+    with open(os.path.join(GOLD, "extra_anchors.json")) as f:
+        anchors = json.load(f)
+    return anchors, np.load(os.path.join(GOLD, "extra_samples.npz"))
+
+
+def sampled(t, stride):
+    return t[::int(stride[0]), ::int(stride[1])]
+
+
+def dropin_state_dict(tokenizer_dir, enc_layers=1, dec_layers=3, embed_dim=768):
+    """state_dict of OUR MMT4Caption constructed on CPU with the reference's seed: bit-identical to the reference
+    constructor's (tests/test_host.py checks the checksums), so the oracle can be run at full size on the GPU box where
+    /root/reference does not exist."""
+    from model.MMT4Caption import MMT4Caption
+    from vct.synthetic import shipped_model_config
+    torch.manual_seed(666)
+    m = MMT4Caption(shipped_model_config(tokenizer_dir, embed_dim=embed_dim, enc_layers=enc_layers, dec_layers=dec_layers),
+                    device=torch.device("cpu"))
+    return {k: v.detach().clone() for k, v in m.state_dict().items()}

@@ -8,7 +8,7 @@ import torch
 
 from oracle import ref_shims
 from oracle import vct_oracle as O
-from helpers import load_tiny, load_anchors, synth_inputs
+from helpers import load_tiny, load_anchors, synth_inputs, load_extra, sampled, dropin_state_dict
 
 TOL = dict(rtol=2e-5, atol=2e-6)
 
@@ -77,6 +77,75 @@ def test_adam_matches_torch_optim():
         opt.step()
         po, m, v = O.adam_step(po, gr, m, v, step, 1e-4)
         torch.testing.assert_close(po, p.detach(), rtol=1e-6, atol=1e-7)
+
+
+# ---- round-2 anchors (oracle/make_golden.py --extra), produced by the real reference ---------------------------------
+@pytest.mark.parametrize("tag,Le,Ld,B,T,padded", [("bench64", 1, 3, 64, 12, False), ("cfg5", 6, 6, 16, 32, True)])
+def test_oracle_matches_extra_anchors(tokenizer_dir, tag, Le, Ld, B, T, padded):
+    """The bench workload itself (B = 64, un-padded) and BASELINE cfg 5 dims (6 + 6 layers, T = 32 -> M = 33): loss,
+    slices, gradient norms and strided PER-ELEMENT gradient samples of the reference vs the oracle."""
+    anchors, smp = load_extra()
+    a = anchors[tag]
+    sd = dropin_state_dict(tokenizer_dir, Le, Ld)
+    x, vm, tok = synth_inputs(B, T, 512, 21, 30522, 1234, padded=padded)
+    loss, grads = O.caption_grads(sd, x, vm, tok, 8, 8, 0.5)
+    assert abs(float(loss) - a["loss"]) < 2e-6 * a["loss"] + 2e-6
+    for k, want in a["grad_norms"].items():
+        if k.startswith("matching."):
+            continue
+        got = float(grads[k].double().norm())
+        assert abs(got - want) <= 2e-4 * want + 1e-9, (k, got, want)
+    n = 0
+    for key in smp.files:
+        if key.startswith(tag + "/grad/"):
+            k = key[len(tag + "/grad/"):]
+            got = sampled(grads[k], smp[f"{tag}/stride/{k}"])
+            want = torch.from_numpy(smp[key])
+            scale = float(want.abs().max())
+            torch.testing.assert_close(got, want, rtol=2e-4, atol=2e-5 * scale + 1e-10, msg=lambda m, k=k: f"{k}: {m}")
+            n += 1
+    assert n == 8
+
+
+def test_oracle_eval_fastpath_matches_reference(tokenizer_dir):
+    """val_epoch / eval.py run eval() + no_grad + masks, i.e. torch's nested-tensor fast path: padded memory
+    rows are LayerNorm(0) = norm.bias, which changes the (never masked) cross-attention and so the validation loss and
+    the greedy ids of padded batches.  The oracle restates both behaviours; both are pinned here."""
+    anchors, smp = load_extra()
+    sd = dropin_state_dict(tokenizer_dir)
+    x, vm, tok = synth_inputs(8, 12, 512, 21, 30522, 1234, padded=True, vid_padded=True)
+    assert torch.equal(vm, torch.from_numpy(smp["evalfast/vid_pad"]))
+    for key, fast in (("slow", False), ("fast", True)):
+        mem, logits, loss = O.caption_forward(sd, x, vm, tok, 8, 8, 0.5, eval_fastpath=fast)
+        assert abs(float(loss) - anchors["evalfast"][key]["loss"]) < 1e-5
+        torch.testing.assert_close(mem[:, :, ::16], torch.from_numpy(smp[f"evalfast/{key}/memory"]), rtol=1e-4, atol=2e-5)
+        ys = O.greedy_decode_ids(sd, x, vm, 8, 8, max_len=6, eval_fastpath=fast)
+        assert ys.tolist() == anchors["evalfast"][key]["greedy_ys"]
+    mem, _, _ = O.caption_forward(sd, x, vm, tok, 8, 8, 0.5, eval_fastpath=True)
+    full = torch.cat([torch.zeros(8, 1, dtype=torch.bool), vm], 1)
+    want = torch.from_numpy(smp["evalfast/norm_bias"]).expand(int(full.sum()), -1)
+    torch.testing.assert_close(mem[full][:, ::16], want, rtol=0, atol=1e-6)
+    assert abs(anchors["evalfast"]["slow"]["loss"] - anchors["evalfast"]["fast"]["loss"]) > 1e-3
+
+
+def test_oracle_greedy_decode_cfg3_b256_matches_reference(tokenizer_dir):
+    """BASELINE cfg 3: greedy decode, B = 256, max_len 30 (random weights never emit [SEP]: 29 steps).  Ids must equal
+    the reference's wherever the reference's own top-1/top-2 logit margin leaves no doubt; rows are compared up to their
+    first ambiguous step (margin < 1e-4: fp32 summation order alone can flip those -- the smallest margin among the
+    7424 argmaxes is 5.7e-6)."""
+    anchors, smp = load_extra()
+    sd = dropin_state_dict(tokenizer_dir)
+    x, vm, _ = synth_inputs(256, 12, 512, 21, 30522, 1234, padded=False)
+    want, margins = torch.from_numpy(smp["decode256/ys"]).long(), torch.from_numpy(smp["decode256/margins"])
+    ys = O.greedy_decode_ids(sd, x[:64], vm[:64], 8, 8, max_len=30)          # a quarter of the batch keeps the CPU suite short
+    assert ys.shape == (64, 30)
+    ok_rows = 0
+    for b in range(64):
+        amb = (margins[b] < 1e-4).nonzero()
+        upto = int(amb[0]) + 1 if len(amb) else 30                 # tokens 0..upto-1 are unambiguous
+        assert ys[b, :upto].tolist() == want[b, :upto].tolist(), b
+        ok_rows += int(ys[b].tolist() == want[b].tolist())
+    assert ok_rows >= 60
 
 
 # ---- live reference (build container only) -------------------------------------------------

@@ -646,6 +646,26 @@ extern "C" int vct_cast(const float* src, void* dst, int dst_dtype, long long n,
 }
 
 // ------------------------------------------------------------------------------------------------
+// zero the rows of x [R, d] whose mask byte is set (eval-mode fast path of nn.TransformerEncoder)
+// ------------------------------------------------------------------------------------------------
+__global__ void zero_rows_kernel(float* __restrict__ x, const unsigned char* __restrict__ mask, int R, int d) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nv = d >> 2;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)R * nv) return;
+    const int r = (int)(i / nv);
+    if (mask[r]) st4(x + i * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+extern "C" int vct_zero_rows(float* x, const unsigned char* mask, int R, int d, vct_stream_t stream) {
+    VCT_REQUIRE(x && mask && R > 0 && d > 0 && d % 4 == 0, "vct_zero_rows: bad argument (d %% 4 must be 0)");
+    const long long n = (long long)R * (d / 4);
+    vct::launch(zero_rows_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, mask, R, d);
+    return check_launch("vct_zero_rows");
+}
+
+// ------------------------------------------------------------------------------------------------
 // greedy argmax + append
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

@@ -100,7 +100,10 @@ class MultiModalEncoder(nn.Module):
     def forward(self, srcs: List[Tensor], src_padding_masks: Optional[List[Tensor]]):
         """srcs: [Tensor[B,T,Din]] (one modality); masks: [Bool[B,T]] (True = padded) or None
         -> (memory [B,T+1,E], global_masks [B,T+1] | None, memory[:, 0])   (model/MMEncoder.py:244-276).
-        Padded rows follow the TRAINING-path semantics everywhere (no nested-tensor zero-fill)."""
+        Padded frames: in training (and whenever gradients are enabled) their memory rows hold the values the layers
+        compute, as in the reference; under eval() + no_grad with masks -- val_epoch / eval.py -- the reference's
+        nn.TransformerEncoder takes torch's nested-tensor fast path and those rows become norm.bias, which
+        is reproduced here (tests/golden "evalfast")."""
         from vct.functional import EncoderFn
         if len(srcs) != 1:
             raise NotImplementedError("single modality only (see class docstring)")
@@ -108,7 +111,8 @@ class MultiModalEncoder(nn.Module):
         feats = srcs[0]
         mask = src_padding_masks[0] if src_padding_masks is not None else None
         params = [p for _, p in self.named_parameters()]
-        memory = EncoderFn.apply(eng, self, feats, mask, int(self._vct_S_hint), *params)
+        fast = (not self.training) and (not torch.is_grad_enabled()) and mask is not None
+        memory = EncoderFn.apply(eng, self, feats, mask, int(self._vct_S_hint), fast, *params)
         global_masks = None
         if mask is not None:
             global_masks = torch.cat([torch.zeros(mask.shape[0], 1, dtype=torch.bool, device=mask.device), mask], dim=1)

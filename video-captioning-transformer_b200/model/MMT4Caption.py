@@ -155,7 +155,7 @@ class MMT4Caption(nn.Module):
         feats = video_feat[0].to(eng.device)
         mask = video_masks[0].to(eng.device) if video_masks is not None else None
         return eng.greedy_decode(feats, mask, max_len, self.cap_preprocessor.start_id, self.cap_preprocessor.end_id,
-                                 sync_every=sync_every)
+                                 sync_every=sync_every, eval_fastpath=not self.training)
 
     def _greedy_patched(self, video_feat, video_masks, max_len):
         """predict_video.py:43-79,126-130 rebinds every decoder layer's ``forward`` to capture
@@ -165,7 +165,7 @@ class MMT4Caption(nn.Module):
         feats = video_feat[0].to(eng.device)
         mask = video_masks[0].to(eng.device) if video_masks is not None else None
         ys, probs = eng.greedy_decode(feats, mask, max_len, self.cap_preprocessor.start_id,
-                                      self.cap_preprocessor.end_id, want_probs=True)
+                                      self.cap_preprocessor.end_id, want_probs=True, eval_fastpath=not self.training)
         for layer, pr in zip(self.cap_decoder.decoder.layers, probs):
             layer.mha = pr
         return ys

@@ -499,7 +499,7 @@ class CaptionEngine:
     # ------------------------------------------------------------------------------------------
     # forward plan
     # ------------------------------------------------------------------------------------------
-    def _build_encoder(self, plan: Plan, ws, p_drop: float):
+    def _build_encoder(self, plan: Plan, ws, p_drop: float, zero_pad: bool = False):
         D, lib = self.dims, self.lib
         d, B, T, M = D.d, ws.B, ws.T, ws.M
         Re = B * M
@@ -537,6 +537,11 @@ class CaptionEngine:
                          e.stats[2].data_ptr(), e.stats[3].data_ptr(), Re, p_drop, _enc_site(l, 3))
             x, x_c = e.x2, e.x2_c
         ws.enc_out = x
+        if zero_pad:
+            # eval() + no_grad + key-padding mask: torch's nested-tensor fast path zero-fills padded positions before the
+            # final norm -- reproduced so validation loss / greedy captions of padded batches match the
+            # reference as it is actually run (train.py:151-168, eval.py:140)
+            plan.add("vct_zero_rows", lib.vct_zero_rows, x.data_ptr(), ws.vid_pad.data_ptr(), Re, d)
         self._ln_fwd(plan, "enc.norm", None, x.data_ptr(), "video_encoder.transformer_encoder.norm.weight",
                      "video_encoder.transformer_encoder.norm.bias", ws.mem.data_ptr(),
                      ws.mem_c.data_ptr() if cd == BF16 else None, None, ws.mem_stats[0].data_ptr(),
@@ -638,13 +643,17 @@ class CaptionEngine:
             ws.plans[key] = p
         return ws.plans[key]
 
-    def plan_encode(self, ws) -> Plan:
-        if "encode" not in ws.plans:
+    def plan_encode(self, ws, zero_pad: bool = False) -> Plan:
+        """zero_pad: eval-mode fast-path semantics for padded frames (see _build_encoder); never used in training."""
+        key = ("encode", bool(zero_pad))
+        if key not in ws.plans:
+            if zero_pad and ws.training:
+                raise RuntimeError("zero_pad is the eval()/no_grad behaviour of the reference's encoder")
             p = Plan()
             p.ws = ws
-            self._build_encoder(p, ws, float(self.dims.dropout) if ws.training else 0.0)
-            ws.plans["encode"] = p
-        return ws.plans["encode"]
+            self._build_encoder(p, ws, float(self.dims.dropout) if ws.training else 0.0, zero_pad=zero_pad)
+            ws.plans[key] = p
+        return ws.plans[key]
 
     # ------------------------------------------------------------------------------------------
     # backward plan
@@ -1020,7 +1029,7 @@ class CaptionEngine:
 
     @torch.no_grad()
     def greedy_decode(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], max_len: int, start_id: int,
-                      end_id: int, sync_every: int = 1, want_probs: bool = False):
+                      end_id: int, sync_every: int = 1, want_probs: bool = False, eval_fastpath: bool = True):
         """Returns ys [B, n] (device int64, incl. the start token).  Same stopping rule as the reference:
         stop once every row has produced end_id (checked every ``sync_every`` tokens; the reference checks
         every token through ``.tolist()``, model/MMT4Caption.py:168-172).  Checking less often only appends
@@ -1031,7 +1040,10 @@ class CaptionEngine:
         B, T, _ = feats.shape
         enc_ws = self.workspace(B, T, 1, False)
         self.stage_inputs(enc_ws, feats, vid_pad, None)
-        self.run(self.plan_encode(enc_ws))
+        # greedy decoding runs under eval() + no_grad in the reference (eval.py:125-142): with masks the encoder takes
+        # the nested-tensor fast path (padded memory rows = norm.bias); predict_video.py passes no masks
+        self.run(self.plan_encode(enc_ws, zero_pad=(vid_pad is not None and eval_fastpath)))
+        enc_ws.enc_version += 1
         dws = self.decode_workspace(B, T, max_len)
         dws.ys.zero_()
         dws.ys[:, 0] = start_id

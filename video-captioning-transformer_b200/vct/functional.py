@@ -56,7 +56,7 @@ class EncoderFn(torch.autograd.Function):
     """MultiModalEncoder.forward (model/MMEncoder.py:244-276) -> memory [B, T+1, d]."""
 
     @staticmethod
-    def forward(ctx, engine: CaptionEngine, module, feats, vid_pad, S_hint: int, *params):
+    def forward(ctx, engine: CaptionEngine, module, feats, vid_pad, S_hint: int, zero_pad: bool, *params):
         B, T, _ = feats.shape
         training = module.training
         ws = engine.workspace(B, T, S_hint, training)
@@ -64,7 +64,7 @@ class EncoderFn(torch.autograd.Function):
         engine.refresh_shadow()
         ctx.rng_step = engine.next_rng_step() if training else None
         engine.stage_inputs(ws, feats, vid_pad, None)
-        engine.run(engine.plan_encode(ws))
+        engine.run(engine.plan_encode(ws, zero_pad=bool(zero_pad) and not training))
         ws.enc_version += 1
         ctx.engine, ctx.ws, ctx.module, ctx.version = engine, ws, module, ws.enc_version
         out = ws.mem.view(B, T + 1, engine.dims.d).clone()
@@ -87,7 +87,7 @@ class EncoderFn(torch.autograd.Function):
             ws.g_mem.copy_(dmem.reshape(ws.g_mem.shape))
         engine.run(engine.plan_backward(ws, sce_first=False, part="enc"))
         grads = _grads_for(engine, "video_encoder.", named)
-        return (None, None, None, None, None, *grads)
+        return (None, None, None, None, None, None, *grads)
 
 
 class DecoderFn(torch.autograd.Function):
