@@ -1,23 +1,34 @@
 #!/usr/bin/env python
-"""Benchmark of the caption hot path (BASELINE.json metric: captions/sec of one train step).
+"""Benchmark of the caption hot path (BASELINE.json metric: captions/sec of one train step; attention kernel
+roofline fractions).
 
-    python bench.py --gpus N --steps K --warmup W            # our arm (B200 kernels)
-    python bench.py --impl reference --gpus N --steps K ...   # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W                    # our arm, BASELINE configs[1] (cfg2)
+    python bench.py --config {cfg1,cfg1-literal,cfg3,cfg4,cfg5,cfg5-b128} ...   # the other BASELINE configs
+    python bench.py --impl reference [--config ...] --steps K --warmup W         # the reference's own CPU path
 
-Workload (config.workload): BASELINE configs[1] -- the shipped MSR-VTT clip4clip model (1 encoder + 3
-decoder layers, d_model 768, 8 heads, FFN 2048, vocab 30522, dropout 0.3, SCE loss), batch 64 per GPU,
-synthetic [64, 12, 512] frame features + random token ids (S = 20 decoder positions), one full train
-step = forward + backward + gradient all-reduce (N > 1) + Adam.  Weak scaling: 64 captions per GPU.
+Workloads (config.workload), all synthetic [B, T, 512] frame features + random token ids, S = 20 decoder positions:
+  cfg2 (default)  shipped MSR-VTT clip4clip model (1 enc + 3 dec layers, d 768, 8 heads, FFN 2048, V 30522, dropout 0.3,
+                  SCE loss), 64 captions per GPU, one train step = forward + backward + gradient exchange (N > 1) + Adam;
+                  weak scaling
+  cfg1 / cfg1-literal   B = 8 train step, shipped dims / the literal "2 enc + 2 dec, d 512" reading
+  cfg3            greedy decode (predict_video path), B = 256, max_len 30 (29 steps), captions/s
+  cfg4            train step, GLOBAL batch 512 over N GPUs (strong scaling: 512 / N per GPU)
+  cfg5 / cfg5-b128      6 enc + 6 dec layers, d 768, T = 32 (M = 33): global batch 128 over N GPUs / 128 per GPU
 
-Prints ONE JSON line (rank 0).  value = device-timed throughput with inputs resident in HBM; e2e = the
-same step driven through the public API with pinned HOST inputs (H2D copies + loss read-back inside the
-timed region).  roofline = the dominant kernel of the step, timed live with CUDA events.
+Prints ONE JSON line (rank 0).  value = device-timed throughput with inputs resident in HBM; e2e = the same workload
+driven through the public API with pinned HOST inputs (H2D copies + result read-back inside the timed region).
+roofline = the kernel family with the LARGEST SHARE of the step (rooflines = every family), timed live with CUDA events;
+traffic = dram bytes per launch from the committed ncu capture (profiles/r02_traffic.json) when present.
+cpu_baseline / --impl reference = the reference's own modules (baseline/_ref, unmodified) on the host cores, train mode
+with dropout 0.3 + torch.optim.Adam; gpu_reference = the same modules on this B200 through PyTorch's own sm_100 kernels
+(fp32 with TF32 off, and bf16 autocast): the "existing Blackwell path".
 """
 from __future__ import annotations
 
 import argparse
 import json
 import os
+import re
 import statistics
 import subprocess
 import sys
@@ -30,8 +41,24 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-WORKLOAD = "msrvtt-clip4clip 1enc+3dec d768 h8 ff2048 V30522 dropout0.3, train step, B=64/GPU, T=12, S=20"
-B_PER_GPU, T, DIN, S1 = 64, 12, 512, 21
+DIN, S1, V = 512, 21, 30522
+CONFIGS = {
+    #            kind     enc dec d    T   batch rule
+    "cfg1":         dict(kind="train", Le=1, Ld=3, d=768, T=12, per_gpu=8, scaling="weak",
+                         name="msrvtt-clip4clip 1enc+3dec d768 h8 ff2048 V30522 dropout0.3, train step, B=8/GPU, T=12, S=20"),
+    "cfg1-literal": dict(kind="train", Le=2, Ld=2, d=512, T=12, per_gpu=8, scaling="weak",
+                         name="cfg1 literal reading: 2enc+2dec d512 h8 ff2048 V30522 dropout0.3, train step, B=8/GPU, T=12, S=20"),
+    "cfg2":         dict(kind="train", Le=1, Ld=3, d=768, T=12, per_gpu=64, scaling="weak",
+                         name="msrvtt-clip4clip 1enc+3dec d768 h8 ff2048 V30522 dropout0.3, train step, B=64/GPU, T=12, S=20"),
+    "cfg3":         dict(kind="decode", Le=1, Ld=3, d=768, T=12, per_gpu=256, scaling="weak", max_len=30,
+                         name="msvd-clip4clip 1enc+3dec d768 h8 ff2048 V30522, greedy decode, B=256/GPU, T=12, max_len=30 (29 steps)"),
+    "cfg4":         dict(kind="train", Le=1, Ld=3, d=768, T=12, global_batch=512, scaling="strong",
+                         name="msrvtt-clip4clip 1enc+3dec d768, train step, GLOBAL batch 512 (512/N per GPU), T=12, S=20"),
+    "cfg5":         dict(kind="train", Le=6, Ld=6, d=768, T=32, global_batch=128, scaling="strong",
+                         name="scaled 6enc+6dec d768 h8 ff2048, T=32 (M=33), train step, GLOBAL batch 128 (128/N per GPU), S=20"),
+    "cfg5-b128":    dict(kind="train", Le=6, Ld=6, d=768, T=32, per_gpu=128, scaling="weak",
+                         name="scaled 6enc+6dec d768 h8 ff2048, T=32 (M=33), train step, B=128/GPU, S=20"),
+}
 
 
 def measured_peaks():
@@ -39,8 +66,18 @@ def measured_peaks():
     if os.path.isfile(p):
         with open(p) as f:
             d = json.load(f)
-        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]), "src": "measured"}
-    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "src": "fallback"}
+        return {"hbm_gbs": d["hbm_gbs"], "tflops": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "tflops_burst": d["bf16_tflops"], "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "src": "fallback"}
+
+
+def ncu_traffic():
+    """{kernel-name regex: dram bytes per launch} from the committed `ncu --set full` capture of this command."""
+    p = os.path.join(ROOT, "profiles", "r02_traffic.json")
+    if os.path.isfile(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
 
 
 class ClockSampler:
@@ -81,95 +118,197 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def tokenizer_dir():
+    from vct.synthetic import make_tokenizer_dir
+    return make_tokenizer_dir(os.path.join(ROOT, "gpurun_out", "_tok"))
+
+
+def model_config(cfg, tokdir):
+    from vct.synthetic import shipped_model_config
+    return shipped_model_config(tokdir, embed_dim=cfg["d"], enc_layers=cfg["Le"], dec_layers=cfg["Ld"])
+
+
+def per_gpu_batch(cfg, world, override=None):
+    if override:
+        return override
+    if "per_gpu" in cfg:
+        return cfg["per_gpu"]
+    if cfg["global_batch"] % world:
+        raise SystemExit(f"global batch {cfg['global_batch']} is not divisible by {world} ranks")
+    return cfg["global_batch"] // world
+
+
 # ---------------------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port of the reference algorithm on the host cores
+# the reference on the host cores (reference arm / cpu_baseline) and on the GPU (gpu_reference)
 # ---------------------------------------------------------------------------------------------------
-def cpu_train_steps(batch: int, steps: int, warmup: int, threads: int):
-    """fp32 CPU train step of the reference algorithm (oracle/vct_oracle.py restatement: forward,
-    autograd backward, Adam) on synthetic inputs.  Returns (median seconds per step, steps run).
-    NOTE: dropout (p = 0.3 in the reference) is not applied by the port, which only makes this baseline
-    faster than the reference's own CPU path (its bernoulli masks cost ~14 % of a step)."""
+def build_reference(cfg, device):
+    """The UNMODIFIED reference MMT4Caption (baseline/_ref, or /root/reference in the build container) with the offline
+    shims (tokenizer directory, clip stub).  Returns (model, kind) or (None, why)."""
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        return None, "baseline/_ref not installed (python baseline/install_reference.py)"
+    ref = ref_shims.import_reference_model()
+    torch.manual_seed(666)
+    model = ref.MMT4Caption.MMT4Caption(model_config(cfg, tokenizer_dir()), device=device)
+    model.mode("caption")
+    return model.to(device), "reference"
+
+
+def reference_train_steps(model, x, vm, tok, steps, warmup, autocast=None):
+    """Loop body of train.py:119-126 on pre-tokenised ids: forward (encoder + decoder + SCE loss), zero_grad, backward,
+    Adam.  Returns the per-step wall times (s)."""
+    model.train()
+    opt = torch.optim.Adam(filter(lambda p: p.requires_grad, model.parameters()), lr=1e-4, betas=(0.9, 0.999))
+    cuda = x.is_cuda
+    times = []
+    for it in range(warmup + steps):
+        if cuda:
+            torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        with (torch.autocast("cuda", dtype=autocast) if autocast is not None else torch.autocast("cpu", enabled=False)):
+            mem, _, _ = model.video_encoder([x], [vm])
+            _, loss = model.cap_decoder(mem, tok, tok == 0)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        _ = loss.item()
+        if cuda:
+            torch.cuda.synchronize()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def reference_decode(model, x, vm, max_len, reps, warmup=1):
+    """MMT4Caption.greedy_decode's loop (model/MMT4Caption.py:156-172) with ids kept as ids."""
+    model.eval()
+    times = []
+    with torch.no_grad():
+        for it in range(warmup + reps):
+            if x.is_cuda:
+                torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            memory, _, _ = model.video_encoder([x], [vm])
+            ys = torch.full((x.shape[0], 1), 101, dtype=torch.long, device=x.device)
+            for _ in range(max_len - 1):
+                logits = model.cap_decoder.decode_word(memory, ys, None)
+                ys = torch.cat([ys, logits.argmax(dim=1, keepdim=True)], dim=1)
+                if bool((ys == 102).any(dim=1).all()):
+                    break
+            if x.is_cuda:
+                torch.cuda.synchronize()
+            if it >= warmup:
+                times.append(time.perf_counter() - t0)
+    return times
+
+
+def cpu_baseline(cfg, steps, warmup, batch=None):
+    """The reference's CPU path on a bounded sample of the workload.  Returns the cpu_baseline dict."""
+    from vct.synthetic import synth_batch
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    cpu = torch.device("cpu")
+    model, kind = build_reference(cfg, cpu)
+    if model is None:
+        return _cpu_baseline_port(cfg, steps, warmup, threads, kind)
+    if cfg["kind"] == "decode":
+        B = batch or 32
+        x, vm, _ = synth_batch(B, cfg["T"], DIN, S1)
+        t = reference_decode(model, x, vm, cfg["max_len"], max(1, min(steps, 3)), warmup=1)
+        sec = statistics.median(t)
+        return {"value": B / sec, "unit": "captions/s", "cores": threads, "kind": kind, "ms": sec * 1e3,
+                "sample": f"{len(t)} greedy decodes of batch {B} (the reference's recompute-everything loop, max_len {cfg['max_len']}, "
+                          f"fp32, eval), median"}
+    B = batch or min(64, cfg.get("per_gpu", 64))
+    x, vm, tok = synth_batch(B, cfg["T"], DIN, S1)
+    t = reference_train_steps(model, x, vm, tok, steps, warmup)
+    sec = statistics.median(t)
+    return {"value": B / sec, "unit": "captions/s", "cores": threads, "kind": kind, "ms": sec * 1e3,
+            "sample": f"{len(t)} train steps of batch {B} (the reference's own modules: fwd + bwd + torch.optim.Adam, fp32, "
+                      f"train mode with dropout 0.3, pre-tokenised ids), median"}
+
+
+def _cpu_baseline_port(cfg, steps, warmup, threads, why):
+    """baseline/_ref missing: time the oracle restatement instead (kind "port")."""
     from oracle import vct_oracle as O
     from vct.synthetic import synth_batch
-    torch.set_num_threads(threads)
-    d, Fd, V, H = 768, 2048, 30522, 8
-    g = torch.Generator().manual_seed(666)
-
-    def rnd(*shape, scale=0.02):
-        return (torch.randn(*shape, generator=g) * scale)
-
-    sd = {"video_encoder.unify.0.weight": rnd(d, DIN), "video_encoder.unify.0.bias": torch.zeros(d),
-          "video_encoder.temp_emb.pe": O.temporal_sinusoid_table(512, d).unsqueeze(0),
-          "video_encoder.transformer_encoder.norm.weight": torch.ones(d),
-          "video_encoder.transformer_encoder.norm.bias": torch.zeros(d),
-          "cap_decoder.decoder.norm.weight": torch.ones(d), "cap_decoder.decoder.norm.bias": torch.zeros(d),
-          "cap_decoder.generator.weight": rnd(V, d), "cap_decoder.generator.bias": torch.zeros(V),
-          "cap_decoder.tgt_to_emb.weight": rnd(V, d, scale=1.0),
-          "cap_decoder.positional_encoding.pos_embedding": O.sinusoid_table(5000, d)}
-
-    def layer(pre, cross):
-        for a in (["self_attn"] + (["multihead_attn"] if cross else [])):
-            sd[pre + a + ".in_proj_weight"] = rnd(3 * d, d); sd[pre + a + ".in_proj_bias"] = torch.zeros(3 * d)
-            sd[pre + a + ".out_proj.weight"] = rnd(d, d); sd[pre + a + ".out_proj.bias"] = torch.zeros(d)
-        sd[pre + "linear1.weight"] = rnd(Fd, d); sd[pre + "linear1.bias"] = torch.zeros(Fd)
-        sd[pre + "linear2.weight"] = rnd(d, Fd); sd[pre + "linear2.bias"] = torch.zeros(d)
-        for n in (("norm1", "norm2", "norm3") if cross else ("norm1", "norm2")):
-            sd[pre + n + ".weight"] = torch.ones(d); sd[pre + n + ".bias"] = torch.zeros(d)
-
-    layer("video_encoder.transformer_encoder.layers.0.", False)
-    for l in range(3):
-        layer(f"cap_decoder.decoder.layers.{l}.", True)
-    x, vm, tok = synth_batch(batch, T, DIN, S1)
-    state = {k: (torch.zeros_like(v), torch.zeros_like(v)) for k, v in sd.items()
-             if not k.endswith(("pos_embedding", "temp_emb.pe"))}
+    from model.MMT4Caption import MMT4Caption
+    torch.manual_seed(666)
+    m = MMT4Caption(model_config(cfg, tokenizer_dir()), device=torch.device("cpu"))
+    sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+    B = min(64, cfg.get("per_gpu", 64))
+    x, vm, tok = synth_batch(B, cfg["T"], DIN, S1)
+    state = {}
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        _, grads = O.caption_grads(sd, x, vm, tok, H, H, 0.5)
+        _, grads = O.caption_grads(sd, x, vm, tok, 8, 8, 0.5)
         for k, gk in grads.items():
-            m, v = state[k]
-            sd[k], m, v = O.adam_step(sd[k], gk, m, v, it + 1, 1e-4)
-            state[k] = (m, v)
-        dt = time.perf_counter() - t0
+            mm, vv = state.get(k, (torch.zeros_like(gk), torch.zeros_like(gk)))
+            sd[k], mm, vv = O.adam_step(sd[k], gk, mm, vv, it + 1, 1e-4)
+            state[k] = (mm, vv)
         if it >= warmup:
-            times.append(dt)
-    return statistics.median(times), len(times)
+            times.append(time.perf_counter() - t0)
+    sec = statistics.median(times)
+    return {"value": B / sec, "unit": "captions/s", "cores": threads, "kind": "port", "ms": sec * 1e3,
+            "sample": f"{len(times)} train steps of batch {B} (oracle port: fwd+bwd+Adam, fp32, no dropout; {why}), median"}
 
 
-def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+def run_reference_arm(args, cfg):
+    if int(os.environ.get("RANK", "0")) != 0:
         return
-    threads = os.cpu_count() or 1
-    # bound the run: probe one small step, then pick the per-step sample so the whole run stays ~2 minutes
-    t_probe, _ = cpu_train_steps(8, 1, 0, threads)
-    est64 = t_probe * 8 * 0.6
-    budget = 150.0
-    batch = 64
-    while batch > 8 and est64 * (batch / 64) * (args.steps + args.warmup) > budget:
-        batch //= 2
-    sec, n = cpu_train_steps(batch, args.steps, args.warmup, threads)
-    val = batch / sec
-    line = {"impl": "reference", "metric": "captions/sec (train step)", "value": val, "unit": "captions/s",
-            "n_gpus": args.gpus, "steps": n, "warmup": args.warmup, "ms_per_step": sec * 1e3,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "cpu_sample_batch": batch},
-            "cpu_baseline": {"value": val, "unit": "captions/s", "cores": threads, "kind": "port",
-                             "sample": f"{n} train steps of batch {batch} (fwd+bwd+Adam, fp32, torch CPU kernels, no dropout)"},
-            "e2e": {"value": val, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    cb = cpu_baseline(cfg, args.steps, args.warmup)
+    metric = "captions/sec (greedy decode)" if cfg["kind"] == "decode" else "captions/sec (train step)"
+    line = {"impl": "reference", "metric": metric, "value": cb["value"], "unit": "captions/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": cb["ms"],
+            "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": cfg["name"]},
+            "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": cb["value"], "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+def gpu_reference(cfg, B, dev, steps=12, warmup=4):
+    """The reference's own modules on THIS GPU through PyTorch's stock sm_100 kernels (cuBLAS + SDPA + ATen): fp32 with
+    TF32 off (the reference's precision) and under bf16 autocast.  Same synthetic batch, train mode, dropout 0.3, Adam."""
+    from vct.synthetic import synth_batch
+    out = {}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    for tag, ac in (("fp32", None), ("bf16_autocast", torch.bfloat16)):
+        try:
+            model, kind = build_reference(cfg, dev)
+            if model is None:
+                return {"unavailable": kind}
+            if cfg["kind"] == "decode":
+                if ac is not None:
+                    continue
+                x, vm, _ = synth_batch(B, cfg["T"], DIN, S1)
+                t = reference_decode(model, x.to(dev), vm.to(dev), cfg["max_len"], 3, warmup=1)
+            else:
+                x, vm, tok = synth_batch(B, cfg["T"], DIN, S1)
+                t = reference_train_steps(model, x.to(dev), vm.to(dev), tok.to(dev), steps, warmup, autocast=ac)
+            sec = statistics.median(t)
+            out[tag] = {"value": B / sec, "unit": "captions/s", "ms": sec * 1e3, "batch": B}
+        except Exception as e:                                  # the reference itself cannot run some modes (SURVEY Q17)
+            out[tag] = {"error": f"{type(e).__name__}: {e}"[:200]}
+        finally:
+            model = None
+            torch.cuda.empty_cache()
+    out["how"] = ("unmodified reference modules (baseline/_ref) on this GPU, PyTorch %s stock kernels, wall clock around "
+                  "synchronised steps, median of %d" % (torch.__version__, steps))
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------
-# our arm
+# per-kernel timing of our arm
 # ---------------------------------------------------------------------------------------------------
-def profile_calls(engine, plans):
-    """Per-launch device time of every C-ABI call of the given plans (CUDA events on the launching
-    stream, eager).  Returns [(name, ms, call)] in issue order."""
+def profile_calls(plans):
+    """Per-launch device time of every C-ABI call of the given plans (CUDA events on the launching stream, eager).
+    Returns [(name, ms, args)] in issue order."""
     stream = torch.cuda.current_stream()
     out = []
     # keep the GPU busy while the host queues every launch + event, so the event deltas are device time
-    # (kernel + its dependency gap), not host submission latency
     torch.cuda._sleep(int(4e7))
     for plan in plans:
         for name, fn, a, _lane in plan.calls:
@@ -186,97 +325,185 @@ def profile_calls(engine, plans):
     return [(n, e0.elapsed_time(e1), a) for n, e0, e1, a in out]
 
 
-def gemm_flops(a):
-    g = a[0]._obj
-    return 2.0 * g.M * g.N * g.K
-
-
 def lib_fn(name):
     from vct import lib as L
     return getattr(L.load(), name.split(":")[0])
 
 
-def attention_rooflines(names, med, calls, peaks):
-    """Roofline of the fused attention kernels (BASELINE metric: "attn kernel HBM GB/s vs peak"; SURVEY section 8d
-    formulas, bf16 = 2 bytes): per flavour the median per-launch device time of the step's launches, the kernel's
-    ALGORITHMIC bytes and FLOPs, both bounds, and the fraction of the tighter (larger ideal time) one.
-      self fwd : reads x, W_in[3d,d], b; writes o and the saved q|k|v rows;   FLOPs = B (6 L d^2 + 4 L^2 d)
-      cross fwd: reads x, pre-projected K|V of the memory, W_q, b_q; writes o, q; FLOPs = B (2 S d^2 + 4 S M d)
-      bwd      : reads q, k, v, dO; writes dq, dk, dv;                         FLOPs = 10 B Lq Lk d"""
-    groups = {}
-    fns = {}
+def graph_time_ms(name, a, reps=10):
+    """One kernel alone: a CUDA graph of `reps` back-to-back launches of the call, CUDA events around the replay (the
+    eager per-launch figure also contains the event / launch gap of ~3 us)."""
+    fn = lib_fn(name)
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        for _ in range(2):
+            fn(*a, st.cuda_stream)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps):
+                fn(*a, st.cuda_stream)
+        g.replay()
+        torch.cuda.synchronize()
+        best = 1e9
+        for _ in range(3):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(st); g.replay(); e1.record(st); torch.cuda.synchronize()
+            best = min(best, e0.elapsed_time(e1) / reps)
+    return best
+
+
+def family_of(name):
+    base = name.split(":")[0]
+    if base == "vct_gemm":
+        return "vct_gemm:generator" if "generator" in name else "vct_gemm:layers"
+    if base == "vct_attn_bwd":
+        return "vct_attn_bwd"
+    return base
+
+
+def algorithmic_work(name, a, eng):
+    """(bytes, flops) of one call -- SURVEY section 8d formulas, bf16 = 2 bytes, fp32 = 4 (stated per kernel in DESIGN.md)."""
+    base = name.split(":")[0]
+    es = 2.0 if eng.precision == "bf16" else 4.0
+    if base == "vct_gemm":
+        g = a[0]._obj
+        fl = 2.0 * g.M * g.N * g.K
+        cb = 4.0 if g.c_dtype == 0 else 2.0
+        by = es * (g.M * g.K + g.N * g.K) + cb * g.M * g.N + (2.0 * g.M * g.N if g.C2 else 0.0)
+        return by, fl
+    if base in ("vct_attn_enc_self_fwd", "vct_attn_dec_self_fwd"):
+        o = a[0]._obj
+        B, L, d = o.B, o.L, o.d
+        return es * (B * L * d + 3 * d * d + 3 * d + B * L * d + 3 * B * L * d) + B * L, B * (6.0 * L * d * d + 4.0 * L * L * d)
+    if base == "vct_attn_dec_cross_fwd":
+        o = a[0]._obj
+        B, S, M, d = o.B, o.L, o.Lk, o.d
+        return es * (B * S * d + B * M * 2 * d + d * d + d + 2 * B * S * d), B * (2.0 * S * d * d + 4.0 * S * M * d)
+    if base in ("vct_attn_bwd", "vct_attn_fwd"):
+        o = a[0]._obj
+        B, Lq, Lk, d = o.B, o.Lq, o.Lk, o.H * o.dh
+        if base == "vct_attn_fwd":
+            return es * B * d * (2 * Lq + 2 * Lk), 4.0 * B * Lq * Lk * d
+        return es * B * d * (3 * Lq + 4 * Lk), 10.0 * B * Lq * Lk * d
+    if base == "vct_ln_residual_fwd":
+        R, d = a[10], a[11]
+        # reads r (+ x when there is a residual), writes s (when kept), y fp32 and the compute-dtype copy
+        n_in = 2 if a[0] else 1
+        return R * d * (4.0 * n_in + (4.0 if a[7] else 0.0) + 4.0 + (es if a[5] else 0.0)), 0.0
+    if base == "vct_ln_residual_bwd":
+        R, d = a[13], a[14]
+        return R * d * (4.0 + 4.0 + 4.0 + (es if a[6] else 0.0)), 0.0
+    if base == "vct_sce":
+        B, S, Vv = a[4], a[5], a[6]
+        lb = 4.0 if len(a) < 18 or a[17] == 0 else 2.0      # logits storage type (last argument when present)
+        return B * S * Vv * (lb + (es if a[13] else 0.0)), 0.0
+    if base == "vct_adam":
+        n = a[5]
+        return n * (16.0 + 12.0 + (2.0 if a[4] else 0.0)), 0.0
+    return 0.0, 0.0
+
+
+def attn_key(name, a):
+    base = name.split(":")[0]
+    if base == "vct_attn_bwd":
+        o = a[0]._obj
+        return "vct_attn_bwd:" + ("cross" if "cross" in name else ("enc_self" if "enc" in name else "dec_self"))
+    return base
+
+
+def kernel_rooflines(eng, plans, peaks, adam_ms, extra_adam=True):
+    """Every kernel family of the step: eager per-launch CUDA-event time (share of the step), each distinct call also
+    timed ALONE in a CUDA graph (achieved rate against the measured peaks)."""
+    profile_calls(plans)                               # warm
+    reps = [profile_calls(plans) for _ in range(3)]
+    names = [r[0] for r in reps[0]]
+    calls = [r[2] for r in reps[0]]
+    med = [statistics.median(rep[i][1] for rep in reps) for i in range(len(names))]
+    total = sum(med) + (adam_ms or 0.0)
+    traffic = ncu_traffic()
+    fam = {}
+    alone_cache = {}
     for n, m, a in zip(names, med, calls):
-        if n.startswith(("vct_attn_enc_self_fwd", "vct_attn_dec_self_fwd")):
-            o = a[0]._obj
-            B, L, d = o.B, o.L, o.d
-            by = 2.0 * (B * L * d + 3 * d * d + 3 * d + B * L * d + 3 * B * L * d) + B * L
-            fl = B * (6.0 * L * d * d + 4.0 * L * L * d)
-            key = n.split(":")[0]
-        elif n.startswith("vct_attn_dec_cross_fwd"):
-            o = a[0]._obj
-            B, S, M, d = o.B, o.L, o.Lk, o.d
-            by = 2.0 * (B * S * d + B * M * 2 * d + d * d + d + 2 * B * S * d)
-            fl = B * (2.0 * S * d * d + 4.0 * S * M * d)
-            key = "vct_attn_dec_cross_fwd"
-        elif n.startswith("vct_attn_bwd"):
-            o = a[0]._obj
-            B, Lq, Lk, d = o.B, o.Lq, o.Lk, o.H * o.dh
-            by = 2.0 * B * d * (3 * Lq + 4 * Lk)
-            fl = 10.0 * B * Lq * Lk * d
-            key = "vct_attn_bwd:" + ("cross" if Lq != Lk else ("enc_self" if "enc" in n else "dec_self"))
+        f = family_of(n)
+        by, fl = algorithmic_work(n, a, eng)
+        if f.startswith(("vct_gemm", "vct_attn", "vct_ln", "vct_sce")):
+            if n not in alone_cache:
+                alone_cache[n] = graph_time_ms(n, a)
+            alone = alone_cache[n]
         else:
-            continue
-        groups.setdefault(key, []).append((m, by, fl))
-        fns.setdefault(key, (n, a))
+            alone = m
+        e = fam.setdefault(f, {"launches": 0, "eager_ms": 0.0, "alone_ms": 0.0, "bytes": 0.0, "flops": 0.0})
+        e["launches"] += 1
+        e["eager_ms"] += m
+        e["alone_ms"] += alone
+        e["bytes"] += by
+        e["flops"] += fl
+    if adam_ms:
+        a = eng.arena
+        fam["vct_adam"] = {"launches": 1, "eager_ms": adam_ms, "alone_ms": adam_ms,
+                           "bytes": a.numel * (16.0 + 12.0 + (2.0 if eng.precision == "bf16" else 0.0)), "flops": 0.0}
     out = []
-    for key, rows in groups.items():
-        eager_ms = statistics.median(r[0] for r in rows)
-        # kernel alone: a CUDA graph of 10 back-to-back launches of the flavour's first call of the step, CUDA events
-        # around the replay (the eager per-launch figure also contains the event / launch gap of ~3 us)
-        n0, a0 = fns[key]
-        fn = lib_fn(n0)
-        st = torch.cuda.Stream()
-        with torch.cuda.stream(st):
-            for _ in range(2):
-                fn(*a0, st.cuda_stream)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g, stream=st):
-                for _ in range(10):
-                    fn(*a0, st.cuda_stream)
-            g.replay()
-            torch.cuda.synchronize()
-            best = 1e9
-            for _ in range(3):
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(st); g.replay(); e1.record(st); torch.cuda.synchronize()
-                best = min(best, e0.elapsed_time(e1) / 10)
-        ms = best
-        by, fl = rows[0][1], rows[0][2]
-        t_hbm, t_tc = by / (peaks["hbm_gbs"] * 1e9), fl / (peaks["tflops"] * 1e12)
-        bound = "hbm" if t_hbm >= t_tc else "tensor"
-        out.append({"kernel": key, "launches_per_step": len(rows), "ms": round(ms, 5), "ms_eager_with_gap": round(eager_ms, 5),
-                    "bytes": by, "flops": fl,
-                    "achieved_gbs": by / (ms * 1e-3) / 1e9, "achieved_tflops": fl / (ms * 1e-3) / 1e12,
-                    "ideal_us_hbm": t_hbm * 1e6, "ideal_us_tensor": t_tc * 1e6, "bound": bound,
-                    "frac": max(t_hbm, t_tc) / (ms * 1e-3)})
-    return out
+    for f, e in fam.items():
+        t = e["alone_ms"] * 1e-3
+        t_hbm, t_tc = e["bytes"] / (peaks["hbm_gbs"] * 1e9), e["flops"] / (peaks["tflops"] * 1e12)
+        bound = "tensor" if t_tc > t_hbm else "hbm"
+        ach = (e["flops"] / t / 1e12) if bound == "tensor" else (e["bytes"] / t / 1e9)
+        peak = peaks["tflops"] if bound == "tensor" else peaks["hbm_gbs"]
+        tr = None
+        for pat, v in traffic.items():
+            if re.search(pat, f):
+                tr = v
+        out.append({"kernel": f, "launches_per_step": e["launches"], "share_of_step": e["eager_ms"] / total,
+                    "ms_eager": round(e["eager_ms"], 4), "ms_alone": round(e["alone_ms"], 4), "bound": bound,
+                    "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
+                    "frac": ach / peak if t > 0 and (e["bytes"] or e["flops"]) else None,
+                    "bytes": e["bytes"], "flops": e["flops"], "traffic": tr, "peak_source": peaks["src"]})
+    out.sort(key=lambda r: -r["share_of_step"])
+    # attention flavours, one line each (BASELINE metric "attn kernel HBM GB/s vs peak")
+    attn = {}
+    for n, m, a in zip(names, med, calls):
+        if not n.startswith("vct_attn"):
+            continue
+        k = attn_key(n, a)
+        by, fl = algorithmic_work(n, a, eng)
+        r = attn.setdefault(k, {"kernel": k, "launches_per_step": 0, "ms": alone_cache[n], "ms_eager_with_gap": m,
+                                "bytes": by, "flops": fl})
+        r["launches_per_step"] += 1
+    attn_out = []
+    for k, r in attn.items():
+        t = r["ms"] * 1e-3
+        t_hbm, t_tc = r["bytes"] / (peaks["hbm_gbs"] * 1e9), r["flops"] / (peaks["tflops"] * 1e12)
+        r.update({"achieved_gbs": r["bytes"] / t / 1e9, "achieved_tflops": r["flops"] / t / 1e12,
+                  "ideal_us_hbm": t_hbm * 1e6, "ideal_us_tensor": t_tc * 1e6, "bound": "hbm" if t_hbm >= t_tc else "tensor",
+                  "frac": max(t_hbm, t_tc) / t})
+        r["ms"], r["ms_eager_with_gap"] = round(r["ms"], 5), round(r["ms_eager_with_gap"], 5)
+        attn_out.append(r)
+    breakdown = {r["kernel"]: r["ms_eager"] for r in out}
+    return out, attn_out, breakdown, len(names)
 
 
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)     # 200 x 1.7 ms: long enough for several nvidia-smi clock samples
+    ap.add_argument("--steps", type=int, default=200)     # 200 x ~1.5 ms: long enough for several nvidia-smi clock samples
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="captions per GPU")
+    ap.add_argument("--config", default="cfg2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="captions per GPU (overrides the config's rule)")
     ap.add_argument("--precision", default=os.environ.get("VCT_PRECISION", "bf16"))
     ap.add_argument("--gemm", default=os.environ.get("VCT_GEMM"))
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-reference", action="store_true")
+    ap.add_argument("--no-rooflines", action="store_true")
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
     if args.impl == "reference":
-        return run_reference_arm(args)
+        return run_reference_arm(args, cfg)
     args.warmup = max(args.warmup, 3)
 
     import torch.distributed as dist
@@ -288,27 +515,22 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     from model.MMT4Caption import MMT4Caption
-    from vct.synthetic import make_tokenizer_dir, shipped_model_config, synth_batch
-    from vct.trainer import CaptionTrainer
+    from vct.synthetic import synth_batch
 
-    tokdir = os.path.join(ROOT, "gpurun_out", "_tok") if rank == 0 else None
     if rank == 0:
-        make_tokenizer_dir(tokdir)
+        tokenizer_dir()
     if world > 1:
         dist.barrier()
-    tokdir = os.path.join(ROOT, "gpurun_out", "_tok")
+    tokdir = tokenizer_dir()
     torch.manual_seed(666)
-    model = MMT4Caption(shipped_model_config(tokdir), device=dev).to(dev)
+    model = MMT4Caption(model_config(cfg, tokdir), device=dev).to(dev)
     model.vct_precision, model.vct_gemm = args.precision, args.gemm
     model.mode("caption")
-    model.train()
-    trainer = CaptionTrainer(model, lr=1e-4, betas=(0.9, 0.999), use_graph=not args.no_graph)
-    eng = trainer.engine
-    B = args.batch
+    B = per_gpu_batch(cfg, world, args.batch)
+    T = cfg["T"]
     x, vm, tok = synth_batch(B, T, DIN, S1, seed=1234 + rank)
     xd, vd, td = x.to(dev), vm.to(dev), tok.to(dev)
     xh, vh, th = x.pin_memory(), vm.pin_memory(), tok.pin_memory()
-
     verbose = os.environ.get("VCT_BENCH_VERBOSE") == "1"
 
     def note(msg):
@@ -321,12 +543,41 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- warm-up (also builds plans / captures the graph: needs >= 3 steps) -------------------------
+    peaks = measured_peaks()
+    decode = cfg["kind"] == "decode"
+    if decode:
+        model.eval()
+        eng = model._engine()
+        max_len = cfg["max_len"]
+
+        def step_dev():
+            return model.greedy_decode_ids([xd], [vd], max_len=max_len, sync_every=max_len - 1)
+
+        def step_host():
+            ys = model.greedy_decode_ids([xh], [vh], max_len=max_len, sync_every=max_len - 1)
+            return ys.cpu()
+        d2h = B * max_len * 8
+        h2d = x.numel() * 4 + vm.numel()
+        trainer = None
+    else:
+        from vct.trainer import CaptionTrainer
+        model.train()
+        trainer = CaptionTrainer(model, lr=1e-4, betas=(0.9, 0.999), use_graph=not args.no_graph)
+        eng = trainer.engine
+
+        def step_dev():
+            return trainer.step(xd, vd, td)
+
+        def step_host():
+            return trainer.step(xh, vh, th).item()
+        d2h = 4
+        h2d = x.numel() * 4 + vm.numel() + tok.numel() * 8
+
+    # ---- warm-up (also builds plans / captures the graphs: needs >= 3 steps) -------------------------
     note("model built")
     for i in range(max(args.warmup, 3)):
-        trainer.step(xd, vd, td)
+        step_dev()
         torch.cuda.synchronize()
-        note(f"warm-up step {i} done")
     sync_all()
     note("warm-up done")
     # ---- value: device-resident inputs ----------------------------------------------------------------
@@ -338,7 +589,7 @@ def main():
     sync_all()
     e0.record()
     for _ in range(args.steps):
-        loss = trainer.step(xd, vd, td)
+        last = step_dev()
     e1.record()
     sync_all()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -346,96 +597,78 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = eng.launches - launches0
-    final_loss = float(loss.item())
+    final = float(last.item()) if not decode else int(last.shape[1])
     note("timed region done")
-    # ---- e2e: pinned host inputs, H2D + loss read-back every step -----------------------------------
+    # ---- e2e: pinned host inputs, H2D + result read-back every step -----------------------------------
     sync_all()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        loss = trainer.step(xh, vh, th)
-        _ = loss.item()
+        step_host()
     torch.cuda.synchronize()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     note("e2e done")
     clocks = sampler.stop() if rank == 0 else None
-    h2d = x.numel() * 4 + vm.numel() + tok.numel() * 8
-    # ---- roofline of the dominant kernel (rank 0): per-launch CUDA-event times of one eager step ------
-    roofline, breakdown, attn_roof = None, None, None
-    if rank == 0:
-        ws = eng.workspace(B, T, S1 - 1, True)
-        plans = [eng.plan_forward(ws, fused_grad=True, part="all"), eng.plan_backward(ws, sce_first=False, part="all")]
-        profile_calls(eng, plans)                      # warm
-        reps = [profile_calls(eng, plans) for _ in range(3)]
-        names = [r[0] for r in reps[0]]
-        med = [statistics.median(rep[i][1] for rep in reps) for i in range(len(names))]
-        calls = [r[2] for r in reps[0]]
-        a = eng.arena
-        e_ad0, e_ad1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e_ad0.record(); eng.adam(1.0); e_ad1.record(); torch.cuda.synchronize()
-        adam_ms = e_ad0.elapsed_time(e_ad1)
-        total = sum(med) + adam_ms
-        groups = {}
-        for n, m in zip(names, med):
-            k = n.split(":")[0] if not n.startswith("vct_gemm") else ("vct_gemm:generator" if "generator" in n else "vct_gemm:layers")
-            groups[k] = groups.get(k, 0.0) + m
-        groups["vct_adam"] = adam_ms
-        breakdown = {k: round(v, 4) for k, v in sorted(groups.items(), key=lambda kv: -kv[1])}
-        peaks = measured_peaks()
-        attn_roof = attention_rooflines(names, med, calls, peaks)
-        top = max(range(len(names)), key=lambda i: med[i])
-        if adam_ms >= med[top]:
-            nbytes = a.numel * (16 + 12 + (2 if eng.precision == "bf16" else 0))
-            ach = nbytes / (adam_ms * 1e-3) / 1e9
-            roofline = {"kernel": "vct_adam", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": ach / peaks["hbm_gbs"], "traffic": None, "ms": adam_ms, "peak_source": peaks["src"]}
-        elif names[top].startswith("vct_gemm"):
-            fl = gemm_flops(calls[top])
-            ach = fl / (med[top] * 1e-3) / 1e12
-            roofline = {"kernel": names[top], "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                        "frac": ach / peaks["tflops"], "traffic": None, "ms": med[top], "flops": fl,
-                        "peak_source": peaks["src"], "share_of_step": med[top] / total}
+
+    # ---- rooflines (rank 0): per-launch CUDA-event times of one eager pass + every distinct call alone in a graph ------
+    rooflines, attn_roof, breakdown, phase_ms, roofline = None, None, None, None, None
+    if rank == 0 and not args.no_rooflines:
+        if decode:
+            dws = eng.decode_workspace(B, T, max_len)
+            plans = [eng.plan_decode_step(dws, max_len - 2)]
+            rooflines, attn_roof, breakdown, _ = kernel_rooflines(eng, plans, peaks, None)
         else:
-            roofline = {"kernel": names[top], "bound": "hbm", "achieved": None, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                        "frac": None, "traffic": None, "ms": med[top], "peak_source": peaks["src"]}
-    # ---- phase timing (rank 0): eager run of the same plans with the side lanes active ----------------
-    phase_ms = None
-    if rank == 0:
-        ws = eng.workspace(B, T, S1 - 1, True)
-        fwd = eng.plan_forward(ws, fused_grad=True, part="all")
-        bwd = eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=(world == 1 and trainer.fuse_adam))
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
-        acc = [0.0, 0.0]
-        for rep in range(4):
-            torch.cuda._sleep(int(2e7))
-            ev[0].record(); eng.run(fwd); ev[1].record(); eng.run(bwd); ev[2].record()
-            torch.cuda.synchronize()
-            if rep:
-                acc[0] += ev[0].elapsed_time(ev[1]) / 3
-                acc[1] += ev[1].elapsed_time(ev[2]) / 3
-        phase_ms = {"forward": round(acc[0], 4), "backward_incl_side_lanes": round(acc[1], 4),
-                    "n_forward_calls": len(fwd), "n_backward_calls": len(bwd)}
-    # ---- cpu baseline (rank 0, N = 1 only) --------------------------------------------------------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sec, n = cpu_train_steps(64, 4, 1, threads)
-        cpu = {"value": 64 / sec, "unit": "captions/s", "cores": threads, "kind": "port",
-               "sample": f"{n} train steps of batch 64 (fwd+bwd+Adam, fp32, torch CPU kernels, no dropout), median"}
+            ws = eng.workspace(B, T, S1 - 1, True)
+            plans = [eng.plan_forward(ws, fused_grad=True, part="all"), eng.plan_backward(ws, sce_first=False, part="all")]
+            e_ad0, e_ad1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            eng.adam(1.0); torch.cuda.synchronize()
+            e_ad0.record(); eng.adam(1.0); e_ad1.record(); torch.cuda.synchronize()
+            rooflines, attn_roof, breakdown, _ = kernel_rooflines(eng, plans, peaks, e_ad0.elapsed_time(e_ad1))
+            fwd = plans[0]
+            bwd = eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=(world == 1 and trainer.fuse_adam))
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+            acc = [0.0, 0.0]
+            for rep in range(4):
+                torch.cuda._sleep(int(2e7))
+                ev[0].record(); eng.run(fwd); ev[1].record(); eng.run(bwd); ev[2].record()
+                torch.cuda.synchronize()
+                if rep:
+                    acc[0] += ev[0].elapsed_time(ev[1]) / 3
+                    acc[1] += ev[1].elapsed_time(ev[2]) / 3
+            phase_ms = {"forward": round(acc[0], 4), "backward_incl_side_lanes": round(acc[1], 4),
+                        "n_forward_calls": len(fwd), "n_backward_calls": len(bwd)}
+        top = rooflines[0]                                  # the family with the largest share of the step
+        roofline = {k: top[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "share_of_step",
+                                        "launches_per_step", "ms_alone", "peak_source")}
+    # ---- reference arms (rank 0, N = 1 only) -------------------------------------------------------------
+    cpu, gref = None, None
+    if rank == 0 and world == 1:
+        if not args.no_cpu_baseline:
+            cpu = cpu_baseline(cfg, 4 if not decode else 1, 1)
+            cpu.pop("ms", None)
+        if not args.no_gpu_reference:
+            model_ref_B = B
+            del model
+            torch.cuda.empty_cache()
+            gref = gpu_reference(cfg, model_ref_B, dev)
     if rank == 0:
         ms_step = ms_total / args.steps
-        line = {"metric": "captions/sec (train step)", "value": B * world / (ms_step * 1e-3), "unit": "captions/s",
+        metric = "captions/sec (greedy decode)" if decode else "captions/sec (train step)"
+        line = {"metric": metric, "value": B * world / (ms_step * 1e-3), "unit": "captions/s",
                 "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "bf16" if eng.precision == "bf16" else "f32", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                           "gemm": "tcgen05" if eng.gemm_impl == 1 else "simt", "cuda_graph": not args.no_graph,
+                "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None,
+                "dtype": "bf16" if eng.precision == "bf16" else ("f32" if eng.precision == "fp32" else eng.precision),
+                "data": "synthetic",
+                "config": {"workload": cfg["name"], "name": args.config, "global_batch": B * world, "per_gpu_batch": B,
+                           "parallelism": f"dp{world}", "gemm": "tcgen05" if eng.gemm_impl == 1 else "simt",
+                           "cuda_graph": not args.no_graph,
                            "l2": "no explicit flush: one step streams ~2.5 GB of weights/moments/activations, 20x the 126 MB L2"},
                 "e2e": {"value": B * world * args.steps / float(e2e_s.item()), "unit": "captions/s",
-                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
-                "gpu_launches": launches, "loss": final_loss, "clocks": clocks, "roofline": roofline,
-                "attn_rooflines": attn_roof, "cpu_baseline": cpu, "kernel_ms": breakdown, "phase_ms": phase_ms}
+                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, ("tokens" if decode else "loss"): final, "clocks": clocks, "roofline": roofline,
+                "rooflines": rooflines, "attn_rooflines": attn_roof, "cpu_baseline": cpu, "gpu_reference": gref,
+                "kernel_ms": breakdown, "phase_ms": phase_ms}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -322,12 +322,13 @@ attn_fused_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         mbar_wait(ph0 + 16, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (trace && threadIdx.x == 64) trace[105] = clock64();
-        constexpr int SPW = 32 / LQP;                         // sequences per warp (1 or 2)
-        constexpr int NLD = SPW * LKP;                        // score columns the warp loads (32, 64)
+        constexpr int SPW = LQP >= 32 ? 1 : 32 / LQP;         // sequences per warp (1, or 2 when sequences are 16 rows)
+        constexpr int NLD = SPW * LKP;                        // score columns the warp loads (16 .. 64)
         float sc[LKP];
         {
             uint32_t rg[NLD];
-            const int jq = q * SPW < NB ? q * SPW : 0;         // warps past the group's last sequence read (and discard) block 0
+            const int jw = LQP >= 32 ? (q * 32) / LQP : q * SPW;   // first sequence of this warp's 32 rows
+            const int jq = jw < NB ? jw : 0;                   // warps past the group's last sequence read (and discard) block 0
             const uint32_t col0 = kColS + (uint32_t)(jq * LKP);
 #pragma unroll
             for (int c = 0; c < NLD / 16; ++c) tmem_ld16(lane_addr + col0 + 16u * c, rg + 16 * c);
@@ -554,11 +555,12 @@ attn_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         }
         mbar_wait(bar0 + 8, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        constexpr int SPW = 32 / LQP, NLD = SPW * LKP;
+        constexpr int SPW = LQP >= 32 ? 1 : 32 / LQP, NLD = SPW * LKP;
         float sc[LKP], dp[LKP];
         {
             uint32_t rg[NLD], rd[NLD];
-            const int jq = q * SPW < NB ? q * SPW : 0;
+            const int jw = LQP >= 32 ? (q * 32) / LQP : q * SPW;
+            const int jq = jw < NB ? jw : 0;
 #pragma unroll
             for (int c = 0; c < NLD / 16; ++c) {
                 tmem_ld16(lane_addr + kColS + (uint32_t)(jq * LKP) + 16u * c, rg + 16 * c);
@@ -804,43 +806,58 @@ namespace vct {
 // both return 0 when the fused kernel was launched, > 0 when the shape is not covered (the caller composes the
 // projection GEMM with the stand-alone core), < 0 on error
 int attn_fused_self(const vct_mha_args* m, int causal, cudaStream_t st) {
-    if (!common_ok(m) || m->L > 32) return 1;
+    if (!common_ok(m) || m->L > 64) return 1;
     const int dh = m->d / m->H;
-    if (dh == 96) return m->L <= 16 ? launch_fused<96, 16, 16, false>(m, causal, st) : launch_fused<96, 32, 32, false>(m, causal, st);
-    if (dh == 64) return m->L <= 16 ? launch_fused<64, 16, 16, false>(m, causal, st) : launch_fused<64, 32, 32, false>(m, causal, st);
+    // sequences are padded to 16 / 32 / 64 rows: 8 / 4 / 2 of them share one 128-row tile (cfg 5's M = 33 runs on LQP = 64)
+    if (dh == 96) {
+        if (m->L <= 16) return launch_fused<96, 16, 16, false>(m, causal, st);
+        if (m->L <= 32) return launch_fused<96, 32, 32, false>(m, causal, st);
+        return launch_fused<96, 64, 64, false>(m, causal, st);
+    }
+    if (dh == 64) {
+        if (m->L <= 16) return launch_fused<64, 16, 16, false>(m, causal, st);
+        if (m->L <= 32) return launch_fused<64, 32, 32, false>(m, causal, st);
+        return launch_fused<64, 64, 64, false>(m, causal, st);
+    }
     return 1;
 }
 
 // attention backward on the tensor cores: 0 = launched, > 0 = shape not covered (caller runs the SIMT kernel), < 0 = error
 int attn_bwd_tc(const vct_attn_args* m, cudaStream_t st) {
     static const bool on = [] { const char* e = getenv("VCT_ATTN_BWD_TC"); return e == nullptr || e[0] != '0'; }();
-    if (!on || m->dtype != VCT_BF16 || m->Lq > 32 || m->Lk > 64 || (m->causal && m->Lq != m->Lk)) return 1;
+    if (!on || m->dtype != VCT_BF16 || m->Lq > 64 || m->Lk > 64 || (m->causal && m->Lq != m->Lk)) return 1;
     if (m->dq_bs || m->dk_bs || m->dv_bs) return 1;                                  // gradients are written densely
     auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
     if (!al(m->q) || !al(m->k) || !al(m->v) || !al(m->d_o) || !al(m->dq) || !al(m->dk) || !al(m->dv)) return 1;
     if (m->q_ld % 8 || m->k_ld % 8 || m->v_ld % 8 || m->do_ld % 8 || m->dq_ld % 8 || m->dk_ld % 8 || m->dv_ld % 8) return 1;
     if (m->q_bs % 8 || m->k_bs % 8 || m->v_bs % 8 || m->do_bs % 8) return 1;
-    const int lqp = m->Lq <= 16 ? 16 : 32, lkp = m->Lk <= 16 ? 16 : (m->Lk <= 32 ? 32 : 64);
+    // query / key paddings: the smallest covered pair (a 16-row query padding only exists together with 16-row keys)
+    int lqp = m->Lq <= 16 ? 16 : (m->Lq <= 32 ? 32 : 64);
+    const int lkp = m->Lk <= 16 ? 16 : (m->Lk <= 32 ? 32 : 64);
+    if (lqp == 16 && lkp != 16) lqp = 32;
 #define VCT_BWD_CASE(DH, A, B) if (m->dh == DH && lqp == A && lkp == B) return launch_bwd_tc<DH, A, B>(m, st);
     VCT_BWD_CASE(96, 16, 16) VCT_BWD_CASE(96, 32, 32) VCT_BWD_CASE(96, 32, 16) VCT_BWD_CASE(96, 32, 64)
+    VCT_BWD_CASE(96, 64, 16) VCT_BWD_CASE(96, 64, 32) VCT_BWD_CASE(96, 64, 64)
     VCT_BWD_CASE(64, 16, 16) VCT_BWD_CASE(64, 32, 32) VCT_BWD_CASE(64, 32, 16) VCT_BWD_CASE(64, 32, 64)
+    VCT_BWD_CASE(64, 64, 16) VCT_BWD_CASE(64, 64, 32) VCT_BWD_CASE(64, 64, 64)
 #undef VCT_BWD_CASE
     return 1;
 }
 
 int attn_fused_cross(const vct_mha_args* m, cudaStream_t st) {
     if (!common_ok(m) || !m->kv_ready || m->kv == nullptr || (reinterpret_cast<uintptr_t>(m->kv) & 15)) return 1;
-    if (m->L > 32 || m->L <= 16 || m->Lk < 1 || m->Lk > 64) return 1;       // query rows are padded to 32 per sequence
+    if (m->L > 64 || m->L < 1 || m->Lk < 1 || m->Lk > 64) return 1;          // query rows are padded to 32 or 64 per sequence
     const int dh = m->d / m->H;
+    const bool q64 = m->L > 32;
     if (dh == 96) {
-        if (m->Lk <= 16) return launch_fused<96, 32, 16, true>(m, 0, st);
-        if (m->Lk <= 32) return launch_fused<96, 32, 32, true>(m, 0, st);
-        return launch_fused<96, 32, 64, true>(m, 0, st);
+        if (m->Lk <= 16) return q64 ? launch_fused<96, 64, 16, true>(m, 0, st) : launch_fused<96, 32, 16, true>(m, 0, st);
+        if (m->Lk <= 32) return q64 ? launch_fused<96, 64, 32, true>(m, 0, st) : launch_fused<96, 32, 32, true>(m, 0, st);
+        return q64 ? launch_fused<96, 64, 64, true>(m, 0, st) : launch_fused<96, 32, 64, true>(m, 0, st);
     }
     if (dh == 64) {
-        if (m->Lk <= 16) return launch_fused<64, 32, 16, true>(m, 0, st);
-        if (m->Lk <= 32) return launch_fused<64, 32, 32, true>(m, 0, st);
-        return launch_fused<64, 32, 64, true>(m, 0, st);
+        if (m->Lk <= 16) return q64 ? launch_fused<64, 64, 16, true>(m, 0, st) : launch_fused<64, 32, 16, true>(m, 0, st);
+        if (m->Lk <= 32) return q64 ? launch_fused<64, 64, 32, true>(m, 0, st) : launch_fused<64, 32, 32, true>(m, 0, st);
+        return q64 ? launch_fused<64, 64, 64, true>(m, 0, st) : launch_fused<64, 32, 64, true>(m, 0, st);
     }
     return 1;
 }
