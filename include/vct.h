@@ -228,6 +228,23 @@ int vct_embed_bwd(const long long* ids, long long ids_ld, const float* dx, float
                   int pad_id, float drop_p, const unsigned long long* rng_state, unsigned int site,
                   vct_stream_t stream);
 
+/* The same gradient in its sparse form: rows[b*S + s, :] = dropmask * dx[b*S + s, :] (fp32 [B*S, d]), no scatter.  The
+ * data-parallel trainer all-gathers these rows + the ids of every rank (B*S*d*4 bytes per rank, < 4 MB) and scatters them
+ * locally with vct_embed_bwd (drop_p = 0) instead of all-reducing the dense [V, d] table gradient that DDP exchanges
+ * (train.py:218; 94 MB with at most B*S non-zero rows). */
+int vct_embed_bwd_rows(const float* dx, float* rows, int B, int S, int d, float drop_p,
+                       const unsigned long long* rng_state, unsigned int site, vct_stream_t stream);
+/* Deterministic scatter: dE[id, :] = sum over the tokens (b, s) with ids[b*ids_ld + s] == id of rows[b*S + s, :], summed in a
+ * FIXED order (tokens sorted by id, then by index), rows of dE that no token maps to are left untouched, pad / out-of-range
+ * ids are skipped.  Every data-parallel rank runs it on the same gathered rows and obtains bit-identical table gradients
+ * (replicas must not drift; an atomicAdd scatter sums in a run-dependent order).  keys_ws: uint32 workspace [B*S].
+ * Limits: B*S <= 16384, V <= 32768, d % 4 == 0, d <= 1024. */
+int vct_embed_bwd_det(const long long* ids, long long ids_ld, const float* rows, float* dE, int B, int S, int d, int V,
+                      int pad_id, unsigned int* keys_ws, vct_stream_t stream);
+/* dE[ids[b*ids_ld + s], :] = 0 for every (b, s): re-zeroes exactly the rows vct_embed_bwd scattered into, once the
+ * optimizer has consumed them (replaces a memset of the whole table gradient per step; optimizer.zero_grad, train.py:124). */
+int vct_embed_zero(const long long* ids, long long ids_ld, float* dE, int B, int S, int d, int V, vct_stream_t stream);
+
 /* ---- SCE loss (model/loss.py:69-92; closed form SURVEY Q9) -----------------------------------
  * logits fp32 [N, ld_logits] (N = B*S), label of row (b,s) = ids[b*ids_ld + s + 1].
  * loss = alpha * mean_{label != pad}(lse - z_y) + beta * mean_all( A * sum_{c != y} clamp(p_c,1e-7,1) )
@@ -250,10 +267,11 @@ int vct_colsum(const void* X, int dtype, long long ld, int M, int N, float* out,
                unsigned int* counter, vct_stream_t stream);
 
 /* ---- Adam over the flat parameter arena (torch.optim.Adam semantics, train.py:22-31,126) -----
- * p, g, m, v: fp32 [n]; hyper: the float[8] of vct_step_tick (already ticked for this step);
+ * p, m, v: fp32 [n]; g: gradients in g_dtype (VCT_F32, or VCT_BF16 when the data-parallel trainer exchanged the
+ * gradient bucket in bf16); hyper: the float[8] of vct_step_tick (already ticked for this step);
  * grad_scale multiplies g first (1/world_size after a SUM all-reduce).  If p_c != NULL also
  * writes the bf16 shadow copy the tensor-core GEMMs read next step. */
-int vct_adam(float* p, const float* g, float* m, float* v, void* p_c, long long n, const float* hyper,
+int vct_adam(float* p, const void* g, int g_dtype, float* m, float* v, void* p_c, long long n, const float* hyper,
              float grad_scale, vct_stream_t stream);
 
 /* fp32 -> dtype copy (initial bf16 shadow of the parameters, input staging) */

@@ -68,3 +68,49 @@ def test_bucketed_allreduce_gives_mean_gradient_and_identical_replicas():
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert ret["ok"], "mean of per-rank gradients != global-batch gradient"
     assert ret["same"], "replicas diverged after the update"
+
+
+def _sparse_worker(rank, world, port, ret):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "video-captioning-transformer_b200"))
+    sys.path.insert(0, root)
+    from vct.trainer import gather_embedding_rows, scatter_embedding_rows
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    V, d, B, S, pad = 50, 8, 3, 5, 0
+    g = torch.Generator().manual_seed(10 + rank)                 # every rank holds a DIFFERENT shard
+    ids = torch.randint(1, V, (B, S + 1), generator=g)
+    ids[rank % B, 2:] = pad                                      # padded positions contribute nothing (padding_idx)
+    table = torch.randn(V, d, generator=torch.Generator().manual_seed(3), requires_grad=True)
+    w = torch.randn(B, S, d, generator=g)
+    loss = (torch.nn.functional.embedding(ids[:, :-1], table, padding_idx=pad) * w).sum()
+    dense, = torch.autograd.grad(loss, table)                    # what DDP would all-reduce: the dense [V, d] gradient
+    rows = w.reshape(B * S, d).clone()                           # d loss / d embedded row = the sparse form
+    all_rows, all_ids = gather_embedding_rows(rows, ids)
+    sparse_sum = scatter_embedding_rows(all_rows, all_ids, V, pad)
+    dist.all_reduce(dense, op=dist.ReduceOp.SUM)
+    # bf16 bucket: cast -> SUM all-reduce -> 1/world in the optimizer; compared with the fp32 exchange
+    flat = torch.randn(1000, generator=g)
+    f32 = flat.clone()
+    dist.all_reduce(f32, op=dist.ReduceOp.SUM)
+    b16 = flat.to(torch.bfloat16)
+    dist.all_reduce(b16, op=dist.ReduceOp.SUM)
+    if rank == 0:
+        ret["sparse_equals_dense"] = bool(torch.allclose(sparse_sum, dense, rtol=1e-6, atol=1e-6))
+        ret["shapes"] = (tuple(all_rows.shape), tuple(all_ids.shape))
+        ret["bf16_rel"] = float((b16.float() - f32).norm() / f32.norm())
+    dist.destroy_process_group()
+
+
+def test_sparse_embedding_exchange_equals_dense_allreduce_and_bf16_bucket_is_close():
+    """The N > 1 trainer exchanges the embedding-table gradient as rows + ids (all-gather) and the dense buckets in
+    bf16: the first must equal DDP's dense SUM all-reduce exactly (up to fp32 summation order), the second stays within
+    bf16 rounding of the fp32 exchange."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sparse_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert ret["sparse_equals_dense"]
+    assert ret["shapes"] == ((2 * 15, 8), (2 * 3, 6))
+    assert ret["bf16_rel"] < 8e-3

@@ -280,6 +280,70 @@ def test_embedding_forward_backward(lib):
     torch.nn.functional.embedding(idd[:, :S], Ew, padding_idx=0).backward(dx.view(B, S, d))
     torch.testing.assert_close(dE, Ew.grad, rtol=1e-5, atol=1e-6)
     assert dE[0].abs().sum().item() == 0.0      # padding_idx row
+    # sparse form (data-parallel exchange): masked rows, then the same scatter with p = 0 reproduces the dense gradient
+    rng = torch.tensor([5, 2], dtype=torch.int64, device=DEV)
+    rows = torch.full((B * S, d), float("nan"), device=DEV)
+    L.check(lib.vct_embed_bwd_rows(dx.data_ptr(), rows.data_ptr(), B, S, d, 0.3, rng.data_ptr(), 1, stream()))
+    dE_direct, dE_sparse = torch.zeros(V, d, device=DEV), torch.zeros(V, d, device=DEV)
+    L.check(lib.vct_embed_bwd(idd.data_ptr(), S + 1, dx.data_ptr(), dE_direct.data_ptr(), B, S, d, V, 0, 0.3, rng.data_ptr(), 1, stream()))
+    L.check(lib.vct_embed_bwd(idd.data_ptr(), S + 1, rows.data_ptr(), dE_sparse.data_ptr(), B, S, d, V, 0, 0.0, None, 0, stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dE_sparse, dE_direct, rtol=1e-6, atol=1e-6)
+    keep = (rows != 0).float().mean().item()
+    assert abs(keep - 0.7) < 0.05
+    # deterministic scatter (what the data-parallel ranks run on the gathered rows): equals the atomic scatter up to fp32
+    # summation order, is bit-reproducible, and leaves untouched rows alone
+    for (Bd, Sd, dd, Vd) in ((B, S, d, V), (96, 20, 768, 30522), (13, 7, 512, 1000)):
+        gi = torch.Generator().manual_seed(Bd + Sd)
+        ids2 = torch.randint(0, Vd, (Bd, Sd + 1), generator=gi)
+        ids2[:, 0] = 101 % Vd                                   # one long segment ([CLS] of every caption)
+        ids2[::3, 3:] = 0                                       # pad tails
+        r2 = torch.randn(Bd * Sd, dd, generator=gi).to(DEV)
+        i2 = ids2.to(DEV)
+        want2 = torch.zeros(Vd, dd, device=DEV)
+        L.check(lib.vct_embed_bwd(i2.data_ptr(), Sd + 1, r2.data_ptr(), want2.data_ptr(), Bd, Sd, dd, Vd, 0, 0.0, None, 0, stream()))
+        outs = []
+        for _ in range(2):
+            got2 = torch.zeros(Vd, dd, device=DEV)
+            got2[1] = 7.0                                       # id 1 may or may not occur: only checked when untouched
+            keys = torch.zeros(Bd * Sd, dtype=torch.int32, device=DEV)
+            L.check(lib.vct_embed_bwd_det(i2.data_ptr(), Sd + 1, r2.data_ptr(), got2.data_ptr(), Bd, Sd, dd, Vd, 0, keys.data_ptr(), stream()))
+            torch.cuda.synchronize()
+            outs.append(got2)
+        assert torch.equal(outs[0], outs[1])
+        used = torch.zeros(Vd, dtype=torch.bool, device=DEV)
+        used[i2[:, :Sd].reshape(-1)] = True
+        used[0] = False
+        torch.testing.assert_close(outs[0][used], want2[used], rtol=1e-5, atol=1e-5)
+        if not bool(used[1]):
+            assert float((outs[0][1] - 7.0).abs().sum()) == 0.0
+        assert float(outs[0][0].abs().sum()) == 0.0             # padding_idx row never written
+    # vct_embed_zero clears exactly the touched rows
+    dirty = torch.ones(V, d, device=DEV)
+    L.check(lib.vct_embed_zero(idd.data_ptr(), S + 1, dirty.data_ptr(), B, S, d, V, stream()))
+    torch.cuda.synchronize()
+    touched = torch.zeros(V, dtype=torch.bool, device=DEV)
+    touched[idd[:, :S].reshape(-1)] = True
+    assert float(dirty[touched].abs().sum()) == 0.0 and float((dirty[~touched] - 1).abs().sum()) == 0.0
+
+
+def test_adam_reads_bf16_gradients(lib):
+    """Data-parallel buckets exchanged in bf16: vct_adam with g_dtype = BF16 equals the fp32 kernel fed the rounded values."""
+    n = 2048
+    g = torch.Generator().manual_seed(4)
+    p0, gr = torch.randn(n, generator=g), torch.randn(n, generator=g)
+    hyper = torch.tensor([1e-3, 0.9, 0.999, 1e-8, 0.0, 1.0, 0.1, 0.001], device=DEV)
+    outs = []
+    for dt in (L.BF16, L.F32):
+        p = p0.clone().to(DEV)
+        m, v = torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+        g16 = gr.to(DEV, torch.bfloat16)
+        gin = g16 if dt == L.BF16 else g16.float()
+        L.check(lib.vct_adam(p.data_ptr(), gin.data_ptr(), dt, m.data_ptr(), v.data_ptr(), None, n, hyper.data_ptr(), 0.5, stream()))
+        torch.cuda.synchronize()
+        outs.append((p.clone(), m.clone(), v.clone()))
+    for a, b in zip(*outs):
+        torch.testing.assert_close(a, b, rtol=0, atol=0)
 
 
 @pytest.mark.parametrize("alpha", [0.5, 1.0])
@@ -350,7 +414,7 @@ def test_adam_matches_torch_optim_and_writes_bf16_shadow(lib):
         tp.grad = gr.clone()
         opt.step()
         L.check(lib.vct_step_tick(rng.data_ptr(), hyper.data_ptr(), stream()))
-        L.check(lib.vct_adam(p.data_ptr(), gr.to(DEV).data_ptr(), m.data_ptr(), v.data_ptr(), shadow.data_ptr(), n,
+        L.check(lib.vct_adam(p.data_ptr(), gr.to(DEV).data_ptr(), L.F32, m.data_ptr(), v.data_ptr(), shadow.data_ptr(), n,
                              hyper.data_ptr(), 1.0, stream()))
         torch.cuda.synchronize()
         torch.testing.assert_close(p.cpu(), tp.detach(), rtol=1e-6, atol=1e-7)

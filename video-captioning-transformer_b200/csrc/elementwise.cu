@@ -475,6 +475,162 @@ extern "C" int vct_embed_bwd(const long long* ids, long long ids_ld, const float
     return check_launch("vct_embed_bwd");
 }
 
+// rows[r, :] = dx[r, :] * dropmask -- the embedding-table gradient in its SPARSE form (one row per token, no scatter):
+// what the data-parallel trainer exchanges (all-gather of B*S rows + ids per rank, < 4 MB) instead of all-reducing the
+// dense [V, d] table gradient (94 MB of which at most B*S rows are non-zero).  Same dropout index space as embed_bwd.
+__global__ void embed_bwd_rows_kernel(const float* __restrict__ dx, float* __restrict__ rows, long long n8, float drop_p,
+                                      const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= n8) return;
+    const Rng rng = make_rng(rng_state, drop_p);
+    float g[8], sc[8];
+    ld8(dx + gid * 8, g);
+    dropout_scale8(rng, site, (unsigned long long)gid, sc);
+#pragma unroll
+    for (int q = 0; q < 8; ++q) g[q] *= sc[q];
+    st8(rows + gid * 8, g);
+}
+
+extern "C" int vct_embed_bwd_rows(const float* dx, float* rows, int B, int S, int d, float drop_p,
+                                  const unsigned long long* rng_state, unsigned int site, vct_stream_t stream) {
+    VCT_REQUIRE(d % 8 == 0 && B > 0 && S > 0, "vct_embed_bwd_rows: need d %% 8 == 0 and non-empty input");
+    const long long n8 = (long long)B * S * (d / 8);
+    vct::launch(embed_bwd_rows_kernel, dim3((unsigned)((n8 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, dx, rows, n8, drop_p,
+                rng_state, site);
+    return check_launch("vct_embed_bwd_rows");
+}
+
+// Deterministic scatter of gathered gradient rows into the table gradient.  Every data-parallel rank runs this on the SAME
+// gathered (rows, ids) and must obtain bit-identical sums, otherwise the replicas drift apart (an atomicAdd scatter sums in
+// a run-dependent order).  Step 1 (one CTA): keys (id << 16 | token index) of the n = B*S tokens, bitonic sort in shared
+// memory (invalid / pad tokens sort to the end) -> tokens of the same id become one contiguous, index-ordered segment.
+// Step 2 (one CTA per sorted position, only segment starts work): the segment's rows are summed by four row-chunks
+// (chunk c takes segment elements c, c+4, ...; fixed order) and the four partials are added in chunk order; the row of dE
+// is WRITTEN (rows no token maps to are left untouched, i.e. zero on the trainer's path).
+constexpr int kDetMaxTokens = 16384;
+
+__global__ void __launch_bounds__(1024)
+embed_sort_kernel(const long long* __restrict__ ids, long long ids_ld, int B, int S, int V, int pad_id,
+                  unsigned int* __restrict__ keys_out, int P) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ unsigned int skeys[];
+    const int n = B * S;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        unsigned int key = 0xFFFFFFFFu;
+        if (i < n) {
+            const long long id = ids[(long long)(i / S) * ids_ld + (i % S)];
+            if (id != pad_id && id >= 0 && id < V) key = ((unsigned int)id << 16) | (unsigned int)i;
+        }
+        skeys[i] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = threadIdx.x; t < (P >> 1); t += blockDim.x) {
+                const int pos = 2 * t - (t & (stride - 1));
+                const unsigned int a = skeys[pos], b = skeys[pos + stride];
+                const bool up = (pos & size) == 0;
+                if ((a > b) == up) { skeys[pos] = b; skeys[pos + stride] = a; }
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = threadIdx.x; i < n; i += blockDim.x) keys_out[i] = skeys[i];
+}
+
+__global__ void __launch_bounds__(1024)
+embed_segment_sum_kernel(const unsigned int* __restrict__ keys, const float* __restrict__ rows, float* __restrict__ dE, int n,
+                         int d) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ int s_len;
+    extern __shared__ float4 s_part[];                     // [3][d / 4] partials of row-chunks 1..3
+    const int i = blockIdx.x;
+    const unsigned int key = keys[i];
+    if (key == 0xFFFFFFFFu) return;
+    const unsigned int id = key >> 16;
+    if (i > 0 && (keys[i - 1] >> 16) == id) return;      // not the first token of its segment
+    if (threadIdx.x == 0) s_len = n - i;
+    __syncthreads();
+    // segment length: first position whose id differs (all threads probe a window; the smallest hit wins)
+    for (int base = i + 1; base < n; base += blockDim.x) {
+        const int j = base + threadIdx.x;
+        const bool hit = j < n && (keys[j] >> 16) != id;
+        if (__syncthreads_or(hit)) {                       // block-uniform
+            if (hit) atomicMin(&s_len, j - i);
+            break;
+        }
+    }
+    __syncthreads();
+    const int len = s_len;
+    const int nv = d >> 2;
+    const int chunk = threadIdx.x / nv, c4 = threadIdx.x % nv;      // 4 row-chunks x d/4 float4 columns
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = chunk; j < len; j += 4) {
+        const unsigned int tok = keys[i + j] & 0xFFFFu;
+        const float4 v = ld4(rows + (long long)tok * d + c4 * 4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    if (chunk > 0) s_part[(chunk - 1) * nv + c4] = acc;
+    __syncthreads();
+    if (chunk == 0) {
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float4 v = s_part[c * nv + c4];
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        st4(dE + (long long)id * d + c4 * 4, acc);
+    }
+}
+
+extern "C" int vct_embed_bwd_det(const long long* ids, long long ids_ld, const float* rows, float* dE, int B, int S, int d, int V,
+                                 int pad_id, unsigned int* keys_ws, vct_stream_t stream) {
+    const long long n = (long long)B * S;
+    VCT_REQUIRE(ids && rows && dE && keys_ws && B > 0 && S > 0, "vct_embed_bwd_det: null / empty argument");
+    VCT_REQUIRE(n <= kDetMaxTokens && V <= 32768, "vct_embed_bwd_det: at most %d tokens and V <= 32768 (got %lld, %d)", kDetMaxTokens, n, V);
+    VCT_REQUIRE(d % 4 == 0 && d <= 1024, "vct_embed_bwd_det: need d %% 4 == 0 and d <= 1024");
+    int P = 2;
+    while (P < n) P <<= 1;
+    static bool once = false;
+    if (!once) {
+        VCT_CUDA(cudaFuncSetAttribute(embed_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDetMaxTokens * 4));
+        once = true;
+    }
+    vct::launch(embed_sort_kernel, dim3(1), dim3(1024), (size_t)P * 4, (cudaStream_t)stream, ids, ids_ld, B, S, V, pad_id, keys_ws, P);
+    if (int e = check_launch("vct_embed_bwd_det(sort)")) return e;
+    vct::launch(embed_segment_sum_kernel, dim3((unsigned)n), dim3(d), (size_t)3 * (d / 4) * 16, (cudaStream_t)stream,
+                (const unsigned int*)keys_ws, rows, dE, (int)n, d);
+    return check_launch("vct_embed_bwd_det(sum)");
+}
+
+// dE[ids[b, s], :] = 0: re-zero exactly the rows a step scattered into (after the optimizer consumed them), instead of
+// a 94 MB memset of the whole table gradient at the start of every step
+__global__ void embed_zero_kernel(const long long* __restrict__ ids, long long ids_ld, float* __restrict__ dE, int B, int S,
+                                  int d, int V) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nv = d >> 2;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)B * S * nv) return;
+    const int c = (int)(gid % nv);
+    const long long row = gid / nv;
+    const int b = (int)(row / S), sidx = (int)(row % S);
+    const long long id = ids[(long long)b * ids_ld + sidx];
+    if (id < 0 || id >= V) return;
+    st4(dE + id * d + c * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+}
+
+extern "C" int vct_embed_zero(const long long* ids, long long ids_ld, float* dE, int B, int S, int d, int V,
+                              vct_stream_t stream) {
+    VCT_REQUIRE(d % 4 == 0 && B > 0 && S > 0, "vct_embed_zero: need d %% 4 == 0 and non-empty input");
+    const long long n = (long long)B * S * (d / 4);
+    vct::launch(embed_zero_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, ids, ids_ld, dE, B, S, d, V);
+    return check_launch("vct_embed_zero");
+}
+
 // ------------------------------------------------------------------------------------------------
 // column sums (bias gradients): deterministic two-level reduction in one launch
 // ------------------------------------------------------------------------------------------------
@@ -581,8 +737,9 @@ __device__ __forceinline__ void adam_update4(float4& pv, const float4& gv, float
     vv = make_float4(ve[0], ve[1], ve[2], ve[3]);
 }
 
+template <typename TG>
 __global__ void __launch_bounds__(256)
-adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+adam_kernel(float* __restrict__ p, const TG* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
             __nv_bfloat16* __restrict__ p_c, long long n4, const float* __restrict__ hyper, float grad_scale) {
     pdl_launch_dependents();
     pdl_wait();
@@ -608,16 +765,22 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
     }
 }
 
-extern "C" int vct_adam(float* p, const float* g, float* m, float* v, void* p_c, long long n, const float* hyper,
+extern "C" int vct_adam(float* p, const void* g, int g_dtype, float* m, float* v, void* p_c, long long n, const float* hyper,
                         float grad_scale, vct_stream_t stream) {
     VCT_REQUIRE(n > 0 && n % 4 == 0, "vct_adam: arena length must be a positive multiple of 4 (n=%lld)", n);
+    VCT_REQUIRE(g_dtype == VCT_F32 || g_dtype == VCT_BF16, "vct_adam: bad gradient dtype");
     static const int ctas_per_sm = getenv("VCT_ADAM_CTAS_PER_SM") ? atoi(getenv("VCT_ADAM_CTAS_PER_SM")) : 8;
     const long long n4 = n / 4;
     long long want = (n4 + 511) / 512;
     const long long cap = (long long)kNumSMs * (ctas_per_sm > 0 ? ctas_per_sm : 8);
     int blocks = (int)(want < cap ? want : cap);
     if (blocks < 1) blocks = 1;
-    vct::launch(adam_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)p_c, n4, hyper, grad_scale);
+    if (g_dtype == VCT_BF16)
+        vct::launch(adam_kernel<__nv_bfloat16>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, (const __nv_bfloat16*)g, m, v,
+                    (__nv_bfloat16*)p_c, n4, hyper, grad_scale);
+    else
+        vct::launch(adam_kernel<float>, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, (const float*)g, m, v, (__nv_bfloat16*)p_c,
+                    n4, hyper, grad_scale);
     return check_launch("vct_adam");
 }
 

@@ -70,6 +70,12 @@ class ParamArena:
             self.exp_avg = torch.zeros_like(self.p32)
             self.exp_avg_sq = torch.zeros_like(self.p32)
 
+    def ensure_grad16(self) -> torch.Tensor:
+        """bf16 twin of the gradient arena: payload of the data-parallel exchange when gradients travel in bf16."""
+        if getattr(self, "grad16", None) is None:
+            self.grad16 = torch.zeros(self.numel, dtype=torch.bfloat16, device=self.device)
+        return self.grad16
+
     def ensure_shadow(self) -> torch.Tensor:
         if self.shadow is None:
             self.shadow = torch.empty(self.numel, dtype=torch.bfloat16, device=self.device)

@@ -146,6 +146,11 @@ class CaptionEngine:
         if impl == "tcgen05" and precision != "bf16":
             raise ValueError("the tcgen05 GEMM takes bf16 operands")
         self.gemm_impl = L.GEMM_TCGEN05 if impl == "tcgen05" else L.GEMM_SIMT
+        # dtype of the data-parallel gradient exchange (dense buckets): bf16 halves the NVLink bytes; fp32 storage keeps fp32
+        comm = os.environ.get("VCT_GRAD_COMM", "bf16" if precision == "bf16" else "fp32")
+        if comm not in ("bf16", "fp32"):
+            raise ValueError("VCT_GRAD_COMM must be 'bf16' or 'fp32'")
+        self.grad_comm_dtype = BF16 if comm == "bf16" else F32
         self.video_encoder, self.cap_decoder = video_encoder, cap_decoder
         named = []
         if video_encoder is not None:
@@ -256,9 +261,13 @@ class CaptionEngine:
         lane 1: weight-gradient GEMMs, bias column sums, LayerNorm partial reductions; lane 2: optimizer slices."""
         return CaptionEngine._Side(plan, lane)
 
-    def _adam_slice(self, plan: Plan, first: str, last: str):
+    def _adam_slice(self, plan: Plan, first: str, last: str, reduce: bool = True):
         """Optimizer-in-backward: update the arena slice [first .. last] (parameter names, arena order) on lane 2
-        as soon as backward has produced its gradients and no longer reads its weights."""
+        as soon as backward has produced its gradients and no longer reads its weights.  Data parallel (plan.allreduce):
+        the slice's gradient is first SUM all-reduced over NCCL on the same lane -- in bf16 when the engine computes in
+        bf16 (VCT_GRAD_COMM=fp32 keeps the exchange in fp32): the fp32 slice is cast into the bf16 gradient arena, that is
+        all-reduced (half the bytes over NVLink) and vct_adam reads the bf16 result.  reduce=False: the caller has already
+        made the slice's gradient global (sparse exchange of the embedding rows)."""
         if not getattr(plan, "fuse_adam", False):
             return
         a = self.arena
@@ -268,22 +277,30 @@ class CaptionEngine:
         a.ensure_optimizer_state()
         shadow = a.ensure_shadow().data_ptr() + 2 * lo if self.cdt == BF16 else None
         grad_scale = 1.0
+        g_ptr, g_dt = a.grad.data_ptr() + 4 * lo, F32
         with self._side(plan, 2):
             ar = getattr(plan, "allreduce", None)
             if ar is not None:
-                # data parallel: SUM all-reduce of this gradient slice over NCCL on the optimizer lane, overlapping
-                # the rest of backward; 1/world is folded into the Adam kernel (DDP averages, train.py:218)
+                # data parallel: 1/world is folded into the Adam kernel (DDP averages, train.py:218)
                 group, world = ar
-                flat = a.grad[lo:hi]
                 grad_scale = 1.0 / world
+                if reduce:
+                    if self.grad_comm_dtype == BF16:
+                        g16 = a.ensure_grad16()
+                        plan.add(f"vct_cast:{first}..{last}", self.lib.vct_cast, a.grad.data_ptr() + 4 * lo, g16.data_ptr() + 2 * lo,
+                                 BF16, hi - lo)
+                        flat = g16[lo:hi]
+                        g_ptr, g_dt = g16.data_ptr() + 2 * lo, BF16
+                    else:
+                        flat = a.grad[lo:hi]
 
-                def all_reduce(stream, flat=flat, group=group):
-                    import torch.distributed as dist
-                    with torch.cuda.stream(stream):
-                        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-                    return 0
-                plan.add(f"py:all_reduce:{first}..{last}", all_reduce)
-            plan.add(f"vct_adam:{first}..{last}", self.lib.vct_adam, a.p32.data_ptr() + 4 * lo, a.grad.data_ptr() + 4 * lo,
+                    def all_reduce(stream, flat=flat, group=group):
+                        import torch.distributed as dist
+                        with torch.cuda.stream(stream):
+                            dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+                        return 0
+                    plan.add(f"py:all_reduce:{first}..{last}", all_reduce)
+            plan.add(f"vct_adam:{first}..{last}", self.lib.vct_adam, a.p32.data_ptr() + 4 * lo, g_ptr, g_dt,
                      a.exp_avg.data_ptr() + 4 * lo, a.exp_avg_sq.data_ptr() + 4 * lo, shadow, hi - lo,
                      self.hyper.data_ptr(), grad_scale)
         plan.adam_covered = getattr(plan, "adam_covered", 0) + (hi - lo)
@@ -782,9 +799,48 @@ class CaptionEngine:
             dx, other = other, dx           # dx = grad wrt the layer input
             self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm3.bias")
         # ---- embedding ---------------------------------------------------------------------------
-        p.add("vct_embed_bwd", lib.vct_embed_bwd, ws.ids.data_ptr(), S + 1, dx.data_ptr(),
-              self._g("cap_decoder.tgt_to_emb.weight"), B, S, d, D.V, D.pad_id, pd, self.rng_state.data_ptr(), SITE_EMBED)
-        self._adam_slice(p, "cap_decoder.tgt_to_emb.weight", "cap_decoder.tgt_to_emb.weight")
+        emb = "cap_decoder.tgt_to_emb.weight"
+        sparse = getattr(p, "allreduce", None) is not None and getattr(p, "fuse_adam", False)
+        if sparse:
+            # the deterministic scatter sorts the gathered tokens inside one CTA: larger exchanges (or vocabularies) fall
+            # back to the dense all-reduce of the table gradient, which also keeps the replicas identical
+            sparse = p.allreduce[1] * Rd <= 16384 and D.V <= 32768 and os.environ.get("VCT_SPARSE_EMB", "1") != "0"
+        if not sparse:
+            p.add("vct_embed_bwd", lib.vct_embed_bwd, ws.ids.data_ptr(), S + 1, dx.data_ptr(), self._g(emb), B, S, d, D.V,
+                  D.pad_id, pd, self.rng_state.data_ptr(), SITE_EMBED)
+            self._adam_slice(p, emb, emb)
+            if getattr(p, "fuse_adam", False):
+                # the table gradient is all-zero at the start of a native-trainer step: once Adam has consumed it, only the
+                # rows this step touched are cleared again (no 94 MB memset per step)
+                with self._side(p, 2):
+                    p.add("vct_embed_zero", lib.vct_embed_zero, ws.ids.data_ptr(), S + 1, self._g(emb), B, S, d, D.V)
+        else:
+            # data parallel: the table gradient has at most B*S non-zero rows per rank.  Exchange THOSE (all-gather of the
+            # masked rows + the ids, < 4 MB per rank) and scatter every rank's rows locally, instead of all-reducing the dense
+            # 94 MB table gradient as DDP does (train.py:218); 1/world is folded into Adam like for the dense buckets.
+            group, world = p.allreduce
+            rows = self._scratch(ws, "emb.rows", Rd, d, torch.float32)
+            all_rows = self._scratch(ws, "emb.all_rows", world * Rd, d, torch.float32)
+            all_ids = torch.zeros((world * B, S + 1), dtype=torch.int64, device=self.device)
+            ws.scratch["emb.all_ids"] = all_ids
+            p.add("vct_embed_bwd_rows", lib.vct_embed_bwd_rows, dx.data_ptr(), rows.data_ptr(), B, S, d, pd,
+                  self.rng_state.data_ptr(), SITE_EMBED)
+            with self._side(p, 2):
+                def gather(stream, rows=rows, all_rows=all_rows, ids=ws.ids, all_ids=all_ids, group=group):
+                    import torch.distributed as dist
+                    with torch.cuda.stream(stream):
+                        dist.all_gather_into_tensor(all_rows, rows, group=group)
+                        dist.all_gather_into_tensor(all_ids, ids, group=group)
+                    return 0
+                keys = torch.zeros(world * Rd, dtype=torch.int32, device=self.device)
+                ws.scratch["emb.keys"] = keys
+                p.add("py:all_gather:embedding_rows", gather)
+                # every rank sums the same rows in the same order: bit-identical table gradients, replicas cannot drift
+                p.add("vct_embed_bwd_det:gathered", lib.vct_embed_bwd_det, all_ids.data_ptr(), S + 1, all_rows.data_ptr(),
+                      self._g(emb), world * B, S, d, D.V, D.pad_id, keys.data_ptr())
+            self._adam_slice(p, emb, emb, reduce=False)
+            with self._side(p, 2):
+                p.add("vct_embed_zero", lib.vct_embed_zero, all_ids.data_ptr(), S + 1, self._g(emb), world * B, S, d, D.V)
 
     def _build_encoder_bwd(self, p: Plan, ws):
         D, lib = self.dims, self.lib
@@ -902,8 +958,15 @@ class CaptionEngine:
     def adam(self, grad_scale: float = 1.0) -> None:
         a = self.arena
         shadow = a.ensure_shadow().data_ptr() if self.cdt == BF16 else None
-        L.check(self.lib.vct_adam(a.p32.data_ptr(), a.grad.data_ptr(), a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(), shadow,
+        L.check(self.lib.vct_adam(a.p32.data_ptr(), a.grad.data_ptr(), F32, a.exp_avg.data_ptr(), a.exp_avg_sq.data_ptr(), shadow,
                                   a.numel, self.hyper.data_ptr(), grad_scale, self._stream()), "vct_adam")
+        self.launches += 1
+
+    def embed_zero(self, ws) -> None:
+        """Clear the embedding-gradient rows the step of ``ws`` scattered into (non-fused optimizer path)."""
+        D = self.dims
+        L.check(self.lib.vct_embed_zero(ws.ids.data_ptr(), ws.S + 1, self._g("cap_decoder.tgt_to_emb.weight"), ws.B, ws.S, D.d, D.V,
+                                        self._stream()), "vct_embed_zero")
         self.launches += 1
 
     # ------------------------------------------------------------------------------------------

@@ -91,10 +91,13 @@ SIGNATURES = {
     "vct_zero_rows": (i32, [vp, vp, i32, i32, vp]),
     "vct_embed_fwd": (i32, [vp, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, u32, vp]),
     "vct_embed_bwd": (i32, [vp, ll, vp, vp, i32, i32, i32, i32, i32, f32, vp, u32, vp]),
+    "vct_embed_bwd_rows": (i32, [vp, vp, i32, i32, i32, f32, vp, u32, vp]),
+    "vct_embed_bwd_det": (i32, [vp, ll, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "vct_embed_zero": (i32, [vp, ll, vp, i32, i32, i32, i32, vp]),
     "vct_sce": (i32, [vp, ll, vp, ll, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, i32, ll, vp, vp]),
     "vct_colsum_workspace_floats": (ll, [i32, i32]),
     "vct_colsum": (i32, [vp, i32, ll, i32, i32, vp, vp, vp, vp]),
-    "vct_adam": (i32, [vp, vp, vp, vp, vp, ll, vp, f32, vp]),
+    "vct_adam": (i32, [vp, vp, i32, vp, vp, vp, ll, vp, f32, vp]),
     "vct_cast": (i32, [vp, vp, i32, ll, vp]),
     "vct_argmax_append": (i32, [vp, ll, i32, i32, vp, ll, i32, i32, vp, vp, vp]),
     "vct_dropout_mask": (i32, [vp, ll, f32, vp, u32, vp]),

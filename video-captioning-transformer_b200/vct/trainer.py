@@ -8,15 +8,43 @@ arenas, optionally captured in a CUDA graph.
 Data parallelism is the reference's: one process per GPU, batch sharded by the caller
 (DistributedSampler, dataloader.py:524), gradients averaged across ranks (DDP, train.py:218).  Here the
 "bucket" is a slice of the flat gradient arena, so no flatten/copy is needed; slices are all-reduced
-(SUM) on a side stream as soon as the backward plan has produced them and the 1/world_size factor is
-folded into the Adam kernel.
+(SUM; in bf16 when the engine computes in bf16) on a side stream as soon as the backward plan has produced
+them and the 1/world_size factor is folded into the Adam kernel.  The embedding-table gradient -- 94 MB
+dense, at most B*S non-zero rows -- is exchanged in its sparse form (all-gather of rows + ids, local scatter).
 """
+
+
 from __future__ import annotations
 
 import os
 from typing import List, Optional, Tuple
 
 import torch
+
+
+def gather_embedding_rows(rows: torch.Tensor, ids: torch.Tensor, group=None):
+    """Sparse exchange of the embedding-table gradient: every rank contributes its [B*S, d] masked gradient rows and
+    its [B, S+1] token ids; returns (all_rows [world*B*S, d], all_ids [world*B, S+1]).  Scattering all_rows by
+    all_ids[:, :-1] (skipping pad ids) gives the SUM over ranks of the dense table gradients -- what DDP's all-reduce of
+    the dense gradient produces (train.py:218) before its 1/world averaging.  Any backend (nccl / gloo)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    all_rows = rows.new_empty((world * rows.shape[0],) + tuple(rows.shape[1:]))
+    all_ids = ids.new_empty((world * ids.shape[0],) + tuple(ids.shape[1:]))
+    dist.all_gather_into_tensor(all_rows, rows.contiguous(), group=group)
+    dist.all_gather_into_tensor(all_ids, ids.contiguous(), group=group)
+    return all_rows, all_ids
+
+
+def scatter_embedding_rows(all_rows: torch.Tensor, all_ids: torch.Tensor, V: int, pad_id: int) -> torch.Tensor:
+    """Dense [V, d] table gradient from gathered rows (host-side restatement of vct_embed_bwd with drop_p = 0;
+    used by the CPU tests of the exchange scheme)."""
+    d = all_rows.shape[-1]
+    tgt = all_ids[:, :-1].reshape(-1)
+    keep = tgt != pad_id
+    out = torch.zeros(V, d, dtype=all_rows.dtype, device=all_rows.device)
+    out.index_add_(0, tgt[keep], all_rows.reshape(-1, d)[keep])
+    return out
 
 
 def gradient_buckets(arena, order: List[str], max_bytes: int = 64 << 20) -> List[Tuple[int, int]]:
@@ -89,6 +117,9 @@ class CaptionTrainer:
             raise ValueError("CaptionTrainer drives the caption task: call model.mode('caption') first")
         self.engine.set_adam(lr, betas, eps, weight_decay)
         self.engine.refresh_shadow(force=True)
+        # invariant of the native step: the embedding-table gradient is all-zero when a step starts (each step re-zeroes
+        # only the rows it scattered into, vct_embed_zero); establish it once
+        self.engine.zero_scatter_grads()
         self.use_graph = use_graph
         self.fuse_adam = os.environ.get("VCT_FUSE_ADAM", "1") != "0" and self.engine.side_streams is not None
         self.group = process_group
@@ -119,18 +150,19 @@ class CaptionTrainer:
     def _compute(self, ws, fuse_adam: bool = False, allreduce=None) -> None:
         eng = self.engine
         eng.tick()
-        eng.zero_scatter_grads()
+        # (the embedding-table gradient is all-zero here: the previous step cleared the rows it had scattered into)
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
         eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=fuse_adam, allreduce=allreduce))
 
     def _forward(self, ws) -> None:
         eng = self.engine
         eng.tick()
-        eng.zero_scatter_grads()
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
 
-    def _update(self) -> None:
+    def _update(self, ws=None) -> None:
         self.engine.adam(grad_scale=1.0 / self.world)
+        if ws is not None:
+            self.engine.embed_zero(ws)
 
     def _graphed(self, key, fn, ws=None):
         """Run ``fn`` eagerly twice (plan building, kernel attributes), then capture it once and replay.  Graphs over a
@@ -232,7 +264,7 @@ class CaptionTrainer:
             # optimizer-in-backward: vct_adam runs slice by slice on a side lane while backward continues
             self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True), ws=ws)
         elif self.world == 1:
-            self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update()), ws=ws)
+            self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update(ws)), ws=ws)
         elif self.fuse_adam and self.segmented:
             # data parallel: forward is one CUDA graph and backward a chain of graph SEGMENTS -- the launches between two
             # optimizer slices are captured together -- with the per-slice NCCL all-reduce + Adam issued eagerly on the
@@ -247,7 +279,8 @@ class CaptionTrainer:
             self._graphed((B, T, S, "forward"), lambda: self._forward(ws), ws=ws)
             eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=(self.group, self.world)))
         else:
+            # (dense exchange of every gradient incl. the embedding table: the reference's DDP scheme, kept for comparison)
             self._graphed((B, T, S, "compute"), lambda: self._compute(ws), ws=ws)
             all_reduce_flat(eng.arena.grad, self.buckets, self.group)
-            self._graphed(("update",), self._update)
+            self._graphed((B, T, S, "update"), lambda: self._update(ws), ws=ws)
         return ws.loss[0]
