@@ -241,6 +241,15 @@ int vct_embed_bwd_rows(const float* dx, float* rows, int B, int S, int d, float 
  * Limits: B*S <= 16384, V <= 32768, d % 4 == 0, d <= 1024. */
 int vct_embed_bwd_det(const long long* ids, long long ids_ld, const float* rows, float* dE, int B, int S, int d, int V,
                       int pad_id, unsigned int* keys_ws, vct_stream_t stream);
+/* The two halves of vct_embed_bwd_det: the sort depends on the ids only, so the trainer runs it at the START of a step
+ * (off the tail of backward) and only the segment sums once the gradient rows have been gathered. */
+int vct_embed_sort(const long long* ids, long long ids_ld, int B, int S, int V, int pad_id, unsigned int* keys_ws,
+                   vct_stream_t stream);
+int vct_embed_segment_sum(const unsigned int* keys, const float* rows, float* dE, int n, int d, vct_stream_t stream);
+/* stamp[id] = current step (rng_state[1]) for every non-pad token id: row `id` of the table is touched by this step iff
+ * stamp[id] == step.  uint32 [V], never cleared. */
+int vct_embed_mark(const long long* ids, long long ids_ld, int B, int S, int V, int pad_id, unsigned int* stamp,
+                   const unsigned long long* rng_state, vct_stream_t stream);
 /* dE[ids[b*ids_ld + s], :] = 0 for every (b, s): re-zeroes exactly the rows vct_embed_bwd scattered into, once the
  * optimizer has consumed them (replaces a memset of the whole table gradient per step; optimizer.zero_grad, train.py:124). */
 int vct_embed_zero(const long long* ids, long long ids_ld, float* dE, int B, int S, int d, int V, vct_stream_t stream);
@@ -273,6 +282,14 @@ int vct_colsum(const void* X, int dtype, long long ld, int M, int N, float* out,
  * writes the bf16 shadow copy the tensor-core GEMMs read next step. */
 int vct_adam(float* p, const void* g, int g_dtype, float* m, float* v, void* p_c, long long n, const float* hyper,
              float grad_scale, vct_stream_t stream);
+
+/* Adam on the rows of a [R, d] table (the embedding) selected by the step stamps of vct_embed_mark: touched = 0 updates the
+ * rows this step does NOT touch -- their gradient is identically zero and is not read; torch.optim.Adam still decays m, v
+ * and moves p along m for them -- which needs nothing from this step's backward and is issued at the start of the step;
+ * touched = 1 updates the (at most B*S) rows that received gradient, at the end.  Together they equal vct_adam over the
+ * table.  g may be NULL when touched = 0. */
+int vct_adam_rows(float* p, const float* g, float* m, float* v, void* p_c, int R, int d, const float* hyper, float grad_scale,
+                  const unsigned int* stamp, const unsigned long long* rng_state, int touched, vct_stream_t stream);
 
 /* fp32 -> dtype copy (initial bf16 shadow of the parameters, input staging) */
 int vct_cast(const float* src, void* dst, int dst_dtype, long long n, vct_stream_t stream);

@@ -10,14 +10,24 @@ args = ap.parse_args()
 from model.MMT4Caption import MMT4Caption
 from vct.synthetic import make_tokenizer_dir, shipped_model_config, synth_batch
 from vct.trainer import CaptionTrainer
-dev = torch.device("cuda", 0)
-tok = os.path.join(ROOT, "gpurun_out", "_tok"); make_tokenizer_dir(tok)
+# under torchrun (WORLD_SIZE > 1) every rank trains data-parallel and rank 0 prints ITS timeline (NCCL kernels included)
+rank, local, world = int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+if world > 1:
+    import torch.distributed as dist
+    dist.init_process_group("nccl", device_id=dev)
+tok = os.path.join(ROOT, "gpurun_out", "_tok")
+if rank == 0:
+    make_tokenizer_dir(tok)
+if world > 1:
+    dist.barrier()
 torch.manual_seed(666)
 model = MMT4Caption(shipped_model_config(tok), device=dev).to(dev)
 model.vct_precision, model.vct_gemm = "bf16", None
 model.mode("caption"); model.train()
 tr = CaptionTrainer(model, lr=1e-4)
-x, vm, ids = synth_batch(args.batch, 12, 512, 21)
+x, vm, ids = synth_batch(args.batch, 12, 512, 21, seed=1234 + rank)
 x, vm, ids = x.to(dev), vm.to(dev), ids.to(dev)
 for _ in range(6):
     tr.step(x, vm, ids)
@@ -26,6 +36,12 @@ with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
     for _ in range(3):
         tr.step(x, vm, ids)
     torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+if rank != 0:
+    if world > 1:
+        dist.destroy_process_group()
+    sys.exit(0)
 path = os.path.join(ROOT, "gpurun_out", "trace_step.json")
 prof.export_chrome_trace(path)
 ev = [e for e in json.load(open(path))["traceEvents"] if e.get("cat") == "kernel"]

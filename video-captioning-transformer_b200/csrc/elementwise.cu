@@ -586,12 +586,11 @@ embed_segment_sum_kernel(const unsigned int* __restrict__ keys, const float* __r
     }
 }
 
-extern "C" int vct_embed_bwd_det(const long long* ids, long long ids_ld, const float* rows, float* dE, int B, int S, int d, int V,
-                                 int pad_id, unsigned int* keys_ws, vct_stream_t stream) {
+extern "C" int vct_embed_sort(const long long* ids, long long ids_ld, int B, int S, int V, int pad_id, unsigned int* keys_ws,
+                              vct_stream_t stream) {
     const long long n = (long long)B * S;
-    VCT_REQUIRE(ids && rows && dE && keys_ws && B > 0 && S > 0, "vct_embed_bwd_det: null / empty argument");
-    VCT_REQUIRE(n <= kDetMaxTokens && V <= 32768, "vct_embed_bwd_det: at most %d tokens and V <= 32768 (got %lld, %d)", kDetMaxTokens, n, V);
-    VCT_REQUIRE(d % 4 == 0 && d <= 1024, "vct_embed_bwd_det: need d %% 4 == 0 and d <= 1024");
+    VCT_REQUIRE(ids && keys_ws && B > 0 && S > 0, "vct_embed_sort: null / empty argument");
+    VCT_REQUIRE(n <= kDetMaxTokens && V <= 32768, "vct_embed_sort: at most %d tokens and V <= 32768 (got %lld, %d)", kDetMaxTokens, n, V);
     int P = 2;
     while (P < n) P <<= 1;
     static bool once = false;
@@ -600,10 +599,42 @@ extern "C" int vct_embed_bwd_det(const long long* ids, long long ids_ld, const f
         once = true;
     }
     vct::launch(embed_sort_kernel, dim3(1), dim3(1024), (size_t)P * 4, (cudaStream_t)stream, ids, ids_ld, B, S, V, pad_id, keys_ws, P);
-    if (int e = check_launch("vct_embed_bwd_det(sort)")) return e;
-    vct::launch(embed_segment_sum_kernel, dim3((unsigned)n), dim3(d), (size_t)3 * (d / 4) * 16, (cudaStream_t)stream,
-                (const unsigned int*)keys_ws, rows, dE, (int)n, d);
-    return check_launch("vct_embed_bwd_det(sum)");
+    return check_launch("vct_embed_sort");
+}
+
+extern "C" int vct_embed_segment_sum(const unsigned int* keys, const float* rows, float* dE, int n, int d, vct_stream_t stream) {
+    VCT_REQUIRE(keys && rows && dE && n > 0 && n <= kDetMaxTokens, "vct_embed_segment_sum: bad argument (n <= %d)", kDetMaxTokens);
+    VCT_REQUIRE(d % 4 == 0 && d <= 1024, "vct_embed_segment_sum: need d %% 4 == 0 and d <= 1024");
+    vct::launch(embed_segment_sum_kernel, dim3((unsigned)n), dim3(d), (size_t)3 * (d / 4) * 16, (cudaStream_t)stream, keys, rows, dE, n, d);
+    return check_launch("vct_embed_segment_sum");
+}
+
+extern "C" int vct_embed_bwd_det(const long long* ids, long long ids_ld, const float* rows, float* dE, int B, int S, int d, int V,
+                                 int pad_id, unsigned int* keys_ws, vct_stream_t stream) {
+    VCT_REQUIRE(rows && dE, "vct_embed_bwd_det: null argument");
+    if (int e = vct_embed_sort(ids, ids_ld, B, S, V, pad_id, keys_ws, stream)) return e;
+    return vct_embed_segment_sum(keys_ws, rows, dE, B * S, d, stream);
+}
+
+// stamp[id] = current training step (rng_state[1]) for every token id of the batch: "this step touches row id of the
+// embedding table".  No clearing pass: a row is touched in step t iff stamp[row] == t.
+__global__ void embed_mark_kernel(const long long* __restrict__ ids, long long ids_ld, int B, int S, int V, int pad_id,
+                                  unsigned int* __restrict__ stamp, const unsigned long long* __restrict__ rng_state) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * S) return;
+    const long long id = ids[(long long)(i / S) * ids_ld + (i % S)];
+    if (id == pad_id || id < 0 || id >= V) return;
+    stamp[id] = (unsigned int)rng_state[1];
+}
+
+extern "C" int vct_embed_mark(const long long* ids, long long ids_ld, int B, int S, int V, int pad_id, unsigned int* stamp,
+                              const unsigned long long* rng_state, vct_stream_t stream) {
+    VCT_REQUIRE(ids && stamp && rng_state && B > 0 && S > 0, "vct_embed_mark: null / empty argument");
+    vct::launch(embed_mark_kernel, dim3((unsigned)((B * S + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, ids, ids_ld, B, S, V, pad_id,
+                stamp, rng_state);
+    return check_launch("vct_embed_mark");
 }
 
 // dE[ids[b, s], :] = 0: re-zero exactly the rows a step scattered into (after the optimizer consumed them), instead of
@@ -763,6 +794,45 @@ adam_kernel(float* __restrict__ p, const TG* __restrict__ g, float* __restrict__
         st4(p + i * 4, p0); st4(m + i * 4, m0); st4(v + i * 4, v0);
         if (p_c) st4(p_c + i * 4, p0);
     }
+}
+
+// Adam restricted to the rows of a [R, d] table that this step touched (touched = 1, gradient read from g) or did not
+// touch (touched = 0, gradient is identically zero and is not read): the embedding table's 23 M parameters receive
+// gradient in at most B*S rows per step, so all the other rows can be updated -- m, v decay, p moves along m -- before
+// the step's backward has produced anything, off the critical tail of the step.
+__global__ void __launch_bounds__(256)
+adam_rows_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                 __nv_bfloat16* __restrict__ p_c, long long n4, int d4, const float* __restrict__ hyper, float grad_scale,
+                 const unsigned int* __restrict__ stamp, const unsigned long long* __restrict__ rng_state, int touched) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const float lr = hyper[0], b1 = hyper[1], b2 = hyper[2], eps = hyper[3], wd = hyper[4];
+    const float step_size = lr / hyper[6], inv_sqrt_bc2 = rsqrtf(hyper[7]);
+    const unsigned int now = (unsigned int)rng_state[1];
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        const bool is_touched = stamp[i / d4] == now;
+        if ((int)is_touched != touched) continue;
+        float4 p0 = ld4(p + i * 4), m0 = ld4(m + i * 4), v0 = ld4(v + i * 4);
+        float4 g0 = touched ? ld4(g + i * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+        adam_update4(p0, g0, m0, v0, grad_scale, wd, b1, b2, eps, step_size, inv_sqrt_bc2);
+        st4(p + i * 4, p0); st4(m + i * 4, m0); st4(v + i * 4, v0);
+        if (p_c) st4(p_c + i * 4, p0);
+    }
+}
+
+extern "C" int vct_adam_rows(float* p, const float* g, float* m, float* v, void* p_c, int R, int d, const float* hyper,
+                             float grad_scale, const unsigned int* stamp, const unsigned long long* rng_state, int touched,
+                             vct_stream_t stream) {
+    VCT_REQUIRE(p && m && v && hyper && stamp && rng_state && R > 0 && d > 0 && d % 4 == 0, "vct_adam_rows: bad argument");
+    VCT_REQUIRE(touched == 0 || g != nullptr, "vct_adam_rows: touched rows need their gradient");
+    const long long n4 = (long long)R * (d / 4);
+    long long want = (n4 + 255) / 256;
+    const long long cap = (long long)kNumSMs * 8;
+    const int blocks = (int)(want < cap ? want : cap);
+    vct::launch(adam_rows_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, (__nv_bfloat16*)p_c, n4, d / 4, hyper,
+                grad_scale, stamp, rng_state, touched);
+    return check_launch("vct_adam_rows");
 }
 
 extern "C" int vct_adam(float* p, const void* g, int g_dtype, float* m, float* v, void* p_c, long long n, const float* hyper,

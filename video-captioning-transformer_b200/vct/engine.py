@@ -45,6 +45,7 @@ class Plan:
         self.calls: List[Tuple] = []
         self.keep: List = []      # keeps ctypes structs / tensors alive
         self.lane = 0             # lane given to calls added while it is set (see CaptionEngine._side)
+        self.no_final_join = False   # leave the side lanes un-joined: a later plan of the same step joins them
         self._events: List = []
 
     def add(self, name: str, fn, *args):
@@ -114,7 +115,7 @@ class Plan:
             if rc:
                 L.check(rc, name)
         for k in range(1, nl):
-            if used[k]:
+            if used[k] and not self.no_final_join:
                 e = event()
                 e.record(sides[k - 1])
                 main.wait_event(e)
@@ -172,6 +173,8 @@ class CaptionEngine:
         self.hyper = torch.zeros(8, dtype=torch.float32, device=device)
         self.counters = torch.zeros(1024, dtype=torch.int32, device=device)
         self.upstream = torch.ones(1, dtype=torch.float32, device=device)
+        # step stamp per embedding row (vct_embed_mark): which rows of the table the current step touches
+        self.emb_stamp = torch.zeros(max(1, int(self.dims.V)), dtype=torch.int32, device=device)
         self.side_streams = [torch.cuda.Stream(device=device) for _ in range(2)] \
             if os.environ.get("VCT_SIDE_STREAM", "1") != "0" else None
         self._tempo: Dict[int, torch.Tensor] = {}
@@ -304,6 +307,67 @@ class CaptionEngine:
                      a.exp_avg.data_ptr() + 4 * lo, a.exp_avg_sq.data_ptr() + 4 * lo, shadow, hi - lo,
                      self.hyper.data_ptr(), grad_scale)
         plan.adam_covered = getattr(plan, "adam_covered", 0) + (hi - lo)
+
+    def emb_mode(self, ws, world: int) -> str:
+        """How the native trainer treats the embedding-table gradient of this workspace:
+        'local'  one GPU: atomic scatter, Adam split into untouched rows (start of the step) and touched rows (end)
+        'sparse' data parallel: ids gathered and sorted at the start of the step, gradient rows all-gathered and summed by
+                 the deterministic segment kernel, same Adam split
+        'dense'  data parallel with more tokens / a larger vocabulary than the one-CTA sort covers: the dense table gradient
+                 is all-reduced like every other bucket"""
+        if os.environ.get("VCT_SPLIT_EMB_ADAM", "1") == "0":
+            return "dense" if world > 1 else "local-unsplit"
+        if world == 1:
+            return "local"
+        ok = world * ws.B * ws.S <= 16384 and self.dims.V <= 32768 and os.environ.get("VCT_SPARSE_EMB", "1") != "0"
+        return "sparse" if ok else "dense"
+
+    def emb_buffers(self, ws, world: int):
+        """(all_ids [world*B, S+1] int64, all_rows [world*B*S, d] fp32, rows [B*S, d] fp32, keys int32 [world*B*S])."""
+        key = ("emb.buffers", world)
+        if key not in ws.scratch:
+            Rd = ws.B * ws.S
+            ws.scratch[key] = (torch.zeros((world * ws.B, ws.S + 1), dtype=torch.int64, device=self.device),
+                               torch.empty((world * Rd, self.dims.d), dtype=torch.float32, device=self.device),
+                               torch.empty((Rd, self.dims.d), dtype=torch.float32, device=self.device),
+                               torch.zeros(world * Rd, dtype=torch.int32, device=self.device))
+        return ws.scratch[key]
+
+    def _emb_range(self):
+        a = self.arena
+        emb = "cap_decoder.tgt_to_emb.weight"
+        lo = a.offset[emb]
+        i = a.names.index(emb)
+        hi = a.offset[a.names[i + 1]] if i + 1 < len(a.names) else a.numel
+        return emb, lo, hi
+
+    def plan_embed_early(self, ws, world: int) -> Plan:
+        """Start-of-step half of the embedding update (optimizer lane, left un-joined): stamp the rows this step touches
+        (for world > 1 from the all-gathered ids, which the trainer has placed in emb_buffers()[0]), sort the gathered
+        tokens for the deterministic scatter, and run Adam on every row the step does NOT touch."""
+        key = ("embed_early", world)
+        if key not in ws.plans:
+            D, lib, a = self.dims, self.lib, self.arena
+            emb, lo, _hi = self._emb_range()
+            a.ensure_optimizer_state()
+            p = Plan()
+            p.ws = ws
+            p.no_final_join = True
+            ids_ptr, nB = ws.ids.data_ptr(), ws.B
+            if world > 1:
+                all_ids, _, _, keys = self.emb_buffers(ws, world)
+                ids_ptr, nB = all_ids.data_ptr(), world * ws.B
+            shadow = a.ensure_shadow().data_ptr() + 2 * lo if self.cdt == BF16 else None
+            with self._side(p, 2):
+                p.add("vct_embed_mark", lib.vct_embed_mark, ids_ptr, ws.S + 1, nB, ws.S, D.V, D.pad_id, self.emb_stamp.data_ptr(),
+                      self.rng_state.data_ptr())
+                if world > 1:
+                    p.add("vct_embed_sort", lib.vct_embed_sort, ids_ptr, ws.S + 1, nB, ws.S, D.V, D.pad_id, keys.data_ptr())
+                p.add("vct_adam_rows:untouched", lib.vct_adam_rows, a.p32.data_ptr() + 4 * lo, None, a.exp_avg.data_ptr() + 4 * lo,
+                      a.exp_avg_sq.data_ptr() + 4 * lo, shadow, D.V, D.d, self.hyper.data_ptr(), 1.0, self.emb_stamp.data_ptr(),
+                      self.rng_state.data_ptr(), 0)
+            ws.plans[key] = p
+        return ws.plans[key]
 
     def _scratch(self, ws, tag: str, rows: int, cols: int, dtype) -> torch.Tensor:
         """Per-use gradient scratch (never shared between call sites, so side-stream readers cannot race
@@ -799,47 +863,57 @@ class CaptionEngine:
             dx, other = other, dx           # dx = grad wrt the layer input
             self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm3.bias")
         # ---- embedding ---------------------------------------------------------------------------
-        emb = "cap_decoder.tgt_to_emb.weight"
-        sparse = getattr(p, "allreduce", None) is not None and getattr(p, "fuse_adam", False)
-        if sparse:
-            # the deterministic scatter sorts the gathered tokens inside one CTA: larger exchanges (or vocabularies) fall
-            # back to the dense all-reduce of the table gradient, which also keeps the replicas identical
-            sparse = p.allreduce[1] * Rd <= 16384 and D.V <= 32768 and os.environ.get("VCT_SPARSE_EMB", "1") != "0"
-        if not sparse:
+        emb, e_lo, e_hi = self._emb_range()
+        fused = getattr(p, "fuse_adam", False)
+        world = p.allreduce[1] if getattr(p, "allreduce", None) is not None else 1
+        mode = self.emb_mode(ws, world) if fused else "plain"
+        a = self.arena
+        if fused:
+            a.ensure_optimizer_state()
+        shadow = a.ensure_shadow().data_ptr() + 2 * e_lo if (fused and cd == BF16) else None
+
+        def touched_adam(grad_scale):
+            # end-of-step half of the embedding update: only the rows that received gradient (see plan_embed_early)
+            p.add("vct_adam_rows:touched", lib.vct_adam_rows, a.p32.data_ptr() + 4 * e_lo, self._g(emb), a.exp_avg.data_ptr() + 4 * e_lo,
+                  a.exp_avg_sq.data_ptr() + 4 * e_lo, shadow, D.V, d, self.hyper.data_ptr(), grad_scale, self.emb_stamp.data_ptr(),
+                  self.rng_state.data_ptr(), 1)
+            p.adam_covered = getattr(p, "adam_covered", 0) + (e_hi - e_lo)
+
+        if mode in ("plain", "local-unsplit", "dense"):
             p.add("vct_embed_bwd", lib.vct_embed_bwd, ws.ids.data_ptr(), S + 1, dx.data_ptr(), self._g(emb), B, S, d, D.V,
                   D.pad_id, pd, self.rng_state.data_ptr(), SITE_EMBED)
             self._adam_slice(p, emb, emb)
-            if getattr(p, "fuse_adam", False):
+            if fused:
                 # the table gradient is all-zero at the start of a native-trainer step: once Adam has consumed it, only the
                 # rows this step touched are cleared again (no 94 MB memset per step)
                 with self._side(p, 2):
                     p.add("vct_embed_zero", lib.vct_embed_zero, ws.ids.data_ptr(), S + 1, self._g(emb), B, S, d, D.V)
+        elif mode == "local":
+            p.add("vct_embed_bwd", lib.vct_embed_bwd, ws.ids.data_ptr(), S + 1, dx.data_ptr(), self._g(emb), B, S, d, D.V,
+                  D.pad_id, pd, self.rng_state.data_ptr(), SITE_EMBED)
+            with self._side(p, 2):
+                touched_adam(1.0)
+                p.add("vct_embed_zero", lib.vct_embed_zero, ws.ids.data_ptr(), S + 1, self._g(emb), B, S, d, D.V)
         else:
             # data parallel: the table gradient has at most B*S non-zero rows per rank.  Exchange THOSE (all-gather of the
-            # masked rows + the ids, < 4 MB per rank) and scatter every rank's rows locally, instead of all-reducing the dense
-            # 94 MB table gradient as DDP does (train.py:218); 1/world is folded into Adam like for the dense buckets.
-            group, world = p.allreduce
-            rows = self._scratch(ws, "emb.rows", Rd, d, torch.float32)
-            all_rows = self._scratch(ws, "emb.all_rows", world * Rd, d, torch.float32)
-            all_ids = torch.zeros((world * B, S + 1), dtype=torch.int64, device=self.device)
-            ws.scratch["emb.all_ids"] = all_ids
+            # masked rows; the ids were gathered and sorted at the start of the step) and sum every rank's rows locally in a
+            # fixed order, instead of all-reducing the dense 94 MB table gradient as DDP does (train.py:218); 1/world is
+            # folded into Adam like for the dense buckets.
+            group = p.allreduce[0]
+            all_ids, all_rows, rows, keys = self.emb_buffers(ws, world)
             p.add("vct_embed_bwd_rows", lib.vct_embed_bwd_rows, dx.data_ptr(), rows.data_ptr(), B, S, d, pd,
                   self.rng_state.data_ptr(), SITE_EMBED)
             with self._side(p, 2):
-                def gather(stream, rows=rows, all_rows=all_rows, ids=ws.ids, all_ids=all_ids, group=group):
+                def gather(stream, rows=rows, all_rows=all_rows, group=group):
                     import torch.distributed as dist
                     with torch.cuda.stream(stream):
                         dist.all_gather_into_tensor(all_rows, rows, group=group)
-                        dist.all_gather_into_tensor(all_ids, ids, group=group)
                     return 0
-                keys = torch.zeros(world * Rd, dtype=torch.int32, device=self.device)
-                ws.scratch["emb.keys"] = keys
                 p.add("py:all_gather:embedding_rows", gather)
                 # every rank sums the same rows in the same order: bit-identical table gradients, replicas cannot drift
-                p.add("vct_embed_bwd_det:gathered", lib.vct_embed_bwd_det, all_ids.data_ptr(), S + 1, all_rows.data_ptr(),
-                      self._g(emb), world * B, S, d, D.V, D.pad_id, keys.data_ptr())
-            self._adam_slice(p, emb, emb, reduce=False)
-            with self._side(p, 2):
+                p.add("vct_embed_segment_sum", lib.vct_embed_segment_sum, keys.data_ptr(), all_rows.data_ptr(), self._g(emb),
+                      world * Rd, d)
+                touched_adam(1.0 / world)
                 p.add("vct_embed_zero", lib.vct_embed_zero, all_ids.data_ptr(), S + 1, self._g(emb), world * B, S, d, D.V)
 
     def _build_encoder_bwd(self, p: Plan, ws):

@@ -93,6 +93,10 @@ SIGNATURES = {
     "vct_embed_bwd": (i32, [vp, ll, vp, vp, i32, i32, i32, i32, i32, f32, vp, u32, vp]),
     "vct_embed_bwd_rows": (i32, [vp, vp, i32, i32, i32, f32, vp, u32, vp]),
     "vct_embed_bwd_det": (i32, [vp, ll, vp, vp, i32, i32, i32, i32, i32, vp, vp]),
+    "vct_embed_sort": (i32, [vp, ll, i32, i32, i32, i32, vp, vp]),
+    "vct_embed_segment_sum": (i32, [vp, vp, vp, i32, i32, vp]),
+    "vct_embed_mark": (i32, [vp, ll, i32, i32, i32, i32, vp, vp, vp]),
+    "vct_adam_rows": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, f32, vp, vp, i32, vp]),
     "vct_embed_zero": (i32, [vp, ll, vp, i32, i32, i32, i32, vp]),
     "vct_sce": (i32, [vp, ll, vp, ll, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, i32, ll, vp, vp]),
     "vct_colsum_workspace_floats": (ll, [i32, i32]),

@@ -151,13 +151,46 @@ class CaptionTrainer:
         eng = self.engine
         eng.tick()
         # (the embedding-table gradient is all-zero here: the previous step cleared the rows it had scattered into)
+        if fuse_adam and eng.emb_mode(ws, 1) == "local":
+            eng.run(eng.plan_embed_early(ws, 1))        # optimizer lane, un-joined: overlaps the whole forward
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
         eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=fuse_adam, allreduce=allreduce))
 
-    def _forward(self, ws) -> None:
+    def _forward(self, ws, tick: bool = True) -> None:
         eng = self.engine
-        eng.tick()
+        early = tick and self.fuse_adam and eng.emb_mode(ws, 1) == "local"
+        if tick:
+            eng.tick()
+        if early:
+            eng.run(eng.plan_embed_early(ws, 1))
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
+        if early and eng.side_streams:
+            # this graph ends with the forward: the optimizer lane forked above must re-join before capture ends
+            torch.cuda.current_stream(eng.device).wait_stream(eng.side_streams[1])
+
+    def _early_embedding(self, ws) -> None:
+        """Data parallel, start of a step (eager, outside the graphs): all-gather the token ids of every rank on the comm
+        stream, then -- optimizer stream -- stamp the touched table rows, sort the gathered tokens for the deterministic
+        scatter and run Adam on all untouched rows of the embedding table.  Everything here overlaps the forward graph."""
+        import torch.distributed as dist
+        from . import lib as L
+        eng = self.engine
+        if eng.emb_mode(ws, self.world) != "sparse":
+            return
+        main = torch.cuda.current_stream(eng.device)
+        opt, comm = eng.side_streams[1], self.comm_stream
+        all_ids = eng.emb_buffers(ws, self.world)[0]
+        ev = ws.graphs.setdefault("_early_events", (torch.cuda.Event(), torch.cuda.Event()))
+        ev[0].record(main)                                   # ids staged, step ticked
+        comm.wait_event(ev[0])
+        opt.wait_event(ev[0])
+        with torch.cuda.stream(comm):
+            dist.all_gather_into_tensor(all_ids, ws.ids, group=self.group)
+        ev[1].record(comm)
+        opt.wait_event(ev[1])
+        for name, fn, args, _lane in eng.plan_embed_early(ws, self.world).calls:
+            L.check(fn(*args, opt.cuda_stream), name)
+            eng.launches += 1
 
     def _update(self, ws=None) -> None:
         self.engine.adam(grad_scale=1.0 / self.world)
@@ -221,25 +254,44 @@ class CaptionTrainer:
                     g = torch.cuda.CUDAGraph()
                     with torch.cuda.graph(g):
                         n = sub.run(torch.cuda.current_stream(eng.device), eng.side_streams)
-                built.append((g, n, opt_calls, torch.cuda.Event(), sub if real else None))
-            segments[key] = (built, torch.cuda.Event())
-        built, done = segments[key]
+                built.append((g, n, opt_calls, torch.cuda.Event(), sub if real else None,
+                              [torch.cuda.Event() for _ in opt_calls]))
+            segments[key] = (built, torch.cuda.Event(), torch.cuda.Event())
+        built, done, done_comm = segments[key]
         from . import lib as L
-        for g, n, opt_calls, ev, _sub in built:
+        # Two optimizer-side streams: the collectives (and the fp32 -> bf16 casts that feed them) queue on the COMM stream
+        # back to back, the Adam / scatter kernels on the OPT stream, each waiting only for the collective it consumes.
+        # A slice's all-reduce therefore overlaps the previous slice's Adam instead of waiting behind it.
+        comm = self.comm_stream if self.world > 1 else opt
+        for g, n, opt_calls, ev, _sub, evs in built:
             if g is not None:
                 g.replay()
                 eng.launches += n
             if opt_calls:
                 ev.record(main)
                 opt.wait_event(ev)
-                for name, fn, args, _lane in opt_calls:
-                    rc = fn(opt) if name.startswith("py:") else fn(*args, opt.cuda_stream)
+                if comm is not opt:
+                    comm.wait_event(ev)
+                pending = None                       # event of the last collective the OPT stream has not waited for yet
+                for (name, fn, args, _lane), e in zip(opt_calls, evs):
+                    on_comm = comm is not opt and (name.startswith("py:") or name.startswith("vct_cast"))
+                    st = comm if on_comm else opt
+                    if not on_comm and pending is not None:
+                        opt.wait_event(pending)
+                        pending = None
+                    rc = fn(st) if name.startswith("py:") else fn(*args, st.cuda_stream)
                     if rc:
                         L.check(rc, name)
                     if not name.startswith("py:"):
                         eng.launches += 1
+                    if on_comm:
+                        e.record(comm)
+                        pending = e
         done.record(opt)
         main.wait_event(done)
+        if comm is not opt:
+            done_comm.record(comm)
+            main.wait_event(done_comm)
 
     def step(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: torch.Tensor) -> torch.Tensor:
         """feats fp32 [B,T,Din], vid_pad bool [B,T] | None, ids int64 [B,S+1] (host -- ideally pinned -- or
@@ -270,14 +322,20 @@ class CaptionTrainer:
             # optimizer slices are captured together -- with the per-slice NCCL all-reduce + Adam issued eagerly on the
             # optimizer lane after each segment.  ~25 host operations per step instead of ~110 ctypes launches, so the
             # N-GPU step is no longer bound by the host.
-            self._graphed((B, T, S, "forward"), lambda: self._forward(ws), ws=ws)
+            eng.tick()
+            self._early_embedding(ws)
+            self._graphed((B, T, S, "forward-only"), lambda: self._forward(ws, tick=False), ws=ws)
             self._backward_segments(ws, (B, T, S))
         elif self.fuse_adam:
             # data parallel with overlap: forward is a CUDA graph; backward runs eagerly (NCCL collectives outside graph
             # capture) -- each arena slice is all-reduced and then updated on the optimizer lane while the rest of
             # backward continues on the main lane
-            self._graphed((B, T, S, "forward"), lambda: self._forward(ws), ws=ws)
+            eng.tick()
+            self._early_embedding(ws)
+            self._graphed((B, T, S, "forward-only"), lambda: self._forward(ws, tick=False), ws=ws)
             eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=True, allreduce=(self.group, self.world)))
+            if self.world > 1:
+                torch.cuda.current_stream(eng.device).wait_stream(self.comm_stream)
         else:
             # (dense exchange of every gradient incl. the embedding table: the reference's DDP scheme, kept for comparison)
             self._graphed((B, T, S, "compute"), lambda: self._compute(ws), ws=ws)
