@@ -661,7 +661,7 @@ def main():
                 "dtype": "bf16" if eng.precision == "bf16" else ("f32" if eng.precision == "fp32" else eng.precision),
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "name": args.config, "global_batch": B * world, "per_gpu_batch": B,
-                           "parallelism": f"dp{world}", "gemm": "tcgen05" if eng.gemm_impl == 1 else "simt",
+                           "parallelism": f"dp{world}", "gemm": {0: "simt", 1: "tcgen05", 2: "tcgen05 split-bf16 x3", 3: "tcgen05 split-bf16 x6"}[eng.gemm_impl],
                            "cuda_graph": not args.no_graph,
                            "l2": "no explicit flush: one step streams ~2.5 GB of weights/moments/activations, 20x the 126 MB L2"},
                 "e2e": {"value": B * world * args.steps / float(e2e_s.item()), "unit": "captions/s",

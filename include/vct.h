@@ -66,8 +66,11 @@ int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, vct_stream_t
  * (generator), torch/nn/functional.py _in_projection_packed + out_proj inside
  * multi_head_attention_forward, torch/nn/modules/transformer.py:980-982,1197-1199 (FFN), and the
  * autograd dgrad / wgrad of each.
- * impl: VCT_GEMM_SIMT (fp32 FFMA tiles; any dtype mix; the exact path) or VCT_GEMM_TCGEN05
- * (bf16 operands, TMA + tcgen05.mma, fp32 accumulation in TMEM). */
+ * impl: VCT_GEMM_SIMT (fp32 FFMA tiles; any dtype mix; the exact path), VCT_GEMM_TCGEN05
+ * (bf16 operands, TMA + tcgen05.mma, fp32 accumulation in TMEM), or VCT_GEMM_TCGEN05_X3 / _X6: the
+ * reference-precision tensor-core path -- fp32 operands are split into 2 / 3 bf16 pieces inside the call
+ * (into split_ws) and the 3 / 6 leading cross terms are accumulated in fp32 by ONE tcgen05 launch with
+ * K' = terms * K (csrc/gemm_split.cu); X6 reproduces fp32 products to ~2^-23, X3 to ~2^-16. */
 #define VCT_ACT_NONE 0
 #define VCT_ACT_GELU_FWD 1
 #define VCT_ACT_GELU_BWD 2
@@ -75,6 +78,8 @@ int vct_step_tick(unsigned long long* rng_state, float* adam_hyper, vct_stream_t
 #define VCT_ACT_MUL_AUX 4    /* C = acc * aux[m,n] (+ addend): FFN backward with the saved factor f, no erf / RNG */
 #define VCT_GEMM_SIMT 0
 #define VCT_GEMM_TCGEN05 1
+#define VCT_GEMM_TCGEN05_X3 2
+#define VCT_GEMM_TCGEN05_X6 3
 
 typedef struct {
     int M, N, K;
@@ -92,9 +97,18 @@ typedef struct {
     /* optional split-K workspace (fp32, caller-allocated): lets the tcgen05 path split a long K (e.g. the
      * generator dgrad, K = vocab) over several CTAs and reduce deterministically in a second kernel */
     void* splitk_ws; long long splitk_ws_floats;
+    /* VCT_GEMM_TCGEN05_X3 / _X6 only: caller-allocated, 256-byte aligned scratch of at least
+     * vct_gemm_split_workspace_bytes(M, N, K, a_trans, b_trans, terms) bytes for the bf16 pieces of A and B */
+    void* split_ws; long long split_ws_bytes;
 } vct_gemm_args;
 
 int vct_gemm(const vct_gemm_args* args, vct_stream_t stream);
+long long vct_gemm_split_workspace_bytes(int M, int N, int K, int a_trans, int b_trans, int terms);
+/* The operand decomposition on its own: src fp32 [rows, cols] -> dst bf16 with the `terms` (3 or 6) pieces of side
+ * 0 (A: h h m | h h m m h l) or 1 (B: h m h | h m h m l h) laid along the contraction axis (1: columns, dst [rows,
+ * terms * Kp]; 0: rows, dst [terms * Kp, ld_dst]; Kp = K rounded up to 8, padding zero-filled). */
+int vct_split_bf16(const float* src, long long ld_src, int rows, int cols, int axis, int side, int terms, void* dst,
+                   long long ld_dst, vct_stream_t stream);
 
 /* Tuning hook for the tcgen05 path (tools/gemm_sweep.py): force the tile width (block_n = 64 / 128 / 256;
  * 0 restores the built-in cost model), the split-K factor (0/1 = none) and the kernel flavour
@@ -173,6 +187,7 @@ typedef struct {
     float drop_p; const unsigned long long* rng_state; unsigned int site;
     float* probs;
     int gemm_impl;
+    void* split_ws; long long split_ws_bytes;   /* for gemm_impl = VCT_GEMM_TCGEN05_X3 / _X6 (see vct_gemm_args) */
 } vct_mha_args;
 
 int vct_attn_enc_self_fwd(const vct_mha_args* args, vct_stream_t stream);

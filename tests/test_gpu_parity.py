@@ -18,7 +18,8 @@ pytestmark = pytest.mark.gpu
 from helpers import load_tiny, load_anchors, synth_inputs  # noqa: E402
 
 DEV = torch.device("cuda")
-MODES = [("fp32", "simt"), ("bf16", "simt"), ("bf16", "tcgen05")]
+MODES = [("fp32", "simt"), ("bf16", "simt"), ("bf16", "tcgen05"), ("bf16x6", None)]
+FP32_CLASS = ("fp32", "bf16x6")     # bf16x6: fp32 storage, GEMMs as 6 bf16 cross terms on tcgen05 (csrc/gemm_split.cu)
 
 
 def build_tiny(name, precision, gemm, dropout=0.0):
@@ -51,7 +52,7 @@ def test_tiny_forward_backward_matches_reference_golden(name, precision, gemm):
     mem_c, logits_c = memory.detach().float().cpu().clone(), logits.detach().float().cpu().clone()
     loss.backward()
     torch.cuda.synchronize()
-    f32 = precision == "fp32"
+    f32 = precision in FP32_CLASS
     atol = 2e-4 if f32 else 6e-2
     torch.testing.assert_close(mem_c, torch.from_numpy(outs["memory"]), rtol=0, atol=atol)
     torch.testing.assert_close(logits_c, torch.from_numpy(outs["logits"]), rtol=0, atol=atol)
@@ -155,7 +156,7 @@ def test_fullsize_anchors(full_model, tag, precision, gemm):
         assert abs(float(sd[k].double().sum()) - s) <= 1e-6 * max(1.0, a), k
     assert sum(p.numel() for p in model.parameters()) == anchors["n_params_total"]
     assert sum(p.numel() for p in model.parameters() if p.requires_grad) == anchors["n_params_trainable"]
-    f32 = precision == "fp32"
+    f32 = precision in FP32_CLASS
     model.train()
     for case, padded in (("padded", True), ("unpadded", False)):
         a = anchors["cases"][case]

@@ -28,3 +28,29 @@ for r in rows[2:]:
                 pass
     tot = sum(v for v, _ in stalls) or 1
     print("stall samples: " + ", ".join(f"{n} {100*v/tot:.0f}%" for v, n in sorted(stalls, reverse=True)[:6]))
+
+# optional: --traffic-json FILE  -> {kernel base name: mean dram bytes (read + write) per captured launch}
+if "--traffic-json" in sys.argv:
+    import json
+    import os
+    import re
+    out = sys.argv[sys.argv.index("--traffic-json") + 1]
+    acc = {}
+    mult = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[idx["Kernel Name"]])
+        name = re.sub(r"<.*", "", re.sub(r"<unnamed>::|\(anonymous namespace\)::|void ", "", name))
+        try:
+            rd = float(r[idx["dram__bytes_read.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_read.sum"]], 1.0)
+            wr = float(r[idx["dram__bytes_write.sum"]].replace(",", "")) * mult.get(units[idx["dram__bytes_write.sum"]], 1.0)
+        except (KeyError, ValueError):
+            continue
+        acc.setdefault(name, []).append(rd + wr)
+    cur = {}
+    if os.path.isfile(out):
+        with open(out) as f:
+            cur = json.load(f)
+    for k, v in acc.items():
+        cur[k] = sum(v) / len(v)
+    with open(out, "w") as f:
+        json.dump(cur, f, indent=1, sort_keys=True)

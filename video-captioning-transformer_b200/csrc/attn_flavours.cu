@@ -16,7 +16,7 @@ namespace {
 size_t esize(int dtype) { return dtype == VCT_BF16 ? 2 : 4; }
 
 int project(const void* x, int rows, int d, int n_out, const void* w, const float* b, void* out, int dtype, int impl,
-            vct_stream_t stream) {
+            vct_stream_t stream, void* split_ws = nullptr, long long split_ws_bytes = 0) {
     vct_gemm_args g;
     memset(&g, 0, sizeof(g));
     g.M = rows; g.N = n_out; g.K = d;
@@ -26,6 +26,7 @@ int project(const void* x, int rows, int d, int n_out, const void* w, const floa
     g.bias = b;
     g.act = VCT_ACT_NONE;
     g.impl = impl;
+    g.split_ws = split_ws; g.split_ws_bytes = split_ws_bytes;
     return vct_gemm(&g, stream);
 }
 
@@ -39,7 +40,7 @@ int self_attention(const vct_mha_args* a, int causal, vct_stream_t stream, const
         const int r = vct::attn_fused_self(a, causal, (cudaStream_t)stream);
         if (r <= 0) return r;
     }
-    if (int e = project(a->x, rows, d, 3 * d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream)) return e;
+    if (int e = project(a->x, rows, d, 3 * d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream, a->split_ws, a->split_ws_bytes)) return e;
     vct_attn_args t;
     memset(&t, 0, sizeof(t));
     const char* base = (const char*)a->qkv;
@@ -77,11 +78,11 @@ extern "C" int vct_attn_dec_cross_fwd(const vct_mha_args* a, vct_stream_t stream
         if (r <= 0) return r;
     }
     // q = x W_in[0:d]^T + b_in[0:d]
-    if (int e = project(a->x, a->B * a->L, d, d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream)) return e;
+    if (int e = project(a->x, a->B * a->L, d, d, a->w_in, a->b_in, a->qkv, a->dtype, a->gemm_impl, stream, a->split_ws, a->split_ws_bytes)) return e;
     if (!a->kv_ready) {
         const char* w_kv = (const char*)a->w_in + (size_t)d * d * es;
         if (int e = project(a->mem, a->B * a->Lk, d, 2 * d, w_kv, a->b_in ? a->b_in + d : nullptr, a->kv, a->dtype,
-                            a->gemm_impl, stream))
+                            a->gemm_impl, stream, a->split_ws, a->split_ws_bytes))
             return e;
     }
     vct_attn_args t;

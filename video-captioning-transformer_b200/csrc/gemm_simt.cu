@@ -142,6 +142,7 @@ int gemm_simt(const vct_gemm_args* a, cudaStream_t st) {
     return launch_simt<float>(a, st);
 }
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st);   // gemm_tc.cu
+int gemm_split(const vct_gemm_args* a, int terms, cudaStream_t st);   // gemm_split.cu
 void gemm_tune(int bn, int splits, int low);                  // gemm_tc.cu
 void gemm_trace(long long* dev_buf);                          // gemm_tc.cu
 }  // namespace vct
@@ -176,5 +177,7 @@ extern "C" int vct_gemm(const vct_gemm_args* a, vct_stream_t stream) {
     VCT_REQUIRE(a->row_table == nullptr || a->row_period > 0, "vct_gemm: row_table needs row_period > 0");
     VCT_REQUIRE(a->addend == nullptr || a->ld_addend >= a->N, "vct_gemm: ld_addend too small");
     if (a->impl == VCT_GEMM_TCGEN05) return vct::gemm_tcgen05(a, (cudaStream_t)stream);
+    if (a->impl == VCT_GEMM_TCGEN05_X3) return vct::gemm_split(a, 3, (cudaStream_t)stream);
+    if (a->impl == VCT_GEMM_TCGEN05_X6) return vct::gemm_split(a, 6, (cudaStream_t)stream);
     return vct::gemm_simt(a, (cudaStream_t)stream);
 }

@@ -136,17 +136,23 @@ class CaptionEngine:
             L.check(self.lib.vct_device_info(C.byref(sm), C.byref(maj), C.byref(mnr)), "vct_device_info")
         self.device = device
         self.dims = SimpleNamespace(**dims)   # Din d H_enc H_dec F_enc F_dec L_enc L_dec V pad_id alpha dropout
-        if precision not in ("bf16", "fp32"):
-            raise ValueError("precision must be 'bf16' or 'fp32'")
+        if precision not in ("bf16", "fp32", "bf16x3", "bf16x6"):
+            raise ValueError("precision must be 'bf16', 'fp32', 'bf16x3' or 'bf16x6'")
         self.precision = precision
         self.cdt = BF16 if precision == "bf16" else F32
-        # VCT_GEMM only selects between the two bf16 implementations; fp32 storage always runs the SIMT kernel
+        # bf16x3 / bf16x6: fp32 storage like 'fp32', but every dense contraction runs on tcgen05 with the fp32 operands split
+        # into 2 / 3 bf16 pieces and 3 / 6 cross terms accumulated in fp32 (csrc/gemm_split.cu) -- the reference-precision
+        # tensor-core mode (token-id argmax exactness without the SIMT FFMA GEMM)
+        self.split_terms = {"bf16x3": 3, "bf16x6": 6}.get(precision, 0)
+        # VCT_GEMM only selects between the two bf16 implementations; fp32 storage runs the SIMT kernel or the split path
         impl = gemm_impl or (os.environ.get("VCT_GEMM", "tcgen05") if precision == "bf16" else "simt")
         if impl not in ("simt", "tcgen05"):
             raise ValueError("gemm_impl must be 'simt' or 'tcgen05'")
-        if impl == "tcgen05" and precision != "bf16":
-            raise ValueError("the tcgen05 GEMM takes bf16 operands")
+        if impl == "tcgen05" and precision == "fp32":
+            raise ValueError("the tcgen05 GEMM takes bf16 operands (precision 'bf16x3' / 'bf16x6' runs fp32 data on it)")
         self.gemm_impl = L.GEMM_TCGEN05 if impl == "tcgen05" else L.GEMM_SIMT
+        if self.split_terms:
+            self.gemm_impl = L.GEMM_TCGEN05_X3 if self.split_terms == 3 else L.GEMM_TCGEN05_X6
         # dtype of the data-parallel gradient exchange (dense buckets): bf16 halves the NVLink bytes; fp32 storage keeps fp32
         comm = os.environ.get("VCT_GRAD_COMM", "bf16" if precision == "bf16" else "fp32")
         if comm not in ("bf16", "fp32"):
@@ -412,8 +418,33 @@ class CaptionEngine:
         if ws is not None and getattr(ws, "splitk", None) is not None:
             sk = ws.splitk[1 if plan.lane else 0]           # one workspace per lane: the lanes run concurrently
             g.splitk_ws, g.splitk_ws_floats = sk.data_ptr(), sk.numel()
+        if self.split_terms:
+            g.split_ws, g.split_ws_bytes = self._split_ws(ws, 1 if plan.lane else 0)
         plan.keep.append(g)
         plan.add("vct_gemm:" + tag, self.lib.vct_gemm, C.byref(g))
+
+    def _split_ws(self, ws, lane: int):
+        """(pointer, bytes) of the lane's operand-split scratch (precision bf16x3 / bf16x6)."""
+        t = ws.split_ws[lane]
+        return t.data_ptr(), t.numel()
+
+    def _alloc_split_ws(self, ws, rows_max: int, with_grad: bool):
+        """Scratch for the bf16 pieces of both operands of the largest GEMM a plan over ``ws`` issues, one per lane."""
+        if not self.split_terms:
+            ws.split_ws = None
+            return
+        D, t = self.dims, self.split_terms
+        Fm = max(D.F_enc, D.F_dec)
+        shapes = [(rows_max, D.V, D.d, 0, 0), (rows_max, 3 * D.d, D.d, 0, 0), (rows_max, Fm, D.d, 0, 0),
+                  (rows_max, D.d, Fm, 0, 0), (rows_max, D.d, D.Din, 0, 0)]
+        if with_grad:
+            shapes += [(rows_max, D.d, D.V, 0, 1), (D.V, D.d, rows_max, 1, 1), (rows_max, Fm, D.d, 0, 1), (rows_max, D.d, Fm, 0, 1),
+                       (Fm, D.d, rows_max, 1, 1), (D.d, Fm, rows_max, 1, 1), (3 * D.d, D.d, rows_max, 1, 1),
+                       (rows_max, D.d, 3 * D.d, 0, 1), (D.d, D.Din, rows_max, 1, 1)]
+        need = max(int(self.lib.vct_gemm_split_workspace_bytes(M, N, K, at, bt, t)) for M, N, K, at, bt in shapes)
+        ws.split_ws = [torch.empty(need + 256, dtype=torch.uint8, device=self.device) for _ in range(2 if with_grad else 1)]
+        if not with_grad:
+            ws.split_ws.append(ws.split_ws[0])
 
     def _colsum(self, plan: Plan, tag: str, X, ld, M, N, out, ws):
         # column sums run on the side lane: they get their own partials buffer (LN backward uses ws.partials)
@@ -559,7 +590,9 @@ class CaptionEngine:
             ws.scratch = {}
         # split-K workspaces (fp32 partial tiles) for long-K GEMMs, one per lane
         ws.splitk = [torch.empty(8 * max(Re, Rd) * max(d, 8), dtype=f32, device=self.device) for _ in range(2)] \
-            if self.gemm_impl == L.GEMM_TCGEN05 else None
+            if self.gemm_impl != L.GEMM_SIMT else None
+        # (the eval encoder / cross-K/V GEMMs of a forward-only workspace also run on the side lane: two buffers always)
+        self._alloc_split_ws(ws, max(Re, Rd), True)
         ws.plans = {}
         ws.graphs = {}            # CUDA graphs captured over this workspace's pointers (vct.trainer): same lifetime
         ws.enc_version = 0        # bumped by every encoder / decoder forward over this workspace: backward checks that
@@ -601,6 +634,8 @@ class CaptionEngine:
             m.qkv, m.o, m.key_pad = e.qkv.data_ptr(), e.ao.data_ptr(), ws.vid_pad.data_ptr()
             m.drop_p, m.rng_state, m.site = p_drop, self.rng_state.data_ptr(), _enc_site(l, 0)
             m.gemm_impl = self.gemm_impl
+            if self.split_terms:
+                m.split_ws, m.split_ws_bytes = self._split_ws(ws, 1 if plan.lane else 0)
             plan.keep.append(m)
             plan.add(f"vct_attn_enc_self_fwd:{l}", lib.vct_attn_enc_self_fwd, C.byref(m))
             self._gemm(plan, f"enc{l}.out_proj", Re, d, d, e.ao.data_ptr(), d, 0, self._w(pre + "self_attn.out_proj.weight"),
@@ -655,6 +690,8 @@ class CaptionEngine:
             m.qkv, m.o, m.key_pad = e.qkv.data_ptr(), e.ao.data_ptr(), ws.tok_pad.data_ptr()
             m.drop_p, m.rng_state, m.site = p_drop, self.rng_state.data_ptr(), _dec_site(l, 0)
             m.gemm_impl = self.gemm_impl
+            if self.split_terms:
+                m.split_ws, m.split_ws_bytes = self._split_ws(ws, 1 if plan.lane else 0)
             plan.keep.append(m)
             plan.add(f"vct_attn_dec_self_fwd:{l}", lib.vct_attn_dec_self_fwd, C.byref(m))
             self._gemm(plan, f"dec{l}.self.out_proj", Rd, d, d, e.ao.data_ptr(), d, 0, self._w(pre + "self_attn.out_proj.weight"),
@@ -671,6 +708,8 @@ class CaptionEngine:
                 plan.add_join()                  # encoder memory + K/V projections (lane 1) are needed from here on
             c.drop_p, c.rng_state, c.site = p_drop, self.rng_state.data_ptr(), _dec_site(l, 2)
             c.gemm_impl = self.gemm_impl
+            if self.split_terms:
+                c.split_ws, c.split_ws_bytes = self._split_ws(ws, 1 if plan.lane else 0)
             plan.keep.append(c)
             plan.add(f"vct_attn_dec_cross_fwd:{l}", lib.vct_attn_dec_cross_fwd, C.byref(c))
             self._gemm(plan, f"dec{l}.cross.out_proj", Rd, d, d, e.ao2.data_ptr(), d, 0,
@@ -1085,6 +1124,7 @@ class CaptionEngine:
             ws.layers.append(e)
         ws.hfin, ws.hfin_c = pair(B, d)
         ws.logits = torch.empty((B, ws.Vp), dtype=f32, device=dev)
+        self._alloc_split_ws(ws, B * M, False)
         ws.plans = {}
         self._ws[key] = ws
         return ws
@@ -1099,6 +1139,7 @@ class CaptionEngine:
             D = self.dims
             d = D.d
             p = Plan()
+            p.ws = dws
             for l, e in enumerate(dws.layers):
                 pre = f"cap_decoder.decoder.layers.{l}.multihead_attn."
                 self._gemm(p, f"dec{l}.cross.kv", dws.B * dws.M, 2 * d, d, enc_ws.mem_c.data_ptr(), d, 0,
@@ -1116,6 +1157,7 @@ class CaptionEngine:
         d, B, M, Lmax = D.d, dws.B, dws.M, dws.max_len
         cd, es = self.cdt, _ESIZE[self.cdt]
         p = Plan()
+        p.ws = dws
         p.add("vct_embed_fwd", lib.vct_embed_fwd, dws.ys.data_ptr() + 8 * t, Lmax, self._p("cap_decoder.tgt_to_emb.weight"),
               self.pos.data_ptr(), dws.x.data_ptr(), dws.x_c.data_ptr() if cd == BF16 else None, cd, B, 1, d, D.V, t,
               0.0, self.rng_state.data_ptr(), SITE_EMBED)

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(os.path.dirname(HERE), "libvct_b200.so")
 
 F32, BF16 = 0, 1
 ACT_NONE, ACT_GELU_FWD, ACT_GELU_BWD, ACT_GELU_FWD_F, ACT_MUL_AUX = 0, 1, 2, 3, 4
-GEMM_SIMT, GEMM_TCGEN05 = 0, 1
+GEMM_SIMT, GEMM_TCGEN05, GEMM_TCGEN05_X3, GEMM_TCGEN05_X6 = 0, 1, 2, 3
 
 vp, ll, i32, u32, f32 = C.c_void_p, C.c_longlong, C.c_int, C.c_uint, C.c_float
 
@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("drop_p", f32), ("rng_state", vp), ("site", u32),
         ("impl", i32),
         ("splitk_ws", vp), ("splitk_ws_floats", ll),
+        ("split_ws", vp), ("split_ws_bytes", ll),
     ]
 
 
@@ -66,6 +67,7 @@ class MhaArgs(C.Structure):
         ("drop_p", f32), ("rng_state", vp), ("site", u32),
         ("probs", vp),
         ("gemm_impl", i32),
+        ("split_ws", vp), ("split_ws_bytes", ll),
     ]
 
 
@@ -76,6 +78,8 @@ SIGNATURES = {
     "vct_device_info": (i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "vct_step_tick": (i32, [vp, vp, vp]),
     "vct_gemm": (i32, [C.POINTER(GemmArgs), vp]),
+    "vct_gemm_split_workspace_bytes": (ll, [i32, i32, i32, i32, i32, i32]),
+    "vct_split_bf16": (i32, [vp, ll, i32, i32, i32, i32, i32, vp, ll, vp]),
     "vct_gemm_tune": (i32, [i32, i32, i32]),
     "vct_gemm_trace": (i32, [vp]),
     "vct_prep_frames": (i32, [vp, vp, i32, i32, i32, i32, vp]),
