@@ -71,8 +71,17 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0, "tflops": 1400.0, "tflops_burst": 1590.0, "src": "fallback"}
 
 
+# kernel family of the bench line -> kernel name in the ncu capture (profiles/r02_traffic.json, written by
+# tools/ncu_summary.py --traffic-json from `ncu --set full` of `bench.py --steps 1 --warmup 3 --no-graph`)
+FAMILY_KERNEL = {"vct_gemm:layers": "gemm_tc_kernel", "vct_gemm:generator": "gemm_tc_persistent_kernel", "vct_adam": "adam_kernel",
+                 "vct_ln_residual_fwd": "ln_fwd_kernel", "vct_ln_residual_bwd": "ln_bwd_kernel", "vct_ln_bwd_reduce": "ln_bwd_reduce_kernel",
+                 "vct_sce": "sce_kernel", "vct_colsum": "colsum_kernel", "vct_attn_bwd": "attn_bwd_tc_kernel",
+                 "vct_attn_enc_self_fwd": "attn_fused_kernel", "vct_attn_dec_self_fwd": "attn_fused_kernel",
+                 "vct_attn_dec_cross_fwd": "attn_fused_kernel"}
+
+
 def ncu_traffic():
-    """{kernel-name regex: dram bytes per launch} from the committed `ncu --set full` capture of this command."""
+    """{kernel name: mean dram bytes (read + write) per launch} from the committed `ncu --set full` capture (cfg2 workload)."""
     p = os.path.join(ROOT, "profiles", "r02_traffic.json")
     if os.path.isfile(p):
         with open(p) as f:
@@ -450,15 +459,15 @@ def kernel_rooflines(eng, plans, peaks, adam_ms, extra_adam=True):
         bound = "tensor" if t_tc > t_hbm else "hbm"
         ach = (e["flops"] / t / 1e12) if bound == "tensor" else (e["bytes"] / t / 1e9)
         peak = peaks["tflops"] if bound == "tensor" else peaks["hbm_gbs"]
-        tr = None
-        for pat, v in traffic.items():
-            if re.search(pat, f):
-                tr = v
+        # dram bytes per LAUNCH (mean over the captured launches of the family's kernel), next to the algorithmic bytes per
+        # launch; only meaningful for the workload the capture was taken on (cfg2)
+        tr = traffic.get(FAMILY_KERNEL.get(f, ""))
         out.append({"kernel": f, "launches_per_step": e["launches"], "share_of_step": e["eager_ms"] / total,
                     "ms_eager": round(e["eager_ms"], 4), "ms_alone": round(e["alone_ms"], 4), "bound": bound,
                     "achieved": ach, "peak": peak, "unit": "TFLOP/s" if bound == "tensor" else "GB/s",
                     "frac": ach / peak if t > 0 and (e["bytes"] or e["flops"]) else None,
-                    "bytes": e["bytes"], "flops": e["flops"], "traffic": tr, "peak_source": peaks["src"]})
+                    "bytes": e["bytes"], "flops": e["flops"], "traffic": tr,
+                    "bytes_per_launch": e["bytes"] / max(1, e["launches"]), "peak_source": peaks["src"]})
     out.sort(key=lambda r: -r["share_of_step"])
     # attention flavours, one line each (BASELINE metric "attn kernel HBM GB/s vs peak")
     attn = {}
@@ -638,6 +647,9 @@ def main():
                     acc[1] += ev[1].elapsed_time(ev[2]) / 3
             phase_ms = {"forward": round(acc[0], 4), "backward_incl_side_lanes": round(acc[1], 4),
                         "n_forward_calls": len(fwd), "n_backward_calls": len(bwd)}
+        if args.config != "cfg2" or B != 64 or eng.precision != "bf16":
+            for r in rooflines:                             # the ncu capture is of the cfg2 workload
+                r["traffic"] = None
         top = rooflines[0]                                  # the family with the largest share of the step
         roofline = {k: top[k] for k in ("kernel", "bound", "achieved", "peak", "unit", "frac", "traffic", "share_of_step",
                                         "launches_per_step", "ms_alone", "peak_source")}

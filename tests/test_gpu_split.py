@@ -1,9 +1,9 @@
 """The reference-precision tensor-core GEMM (csrc/gemm_split.cu: fp32 operands split into bf16 pieces, 3 / 6 cross terms
 accumulated in fp32 by ONE tcgen05 launch) against float64 matmul on the same fp32 operands.
 
-Tolerances: the error of a product rebuilt from 6 terms is ~2^-23 |a||b| (the dropped terms m*l, l*m, l*l), i.e. fp32
-class -- held to the SIMT fp32 kernel's own tolerance (rtol 1e-4 on sqrt(K)-scaled values is loose; measured max errors
-are printed); 3 terms drop m*m ~ 2^-16 |a||b|."""
+Tolerances (max |err| / sum_k |a||b|, printed per case): a product rebuilt from 6 terms is off by ~2^-25 |a||b| (the dropped
+terms m*l, l*m, l*l); what remains is the fp32 accumulation of K' = 6K products in TMEM, a few 1e-7 .. 1e-6 like any fp32
+GEMM -- bound 5e-6.  3 terms drop m*m ~ 2^-17 |a||b| -- bound 4e-5."""
 import ctypes as C
 import math
 
@@ -62,7 +62,7 @@ def test_split_gemm_matches_float64(lib, terms, a_trans, b_trans, M, N, K):
     scale = (A.double().abs() @ B.double().abs().t())            # sum_k |a||b|: what a relative product error scales with
     rel = float(((got - want).abs() / scale).max())
     print(f"split GEMM x{terms} {M}x{N}x{K} trans=({a_trans},{b_trans}): max |err| / sum|a||b| = {rel:.3e}")
-    assert rel <= (3e-7 if terms == 6 else 4e-5), rel
+    assert rel <= (5e-6 if terms == 6 else 4e-5), rel
 
 
 @pytest.mark.parametrize("terms", [3, 6])

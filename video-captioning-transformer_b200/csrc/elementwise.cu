@@ -901,32 +901,57 @@ extern "C" int vct_zero_rows(float* x, const unsigned char* mask, int R, int d, 
 // ------------------------------------------------------------------------------------------------
 // greedy argmax + append
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
+// One CTA (512 threads) per row; the row is read as float4 (ld % 4 == 0, 16-byte aligned base) with four loads in flight
+// per thread, ties resolved towards the lowest index at every level (torch.max semantics, model/MMT4Caption.py:165).
+__device__ __forceinline__ void argmax_take(float v, int i, float& best, int& bi) {
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+}
+
+__global__ void __launch_bounds__(512)
 argmax_append_kernel(const float* __restrict__ logits, long long ld, int V, long long* __restrict__ ys, long long ys_ld,
-                     int t, int end_id, int* __restrict__ ended, int* __restrict__ n_ended) {
+                     int t, int end_id, int* __restrict__ ended, int* __restrict__ n_ended, int vec) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float sv[8];
-    __shared__ int si[8];
+    __shared__ float sv[16];
+    __shared__ int si[16];
     const int b = blockIdx.x;
     const float* row = logits + (long long)b * ld;
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int i = threadIdx.x; i < V; i += blockDim.x) {
-        float v = row[i];
-        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+    if (vec) {
+        const float4* row4 = reinterpret_cast<const float4*>(row);
+        const int n4 = V >> 2;
+        int i = threadIdx.x;
+        for (; i + 3 * (int)blockDim.x < n4; i += 4 * blockDim.x) {
+            float4 a[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = __ldcs(row4 + i + u * blockDim.x);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int c = 4 * (i + u * blockDim.x);
+                argmax_take(a[u].x, c, best, bi); argmax_take(a[u].y, c + 1, best, bi);
+                argmax_take(a[u].z, c + 2, best, bi); argmax_take(a[u].w, c + 3, best, bi);
+            }
+        }
+        for (; i < n4; i += blockDim.x) {
+            const float4 a = __ldcs(row4 + i);
+            argmax_take(a.x, 4 * i, best, bi); argmax_take(a.y, 4 * i + 1, best, bi);
+            argmax_take(a.z, 4 * i + 2, best, bi); argmax_take(a.w, 4 * i + 3, best, bi);
+        }
+        for (int c = (n4 << 2) + threadIdx.x; c < V; c += blockDim.x) argmax_take(row[c], c, best, bi);
+    } else {
+        for (int c = threadIdx.x; c < V; c += blockDim.x) argmax_take(row[c], c, best, bi);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, best, o);
-        int oi = __shfl_xor_sync(0xffffffffu, bi, o);
-        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+        const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        argmax_take(ov, oi, best, bi);
     }
     if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int w = 1; w < 8; ++w)
-            if (sv[w] > best || (sv[w] == best && si[w] < bi)) { best = sv[w]; bi = si[w]; }
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w) argmax_take(sv[w], si[w], best, bi);
         if (bi == 0x7fffffff) bi = 0;
         ys[(long long)b * ys_ld + t] = bi;
         if (bi == end_id && ended && !ended[b]) {
@@ -939,7 +964,8 @@ argmax_append_kernel(const float* __restrict__ logits, long long ld, int V, long
 extern "C" int vct_argmax_append(const float* logits, long long ld_logits, int B, int V, long long* ys, long long ys_ld,
                                  int t, int end_id, int* ended, int* n_ended, vct_stream_t stream) {
     VCT_REQUIRE(B > 0 && V > 0 && logits && ys, "vct_argmax_append: bad arguments");
-    vct::launch(argmax_append_kernel, dim3(B), dim3(256), 0, (cudaStream_t)stream, logits, ld_logits, V, ys, ys_ld, t, end_id, ended, n_ended);
+    const int vec = (ld_logits % 4 == 0 && (reinterpret_cast<uintptr_t>(logits) & 15) == 0) ? 1 : 0;
+    vct::launch(argmax_append_kernel, dim3(B), dim3(512), 0, (cudaStream_t)stream, logits, ld_logits, V, ys, ys_ld, t, end_id, ended, n_ended, vec);
     return check_launch("vct_argmax_append");
 }
 
