@@ -1,0 +1,67 @@
+"""GPU end of rows N2-N4: the packed device-resident loader feeding the native trainer, and the batched / sharded
+evaluation against one-video-at-a-time greedy decoding (the reference's eval loop, train.py:171-185)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from test_data_eval import _dataset  # noqa: E402
+
+DEV = torch.device("cuda")
+
+
+def _model(tokenizer_dir, precision):
+    from model.MMT4Caption import MMT4Caption
+    from vct.synthetic import shipped_model_config
+    torch.manual_seed(666)
+    m = MMT4Caption(shipped_model_config(tokenizer_dir, dropout=0.0), device=DEV).to(DEV)
+    m.vct_precision = precision
+    m.mode("caption")
+    return m
+
+
+def test_packed_loader_feeds_trainer_and_matches_string_captions(tmp_path, tokenizer_dir):
+    """One epoch over the packed loader (device-resident features, pre-tokenised ids): every batch's loss equals the loss
+    of the same batch given as raw caption strings through the reference-style call model(feats, masks, captions)."""
+    from vct.data import build_packed_dataloader
+    model = _model(tokenizer_dir, "fp32")
+    model.eval()
+    cfg = _dataset(tmp_path, ragged=True)
+    ds, loader, _ = build_packed_dataloader(cfg, multi_gpu=False, device=DEV, cap_preprocessor=model.cap_preprocessor)
+    loader.shuffle = False
+    assert ds.feats[0].is_cuda and ds.ids_table.is_cuda
+    n = 0
+    with torch.no_grad():
+        for i, (feats, masks, ids, vids) in zip(range(0, len(ds), 4), loader):
+            assert feats[0].is_cuda and ids.is_cuda and ids.dtype == torch.int64
+            caps = [ds.cap_vid_list[j][0] for j in range(i, min(len(ds), i + 4))]
+            l_ids = float(model(feats, masks, ids))
+            l_str = float(model(feats, masks, caps))
+            assert abs(l_ids - l_str) <= 1e-6 * abs(l_str), (l_ids, l_str)
+            n += 1
+    assert n == len(loader)
+    from vct.trainer import CaptionTrainer
+    model.train()
+    tr = CaptionTrainer(model, lr=1e-4, use_graph=False)
+    losses = []
+    for feats, masks, ids, vids in loader:
+        losses.append(float(tr.step(feats[0], masks[0], ids)))
+    assert all(torch.isfinite(torch.tensor(losses))) and len(losses) == len(loader)
+
+
+def test_batched_sharded_eval_equals_per_video_decode(tmp_path, tokenizer_dir):
+    from vct.data import PackedCaptionDataset
+    from vct.evaluate import sharded_greedy_eval
+    model = _model(tokenizer_dir, "fp32")
+    cfg = _dataset(tmp_path, ragged=True)
+    ds = PackedCaptionDataset(cfg["feat_dir"], cfg["annotation_path"], split_type="train", mode="by_video", device=DEV)
+    batched = sharded_greedy_eval(model, ds, max_len=8, batch_size=4)
+    model.eval()
+    with torch.no_grad():
+        for v in range(len(ds)):
+            feats, _, vid = ds[v]
+            # the reference's loop: batch of one video, masks from the collate (all False for a single video)
+            one = model.greedy_decode([feats[0].unsqueeze(0)], [torch.zeros(1, feats[0].shape[0], dtype=torch.bool, device=DEV)],
+                                      max_len=8)[0]
+            assert batched[vid] == one.replace("[CLS]", "").replace("[SEP]", ""), (vid, batched[vid], one)
+    assert len(batched) == len(ds.video_feat_list)

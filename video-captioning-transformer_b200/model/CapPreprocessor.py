@@ -5,6 +5,7 @@ Same contract -- ``(ids int64 [B, L], pad_mask bool [B, L])`` on ``device`` with
 one ``.to(device)`` per caption plus B row-assign kernels."""
 from typing import List, Tuple
 
+import numpy as np
 import torch
 from transformers import AutoTokenizer
 
@@ -19,12 +20,26 @@ class CapPreprocessor:
         self.end_id = self.tokenizer.convert_tokens_to_ids("[SEP]")
 
     def encode_host(self, captions: List[str]) -> torch.Tensor:
-        enc = [self.tokenizer.encode(c) for c in captions]
-        max_len = max(len(e) for e in enc)
-        ids = torch.full((len(enc), max_len), self.pad_id, dtype=torch.long)
-        for i, e in enumerate(enc):
-            ids[i, :len(e)] = torch.tensor(e, dtype=torch.long)
-        return ids
+        """[B, L] int64 on the host.  ONE batched tokenizer call for the captions not seen before (the reference encodes
+        caption by caption, model/CapPreprocessor.py:24-28; a training set repeats every caption each epoch, so the ids are
+        memoised per string), rows assembled in one numpy buffer."""
+        cache = self.__dict__.setdefault("_ids_cache", {})
+        new = [c for c in dict.fromkeys(captions) if c not in cache]
+        if new:
+            try:
+                enc = self.tokenizer(new, add_special_tokens=True, padding=False, truncation=False)["input_ids"]
+            except Exception:                                    # a tokenizer without a batch entry point
+                enc = [self.tokenizer.encode(c) for c in new]
+            if len(cache) + len(new) > 2_000_000:
+                cache.clear()
+            for c, e in zip(new, enc):
+                cache[c] = np.asarray(e, dtype=np.int64)
+        rows = [cache[c] for c in captions]
+        max_len = max(len(e) for e in rows)
+        ids = np.full((len(rows), max_len), self.pad_id, dtype=np.int64)
+        for i, e in enumerate(rows):
+            ids[i, :len(e)] = e
+        return torch.from_numpy(ids)
 
     def __call__(self, captions: List[str]) -> Tuple[torch.Tensor, torch.Tensor]:
         ids = self.encode_host(captions)
