@@ -315,6 +315,32 @@ int vct_cast(const float* src, void* dst, int dst_dtype, long long n, vct_stream
 int vct_argmax_append(const float* logits, long long ld_logits, int B, int V, long long* ys, long long ys_ld, int t,
                       int end_id, int* ended, int* n_ended, vct_stream_t stream);
 
+/* ---- data-parallel gradient exchange over NVLink peer memory (csrc/peer_comm.cu) ---------------
+ * Replaces DistributedDataParallel's bucketed NCCL all-reduce (train.py:218).  One process per GPU: every rank creates
+ * a communication region (cudaMalloc), publishes its cudaIpc handle (64 bytes, exchanged by the host over any
+ * transport), and maps all peers with vct_comm_connect.  The collectives are plain kernels on `stream` (CUDA-graph
+ * capturable) that read the peers' regions over NVLink and synchronise through flag words in peer memory.  All ranks
+ * must issue the same sequence of calls per channel (0..3) with the same arguments; `ctas` (grid size, <= 64) must be the
+ * same on every rank.  world <= 8.
+ *   vct_peer_allreduce_bf16: in-place SUM over ranks of n_elems bf16 values at byte_off of every region (two-shot, push
+ *       model: every rank sends its values of chunk p into rank p's staging area at stage_off -- world * ceil(n_elems / 8 /
+ *       world) * 16 bytes, disjoint from the data --, reduces its own chunk in fp32 in rank order with one rounding, and
+ *       writes the result into every region): identical results on all ranks.  n_elems % 8 == 0, offsets % 16 == 0.
+ *   vct_peer_allgather: the range is [world][slot_bytes]; rank r has written slot r of its own region; afterwards every
+ *       region holds every slot.  slot_bytes % 16 == 0.
+ *   vct_comm_status: 0, or 1 after a barrier timed out (~4 s: a peer died or the ranks diverged); synchronises.
+ *   vct_comm_connect_in_process: ranks that live in ONE process (tests): peer_bases[p] = vct_comm_base(handle of rank p). */
+int vct_comm_create(int rank, int world, long long bytes, int ctas, void** handle_out);
+void* vct_comm_base(void* handle);
+int vct_comm_ipc_handle(void* handle, unsigned char* out64);
+int vct_comm_connect(void* handle, const unsigned char* all_handles /* world x 64 bytes */);
+int vct_comm_connect_in_process(void* handle, void* const* peer_bases, const int* peer_devices);
+int vct_peer_allreduce_bf16(void* handle, long long byte_off, long long n_elems, long long stage_off, int channel,
+                            vct_stream_t stream);
+int vct_peer_allgather(void* handle, long long byte_off, long long slot_bytes, int channel, vct_stream_t stream);
+int vct_comm_status(void* handle);
+int vct_comm_destroy(void* handle);
+
 /* ---- debug: the keep mask (1 = kept) of `n` elements of a dropout site ----------------------- */
 int vct_dropout_mask(unsigned char* out, long long n, float drop_p, const unsigned long long* rng_state,
                      unsigned int site, vct_stream_t stream);

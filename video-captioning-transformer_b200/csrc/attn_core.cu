@@ -409,12 +409,18 @@ attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool colok = 4 * lane < dh;
     const T* vbase = v + (long long)b * D.v_bs + h * dh + 4 * lane;
-    for (int j = 0; j < Lk; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
-        if (colok) {
-            const float4 vv = ld4(vbase + (long long)j * D.v_ld);
-            acc.x = fmaf(pj, vv.x, acc.x); acc.y = fmaf(pj, vv.y, acc.y);
-            acc.z = fmaf(pj, vv.z, acc.z); acc.w = fmaf(pj, vv.w, acc.w);
+    // eight V rows in flight per pass (a one-row-per-iteration loop is a chain of L2 latencies)
+    for (int j0 = 0; j0 < Lk; j0 += 8) {
+        float4 vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            vv[u] = (colok && j0 + u < Lk) ? ld4(vbase + (long long)(j0 + u) * D.v_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const int j = j0 + u;
+            const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
+            acc.x = fmaf(pj, vv[u].x, acc.x); acc.y = fmaf(pj, vv[u].y, acc.y);
+            acc.z = fmaf(pj, vv[u].z, acc.z); acc.w = fmaf(pj, vv[u].w, acc.w);
         }
     }
     if (colok) st4(o + (long long)b * D.o_bs + h * dh + 4 * lane, acc);

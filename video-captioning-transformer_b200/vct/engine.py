@@ -181,8 +181,9 @@ class CaptionEngine:
         self.upstream = torch.ones(1, dtype=torch.float32, device=device)
         # step stamp per embedding row (vct_embed_mark): which rows of the table the current step touches
         self.emb_stamp = torch.zeros(max(1, int(self.dims.V)), dtype=torch.int32, device=device)
-        self.side_streams = [torch.cuda.Stream(device=device) for _ in range(2)] \
+        self.side_streams = [torch.cuda.Stream(device=device) for _ in range(3)] \
             if os.environ.get("VCT_SIDE_STREAM", "1") != "0" else None
+        self.peer = None             # vct.peer.PeerComm once the data-parallel trainer has attached one (attach_peer)
         self._tempo: Dict[int, torch.Tensor] = {}
         self._ws: Dict[Tuple, SimpleNamespace] = {}
         self._shadow_version = None
@@ -293,7 +294,17 @@ class CaptionEngine:
                 # data parallel: 1/world is folded into the Adam kernel (DDP averages, train.py:218)
                 group, world = ar
                 grad_scale = 1.0 / world
-                if reduce:
+                if reduce and self.peer is not None:
+                    # NVLink peer-memory exchange: cast the slice into the communication region, two-shot all-reduce
+                    # kernel (graph-capturable), Adam reads the bf16 sums
+                    g16 = a.ensure_grad16()
+                    n8 = (hi - lo + 7) // 8 * 8
+                    plan.add(f"vct_cast:{first}..{last}", self.lib.vct_cast, a.grad.data_ptr() + 4 * lo, g16.data_ptr() + 2 * lo,
+                             BF16, hi - lo)
+                    plan.add(f"vct_peer_allreduce:{first}..{last}", self.lib.vct_peer_allreduce_bf16, self.peer.handle,
+                             self._peer_g16_off + 2 * lo, n8, self._peer_stage_off, 0)
+                    g_ptr, g_dt = g16.data_ptr() + 2 * lo, BF16
+                elif reduce:
                     if self.grad_comm_dtype == BF16:
                         g16 = a.ensure_grad16()
                         plan.add(f"vct_cast:{first}..{last}", self.lib.vct_cast, a.grad.data_ptr() + 4 * lo, g16.data_ptr() + 2 * lo,
@@ -314,6 +325,33 @@ class CaptionEngine:
                      self.hyper.data_ptr(), grad_scale)
         plan.adam_covered = getattr(plan, "adam_covered", 0) + (hi - lo)
 
+    PEER_MAX_TOKENS = 16384          # tokens of all ranks the sparse embedding exchange covers (vct_embed_sort limit)
+
+    @staticmethod
+    def peer_region_bytes(numel: int, d: int) -> int:
+        """Size of one rank's communication region: bf16 gradient arena + gathered embedding rows + gathered ids."""
+        r = lambda v: (v + 255) // 256 * 256
+        return 2 * r(numel * 2 + 4096) + r(CaptionEngine.PEER_MAX_TOKENS * d * 4) + r(2 * CaptionEngine.PEER_MAX_TOKENS * 8) + 4096
+
+    def attach_peer(self, comm) -> None:
+        """Route the data-parallel gradient exchange through the NVLink peer-memory kernels (csrc/peer_comm.cu): the bf16
+        gradient arena, the gathered embedding rows and the gathered ids live in the communication region every rank maps."""
+        if self.grad_comm_dtype != BF16:
+            raise RuntimeError("the peer-memory exchange carries bf16 gradients (VCT_GRAD_COMM=bf16)")
+        a = self.arena
+        self.peer = comm
+        self._peer_g16_off = comm.reserve(a.numel * 2 + 256)
+        a.grad16 = comm.tensor(self._peer_g16_off, (a.numel,), torch.bfloat16)
+        a.grad16.zero_()
+        self._peer_stage_off = comm.reserve(a.numel * 2 + 4096)     # staging of the two-shot all-reduce (any slice fits)
+        self._peer_rows_off = comm.reserve(self.PEER_MAX_TOKENS * self.dims.d * 4)
+        self._peer_ids_off = comm.reserve(2 * self.PEER_MAX_TOKENS * 8)
+        for ws in self._ws.values():                      # plans built before the attachment hold stale pointers
+            if hasattr(ws, "plans"):
+                ws.plans.clear()
+                getattr(ws, "graphs", {}).clear()
+                getattr(ws, "scratch", {}).pop(("emb.buffers", comm.world), None)
+
     def emb_mode(self, ws, world: int) -> str:
         """How the native trainer treats the embedding-table gradient of this workspace:
         'local'  one GPU: atomic scatter, Adam split into untouched rows (start of the step) and touched rows (end)
@@ -325,7 +363,9 @@ class CaptionEngine:
             return "dense" if world > 1 else "local-unsplit"
         if world == 1:
             return "local"
-        ok = world * ws.B * ws.S <= 16384 and self.dims.V <= 32768 and os.environ.get("VCT_SPARSE_EMB", "1") != "0"
+        ok = world * ws.B * ws.S <= self.PEER_MAX_TOKENS and self.dims.V <= 32768 and os.environ.get("VCT_SPARSE_EMB", "1") != "0"
+        if self.peer is not None and (ws.B * (ws.S + 1)) % 2:
+            ok = False                                    # the peer all-gather moves 16-byte vectors: ids slots must be even
         return "sparse" if ok else "dense"
 
     def emb_buffers(self, ws, world: int):
@@ -333,10 +373,18 @@ class CaptionEngine:
         key = ("emb.buffers", world)
         if key not in ws.scratch:
             Rd = ws.B * ws.S
-            ws.scratch[key] = (torch.zeros((world * ws.B, ws.S + 1), dtype=torch.int64, device=self.device),
-                               torch.empty((world * Rd, self.dims.d), dtype=torch.float32, device=self.device),
-                               torch.empty((Rd, self.dims.d), dtype=torch.float32, device=self.device),
-                               torch.zeros(world * Rd, dtype=torch.int32, device=self.device))
+            keys = torch.zeros(world * Rd, dtype=torch.int32, device=self.device)
+            if self.peer is not None and world > 1:
+                # views of the communication region: this rank's rows / ids are written straight into its own slot
+                r = self.peer.rank
+                all_ids = self.peer.tensor(self._peer_ids_off, (world * ws.B, ws.S + 1), torch.int64)
+                all_rows = self.peer.tensor(self._peer_rows_off, (world * Rd, self.dims.d), torch.float32)
+                all_ids.zero_()
+                ws.scratch[key] = (all_ids, all_rows, all_rows[r * Rd:(r + 1) * Rd], keys)
+            else:
+                ws.scratch[key] = (torch.zeros((world * ws.B, ws.S + 1), dtype=torch.int64, device=self.device),
+                                   torch.empty((world * Rd, self.dims.d), dtype=torch.float32, device=self.device),
+                                   torch.empty((Rd, self.dims.d), dtype=torch.float32, device=self.device), keys)
         return ws.scratch[key]
 
     def _emb_range(self):
@@ -365,6 +413,10 @@ class CaptionEngine:
                 ids_ptr, nB = all_ids.data_ptr(), world * ws.B
             shadow = a.ensure_shadow().data_ptr() + 2 * lo if self.cdt == BF16 else None
             with self._side(p, 2):
+                if world > 1 and self.peer is not None:
+                    # token ids of every rank (the trainer has staged this rank's ids into its slot of the region)
+                    p.add("vct_peer_allgather:ids", lib.vct_peer_allgather, self.peer.handle, self._peer_ids_off,
+                          ws.B * (ws.S + 1) * 8, 0)
                 p.add("vct_embed_mark", lib.vct_embed_mark, ids_ptr, ws.S + 1, nB, ws.S, D.V, D.pad_id, self.emb_stamp.data_ptr(),
                       self.rng_state.data_ptr())
                 if world > 1:
@@ -942,13 +994,19 @@ class CaptionEngine:
             all_ids, all_rows, rows, keys = self.emb_buffers(ws, world)
             p.add("vct_embed_bwd_rows", lib.vct_embed_bwd_rows, dx.data_ptr(), rows.data_ptr(), B, S, d, pd,
                   self.rng_state.data_ptr(), SITE_EMBED)
-            with self._side(p, 2):
+            # (peer-memory exchange: own lane and own channel, so that this chain and the per-slice all-reduce + Adam chain
+            # of lane 2 do not queue behind each other at the end of the step; NCCL: everything on the optimizer lane)
+            with self._side(p, 3 if self.peer is not None else 2):
                 def gather(stream, rows=rows, all_rows=all_rows, group=group):
                     import torch.distributed as dist
                     with torch.cuda.stream(stream):
                         dist.all_gather_into_tensor(all_rows, rows, group=group)
                     return 0
-                p.add("py:all_gather:embedding_rows", gather)
+                if self.peer is not None:
+                    p.add("vct_peer_allgather:embedding_rows", lib.vct_peer_allgather, self.peer.handle, self._peer_rows_off,
+                          Rd * d * 4, 1)
+                else:
+                    p.add("py:all_gather:embedding_rows", gather)
                 # every rank sums the same rows in the same order: bit-identical table gradients, replicas cannot drift
                 p.add("vct_embed_segment_sum", lib.vct_embed_segment_sum, keys.data_ptr(), all_rows.data_ptr(), self._g(emb),
                       world * Rd, d)
@@ -965,7 +1023,11 @@ class CaptionEngine:
         self._ln_bwd(p, "enc.norm", ws.g_mem.data_ptr(), ws.enc_out.data_ptr(), ws.mem_stats[0].data_ptr(),
                      ws.mem_stats[1].data_ptr(), "video_encoder.transformer_encoder.norm.weight",
                      "video_encoder.transformer_encoder.norm.bias", ws.g_a.data_ptr(), None, None, Re, 0.0, 0, ws)
-        self._adam_slice(p, "video_encoder.transformer_encoder.norm.weight", "video_encoder.transformer_encoder.norm.bias")
+        # Data parallel: the final norm travels with the last layer's slice and unify with the first layer's (contiguous in
+        # the arena), because every extra exchange costs two cross-GPU barriers at the very end of the step.
+        merge = getattr(p, "allreduce", None) is not None
+        if not merge:
+            self._adam_slice(p, "video_encoder.transformer_encoder.norm.weight", "video_encoder.transformer_encoder.norm.bias")
         dx, other = ws.g_a, ws.g_b
         g_o = ws.g_o_c.data_ptr()
         for l in reversed(range(D.L_enc)):
@@ -1014,13 +1076,24 @@ class CaptionEngine:
                        addend=ws.g_s.data_ptr(), ld_addend=d,
                        C2=ws.g_x0_c.data_ptr() if (last and cd == BF16) else None, c2_dtype=cd, ldc2=d)
             dx, other = other, dx
-            self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm2.bias")
+            if not merge:
+                self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm2.bias")
+            elif l > 0:
+                self._adam_slice(p, pre + "self_attn.in_proj_weight",
+                                 "video_encoder.transformer_encoder.norm.bias" if l == D.L_enc - 1 else pre + "norm2.bias")
         g_x0_c = ws.g_x0_c.data_ptr() if cd == BF16 else dx.data_ptr()
         with side(p):
             self._gemm(p, "unify.wgrad", d, D.Din, Re, g_x0_c, d, 1, ws.a0.data_ptr(), D.Din, 1,
                        self._g("video_encoder.unify.0.weight"), F32, D.Din)
             self._colsum(p, "unify.bias", g_x0_c, d, Re, d, self._g("video_encoder.unify.0.bias"), ws)
-        self._adam_slice(p, "video_encoder.unify.0.weight", "video_encoder.unify.0.bias")
+        if not merge:
+            self._adam_slice(p, "video_encoder.unify.0.weight", "video_encoder.unify.0.bias")
+        elif D.L_enc == 0:
+            self._adam_slice(p, "video_encoder.unify.0.weight", "video_encoder.transformer_encoder.norm.bias")
+        else:
+            pre0 = "video_encoder.transformer_encoder.layers.0."
+            self._adam_slice(p, "video_encoder.unify.0.weight",
+                             "video_encoder.transformer_encoder.norm.bias" if D.L_enc == 1 else pre0 + "norm2.bias")
 
     # ------------------------------------------------------------------------------------------
     # running

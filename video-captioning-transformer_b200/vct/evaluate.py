@@ -42,12 +42,20 @@ def sharded_greedy_eval(model, dataset, max_len: int = 30, batch_size: int = 256
     mode = dataset.mode
     dataset.mode = "by_video"
     mine = shard_indices(len(dataset.video_feat_list), rank, world)
+    # Batches hold videos of ONE frame count: the reference decodes one video per call (json data.eval.batch_size = 1), and
+    # a padded batch would not reproduce it -- cross-attention is never masked, so padded frames of a ragged
+    # batch are attended to.  (CLIP4Clip uni_12 features are all 12 frames: one group.)
+    lens = dataset.lengths[0].tolist()
+    groups: Dict[int, List[int]] = {}
+    for v in mine:
+        groups.setdefault(int(lens[v]), []).append(v)
     local: Dict[str, str] = {}
     try:
-        for i in range(0, len(mine), batch_size):
-            feats, masks, _, vids = dataset.batch(mine[i:i + batch_size])
-            caps = model.greedy_decode(feats, masks if with_masks else None, max_len=max_len)
-            local.update(zip(vids, (_strip(c) for c in caps)))
+        for _, members in sorted(groups.items()):
+            for i in range(0, len(members), batch_size):
+                feats, masks, _, vids = dataset.batch(members[i:i + batch_size])
+                caps = model.greedy_decode(feats, masks if with_masks else None, max_len=max_len)
+                local.update(zip(vids, (_strip(c) for c in caps)))
     finally:
         dataset.mode = mode
         if was_training:

@@ -109,6 +109,15 @@ SIGNATURES = {
     "vct_cast": (i32, [vp, vp, i32, ll, vp]),
     "vct_argmax_append": (i32, [vp, ll, i32, i32, vp, ll, i32, i32, vp, vp, vp]),
     "vct_dropout_mask": (i32, [vp, ll, f32, vp, u32, vp]),
+    "vct_comm_create": (i32, [i32, i32, ll, i32, C.POINTER(vp)]),
+    "vct_comm_base": (vp, [vp]),
+    "vct_comm_ipc_handle": (i32, [vp, C.POINTER(C.c_ubyte)]),
+    "vct_comm_connect": (i32, [vp, C.c_char_p]),
+    "vct_comm_connect_in_process": (i32, [vp, C.POINTER(vp), C.POINTER(i32)]),
+    "vct_peer_allreduce_bf16": (i32, [vp, ll, ll, ll, i32, vp]),
+    "vct_peer_allgather": (i32, [vp, ll, ll, i32, vp]),
+    "vct_comm_status": (i32, [vp]),
+    "vct_comm_destroy": (i32, [vp]),
 }
 
 _lib = None

@@ -138,10 +138,45 @@ class CaptionTrainer:
         self._cap_stream = torch.cuda.Stream(device=self.engine.device, priority=-1) \
             if os.environ.get("VCT_MAIN_PRIORITY", "0") == "1" else None
         self.buckets = None
+        self.peer = None
         if self.world > 1:
             # backward finishes the decoder (generator first, embedding last) before the encoder
             self.buckets = gradient_buckets(self.engine.arena, ["video_encoder.", "cap_decoder."])
             self.comm_stream = torch.cuda.Stream(device=self.engine.device)
+            self._attach_peer_comm()
+
+    def _attach_peer_comm(self) -> None:
+        """Gradient exchange over NVLink peer memory (csrc/peer_comm.cu) when every rank of the group can map every other
+        rank's memory; otherwise (VCT_COMM=nccl, fp32 exchange, no P2P) the NCCL path below stays in charge.  The decision
+        is made collectively: one rank that cannot take part switches all of them."""
+        import torch.distributed as dist
+        from .engine import BF16
+        from .peer import PeerComm, peer_comm_supported
+        eng = self.engine
+        rank = dist.get_rank(self.process_group_or_default())
+        ok = self.fuse_adam and eng.cdt == BF16 and eng.grad_comm_dtype == BF16 and peer_comm_supported(eng.device, self.world)
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=eng.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            return
+        try:
+            comm = PeerComm(rank, self.world, eng.peer_region_bytes(eng.arena.numel, eng.dims.d), eng.device, group=self.group)
+            good = 1
+        except Exception as e:                                   # e.g. cudaIpc refused inside this container
+            import sys
+            print(f"[vct] peer-memory communication unavailable on rank {rank} ({e}); using NCCL", file=sys.stderr, flush=True)
+            comm, good = None, 0
+        flag.fill_(good)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 0:
+            if comm is not None:
+                comm.close()
+            return
+        eng.attach_peer(comm)
+        self.peer = comm
+
+    def process_group_or_default(self):
+        return self.group
 
     def set_lr(self, lr: float) -> None:
         self.engine.set_lr(lr)
@@ -150,9 +185,10 @@ class CaptionTrainer:
     def _compute(self, ws, fuse_adam: bool = False, allreduce=None) -> None:
         eng = self.engine
         eng.tick()
+        world = allreduce[1] if allreduce is not None else 1
         # (the embedding-table gradient is all-zero here: the previous step cleared the rows it had scattered into)
-        if fuse_adam and eng.emb_mode(ws, 1) == "local":
-            eng.run(eng.plan_embed_early(ws, 1))        # optimizer lane, un-joined: overlaps the whole forward
+        if fuse_adam and eng.emb_mode(ws, world) in ("local", "sparse"):
+            eng.run(eng.plan_embed_early(ws, world))    # optimizer lane, un-joined: overlaps the whole forward
         eng.run(eng.plan_forward(ws, fused_grad=True, part="all"))
         eng.run(eng.plan_backward(ws, sce_first=False, part="all", fuse_adam=fuse_adam, allreduce=allreduce))
 
@@ -317,6 +353,15 @@ class CaptionTrainer:
             self._graphed((B, T, S, "step+adam"), lambda: self._compute(ws, fuse_adam=True), ws=ws)
         elif self.world == 1:
             self._graphed((B, T, S, "step"), lambda: (self._compute(ws), self._update(ws)), ws=ws)
+        elif self.peer is not None and self.fuse_adam:
+            # data parallel over NVLink peer memory: the collectives are kernels of the library, so [tick, forward, backward,
+            # per-slice all-reduce + Adam] is ONE CUDA graph exactly like the single-GPU step
+            if eng.emb_mode(ws, self.world) == "sparse":
+                all_ids = eng.emb_buffers(ws, self.world)[0]
+                r = self.peer.rank
+                all_ids[r * B:(r + 1) * B].copy_(ws.ids, non_blocking=True)
+            self._graphed((B, T, S, "step+adam+peer"),
+                          lambda: self._compute(ws, fuse_adam=True, allreduce=(self.group, self.world)), ws=ws)
         elif self.fuse_adam and self.segmented:
             # data parallel: forward is one CUDA graph and backward a chain of graph SEGMENTS -- the launches between two
             # optimizer slices are captured together -- with the per-slice NCCL all-reduce + Adam issued eagerly on the
