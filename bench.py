@@ -75,7 +75,7 @@ def measured_peaks():
 # tools/ncu_summary.py --traffic-json from `ncu --set full` of `bench.py --steps 1 --warmup 3 --no-graph`)
 FAMILY_KERNEL = {"vct_gemm:layers": "gemm_tc_kernel", "vct_gemm:generator": "gemm_tc_persistent_kernel", "vct_adam": "adam_kernel",
                  "vct_ln_residual_fwd": "ln_fwd_kernel", "vct_ln_residual_bwd": "ln_bwd_kernel", "vct_ln_bwd_reduce": "ln_bwd_reduce_kernel",
-                 "vct_sce": "sce_kernel", "vct_colsum": "colsum_kernel", "vct_attn_bwd": "attn_bwd_tc_kernel",
+                 "vct_sce_typed": "sce_reg_kernel", "vct_colsum": "colsum_kernel", "vct_attn_bwd": "attn_bwd_tc_kernel",
                  "vct_attn_enc_self_fwd": "attn_fused_kernel", "vct_attn_dec_self_fwd": "attn_fused_kernel",
                  "vct_attn_dec_cross_fwd": "attn_fused_kernel"}
 
@@ -403,10 +403,10 @@ def algorithmic_work(name, a, eng):
     if base == "vct_ln_residual_bwd":
         R, d = a[13], a[14]
         return R * d * (4.0 + 4.0 + 4.0 + (es if a[6] else 0.0)), 0.0
-    if base == "vct_sce":
-        B, S, Vv = a[4], a[5], a[6]
-        lb = 4.0 if len(a) < 18 or a[17] == 0 else 2.0      # logits storage type (last argument when present)
-        return B * S * Vv * (lb + (es if a[13] else 0.0)), 0.0
+    if base == "vct_sce_typed":
+        B, S, Vv = a[5], a[6], a[7]
+        lb = 4.0 if a[1] == 0 else 2.0                      # logits storage type
+        return B * S * Vv * (lb + (es if a[14] else 0.0)), 0.0
     if base == "vct_adam":
         n = a[5]
         return n * (16.0 + 12.0 + (2.0 if a[4] else 0.0)), 0.0
@@ -436,7 +436,7 @@ def kernel_rooflines(eng, plans, peaks, adam_ms, extra_adam=True):
     for n, m, a in zip(names, med, calls):
         f = family_of(n)
         by, fl = algorithmic_work(n, a, eng)
-        if f.startswith(("vct_gemm", "vct_attn", "vct_ln", "vct_sce")):
+        if f.startswith(("vct_gemm", "vct_attn", "vct_ln", "vct_sce", "vct_colsum")):
             if n not in alone_cache:
                 alone_cache[n] = graph_time_ms(n, a)
             alone = alone_cache[n]
@@ -578,7 +578,11 @@ def main():
             return trainer.step(xd, vd, td)
 
         def step_host():
-            return trainer.step(xh, vh, th).item()
+            # the public API as a training loop uses it: this step consumes the batch whose H2D copy was started during the
+            # previous step, then the copy of the next batch is started and the loss is read back (host sync every step)
+            loss = trainer.step(xh, vh, th)
+            trainer.prefetch(xh, vh, th)
+            return loss.item()
         d2h = 4
         h2d = x.numel() * 4 + vm.numel() + tok.numel() * 8
 

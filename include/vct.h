@@ -284,6 +284,15 @@ int vct_sce(const float* logits, long long ld_logits, const long long* ids, long
             void* dlogits, int dl_dtype, long long ld_dl, const float* upstream,
             vct_stream_t stream);
 
+/* The same with the logits stored in logits_dtype (VCT_F32 or VCT_BF16): the training plans let the generator GEMM write
+ * bf16 logits, so no fp32 [B*S, V] buffer exists on that path.  Rows of up to 32768 columns with ld % 8 == 0 and
+ * ld_dl == ld_logits run on a register-resident kernel (no shared-memory staging). */
+int vct_sce_typed(const void* logits, int logits_dtype, long long ld_logits, const long long* ids, long long ids_ld,
+                  int B, int S, int V, float alpha, float beta, int pad_id,
+                  float* loss_out, float* row_parts, unsigned int* counter,
+                  void* dlogits, int dl_dtype, long long ld_dl, const float* upstream,
+                  vct_stream_t stream);
+
 /* ---- column sums (bias gradients): out[n] = sum_m X[m,n]; deterministic ----------------------
  * partials: fp32 workspace vct_colsum_workspace_floats(M, N); counter as above. */
 long long vct_colsum_workspace_floats(int M, int N);

@@ -65,3 +65,49 @@ def test_batched_sharded_eval_equals_per_video_decode(tmp_path, tokenizer_dir):
                                       max_len=8)[0]
             assert batched[vid] == one.replace("[CLS]", "").replace("[SEP]", ""), (vid, batched[vid], one)
     assert len(batched) == len(ds.video_feat_list)
+
+
+def test_prefetched_steps_equal_direct_steps(tokenizer_dir):
+    """trainer.prefetch() only moves the H2D copy off the critical path: losses of prefetched steps are bit-identical to
+    steps fed directly, including when the prefetched batch differs from step to step."""
+    from vct.synthetic import synth_batch
+    from vct.trainer import CaptionTrainer
+    batches = [synth_batch(8, 12, 512, 21, seed=100 + k, padded=True) for k in range(4)]
+    pinned = [tuple(t.pin_memory() for t in b) for b in batches]
+    out = []
+    for mode in ("direct", "prefetch"):
+        model = _model(tokenizer_dir, "bf16")
+        model.train()
+        tr = CaptionTrainer(model, lr=1e-4)
+        losses = []
+        if mode == "prefetch":
+            tr.prefetch(*pinned[0])
+        for k in range(4):
+            x, vm, ids = pinned[k]
+            loss = tr.step(x, vm, ids)
+            if mode == "prefetch" and k + 1 < 4:
+                tr.prefetch(*pinned[k + 1])
+            losses.append(float(loss.item()))
+        out.append(losses)
+    assert out[0] == out[1], out
+
+
+def test_too_long_sequences_fail_up_front_with_a_clear_error(tokenizer_dir):
+    """the attention kernels cover sequences up to 64 rows; anything longer must be rejected before the first
+    launch (not in the middle of an epoch) with a message that names the remedy."""
+    model = _model(tokenizer_dir, "bf16")
+    model.train()
+    x = torch.randn(2, 70, 512, device=DEV)                       # 70 frames -> memory length 71
+    vm = torch.zeros(2, 70, dtype=torch.bool, device=DEV)
+    ids = torch.randint(1000, 30522, (2, 21), device=DEV)
+    with pytest.raises(ValueError, match="sequence too long"):
+        model([x], [vm], ids)
+    x = torch.randn(2, 12, 512, device=DEV)
+    vm = torch.zeros(2, 12, dtype=torch.bool, device=DEV)
+    ids = torch.randint(1000, 30522, (2, 80), device=DEV)         # 79 decoder positions
+    with pytest.raises(ValueError, match="sequence too long"):
+        model([x], [vm], ids)
+    model.eval()
+    with pytest.raises(ValueError, match="sequence too long"):
+        model.greedy_decode([x], [vm], max_len=100)
+    assert len(model.greedy_decode([x], [vm], max_len=6)) == 2    # the engine is still usable afterwards

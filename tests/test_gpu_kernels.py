@@ -382,6 +382,66 @@ def test_sce_forward_backward_against_oracle(lib, alpha, B, S, V):
     torch.testing.assert_close(dlb[:, :V].float().cpu(), 0.25 * zz.grad, rtol=1e-2, atol=1e-7)
 
 
+@pytest.mark.parametrize("alpha", [0.5, 1.0])
+@pytest.mark.parametrize("B,S,V", [(8, 20, 30522), (3, 5, 1000)])
+def test_sce_bf16_logits_against_oracle(lib, alpha, B, S, V):
+    """vct_sce_typed with the logits STORED in bf16 (what the training plans feed it): loss and gradient of the oracle
+    evaluated on the same bf16-rounded logits (fp32 arithmetic on both sides: tolerances as for fp32 logits)."""
+    from oracle import vct_oracle as O
+    g = torch.Generator().manual_seed(V + B + 1)
+    N, Vp = B * S, (V + 7) // 8 * 8
+    logits = (torch.randn(N, V, generator=g) * 2.0).to(torch.bfloat16)
+    ids = torch.randint(1, V, (B, S + 1), generator=g)
+    ids[1, 3:] = 0
+    zz = logits.float().clone().requires_grad_(True)
+    want = O.sce_loss(zz, ids[:, 1:].reshape(-1), alpha, 1 - alpha, 0)
+    want.backward()
+    z = torch.full((N, Vp), 7.0, dtype=torch.bfloat16)          # padding columns hold garbage: must be ignored
+    z[:, :V] = logits
+    z, idd = z.to(DEV), ids.to(DEV)
+    loss = torch.zeros(1, device=DEV)
+    parts = torch.empty(N, 2, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dl = torch.full((N, Vp), float("nan"), device=DEV, dtype=torch.bfloat16)
+    for _ in range(2):
+        L.check(lib.vct_sce_typed(z.data_ptr(), L.BF16, Vp, idd.data_ptr(), S + 1, B, S, V, alpha, 1 - alpha, 0, loss.data_ptr(),
+                                  parts.data_ptr(), counter.data_ptr(), dl.data_ptr(), L.BF16, Vp, None, stream()))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - want.item()) < 2e-5 * max(1.0, abs(want.item()))
+    torch.testing.assert_close(dl[:, :V].float().cpu(), zz.grad, rtol=1e-2, atol=1e-7)      # bf16 rounding of the gradient
+    assert dl[:, V:].float().abs().sum().item() == 0.0
+    dl32 = torch.full((N, Vp), float("nan"), device=DEV)
+    L.check(lib.vct_sce_typed(z.data_ptr(), L.BF16, Vp, idd.data_ptr(), S + 1, B, S, V, alpha, 1 - alpha, 0, None, None, None,
+                              dl32.data_ptr(), L.F32, Vp, None, stream()))
+    torch.cuda.synchronize()
+    torch.testing.assert_close(dl32[:, :V].cpu(), zz.grad, rtol=2e-4, atol=1e-8)
+
+
+def test_sce_staged_kernel_still_covers_unaligned_rows(lib):
+    """Row strides that are not multiples of 8 run on the shared-memory kernel (the register kernel needs 16-byte groups)."""
+    from oracle import vct_oracle as O
+    B, S, V, ld = 3, 4, 1001, 1004
+    g = torch.Generator().manual_seed(5)
+    N = B * S
+    logits = torch.randn(N, V, generator=g)
+    ids = torch.randint(1, V, (B, S + 1), generator=g)
+    zz = logits.clone().requires_grad_(True)
+    want = O.sce_loss(zz, ids[:, 1:].reshape(-1), 0.5, 0.5, 0)
+    want.backward()
+    z = torch.zeros(N, ld)
+    z[:, :V] = logits
+    z, idd = z.to(DEV), ids.to(DEV)
+    loss = torch.zeros(1, device=DEV)
+    parts = torch.empty(N, 2, device=DEV)
+    counter = torch.zeros(1, dtype=torch.int32, device=DEV)
+    dl = torch.full((N, ld), float("nan"), device=DEV)
+    L.check(lib.vct_sce(z.data_ptr(), ld, idd.data_ptr(), S + 1, B, S, V, 0.5, 0.5, 0, loss.data_ptr(), parts.data_ptr(),
+                        counter.data_ptr(), dl.data_ptr(), L.F32, ld, None, stream()))
+    torch.cuda.synchronize()
+    assert abs(loss.item() - want.item()) < 2e-5 * max(1.0, abs(want.item()))
+    torch.testing.assert_close(dl[:, :V].cpu(), zz.grad, rtol=2e-4, atol=1e-8)
+
+
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("M,N,ld", [(1280, 768, 768), (100, 30522, 30528), (7, 40, 48)])
 def test_colsum(lib, dtype, M, N, ld):

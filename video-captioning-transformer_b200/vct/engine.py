@@ -553,6 +553,7 @@ class CaptionEngine:
             ws = self._ws.pop(key)
             self._ws[key] = ws            # most recently used last
             return ws
+        self._check_lengths(T + 1, S)
         self._evict_workspaces()
         D = self.dims
         ws = SimpleNamespace(B=B, T=T, S=S, M=T + 1, training=training)
@@ -620,7 +621,11 @@ class CaptionEngine:
             ws.dec.append(e)
         act("hfin", Rd, d)
         self._buf(ws, "hfin_stats", (2, Rd), f32)
-        self._buf(ws, "logits", (Rd, ws.Vp), f32)
+        # teacher-forced logits: the training plans keep them in bf16 when the engine computes in bf16 (the caption loss is
+        # all the reference keeps of them, model/MMT4Caption.py:120-121; VCT_LOGITS=fp32 restores the fp32 buffer); eval
+        # workspaces stay fp32 (decode_word / argmax read them)
+        ws.logits_dt = BF16 if (self.cdt == BF16 and training and os.environ.get("VCT_LOGITS", "bf16") != "fp32") else F32
+        self._buf(ws, "logits", (Rd, ws.Vp), _TDT[ws.logits_dt])
         self._buf(ws, "loss", (1,), f32)
         self._buf(ws, "row_parts", (Rd, 2), f32)
         if training:
@@ -652,6 +657,20 @@ class CaptionEngine:
         ws.mem_token = None
         self._ws[key] = ws
         return ws
+
+    MAX_LEN = 64        # longest sequence the attention kernels cover (memory rows T + 1, decoder positions S)
+
+    def _check_lengths(self, M: int, S: int) -> None:
+        """The attention kernels (fused tcgen05 and SIMT alike) hold a whole (batch, head) in one tile / one warp's key
+        lanes: sequences are limited to 64 rows, and the dropout counter space assigns 8 groups of 8 keys to a row.  The
+        reference has no such limit (captions are not truncated for training); fail BEFORE the first launch, with the
+        remedy, instead of in the middle of an epoch."""
+        if M > self.MAX_LEN or S > self.MAX_LEN:
+            raise ValueError(
+                f"vct_b200: sequence too long for the attention kernels (memory length T+1 = {M}, decoder positions = {S}; "
+                f"limit {self.MAX_LEN}).  Sample at most {self.MAX_LEN - 1} frames per video and truncate captions to "
+                f"{self.MAX_LEN} word pieces (+1 for the shifted target) in the data pipeline -- the shipped CLIP4Clip "
+                f"features have 12 frames and MSR-VTT / MSVD captions stay below 40 word pieces (see INTEGRATION.md).")
 
     def _evict_workspaces(self) -> None:
         """Bound the per-shape workspace cache (batches built by caption length have a new S almost every step): keep the
@@ -784,13 +803,13 @@ class CaptionEngine:
                      ws.hfin.data_ptr(), ws.hfin_c.data_ptr() if cd == BF16 else None, None, ws.hfin_stats[0].data_ptr(),
                      ws.hfin_stats[1].data_ptr(), Rd, 0.0, 0)
         self._gemm(plan, "generator", Rd, D.V, d, ws.hfin_c.data_ptr(), d, 0, self._w("cap_decoder.generator.weight"), d, 0,
-                   ws.logits.data_ptr(), F32, ws.Vp, bias=self._p("cap_decoder.generator.bias"))
+                   ws.logits.data_ptr(), ws.logits_dt, ws.Vp, bias=self._p("cap_decoder.generator.bias"))
         if with_loss or with_grad:
             self._sce(plan, ws, with_loss, with_grad)
 
     def _sce(self, plan: Plan, ws, with_loss: bool, with_grad: bool):
         D = self.dims
-        plan.add("vct_sce", self.lib.vct_sce, ws.logits.data_ptr(), ws.Vp, ws.ids.data_ptr(), ws.S + 1, ws.B, ws.S, D.V,
+        plan.add("vct_sce_typed", self.lib.vct_sce_typed, ws.logits.data_ptr(), ws.logits_dt, ws.Vp, ws.ids.data_ptr(), ws.S + 1, ws.B, ws.S, D.V,
                  float(D.alpha), float(1.0 - D.alpha), D.pad_id,
                  ws.loss.data_ptr() if with_loss else None, ws.row_parts.data_ptr(), self.counters.data_ptr() + 4 * 4,
                  ws.dlogits.data_ptr() if with_grad else None, self.cdt, ws.Vp, self.upstream.data_ptr())
@@ -1162,6 +1181,7 @@ class CaptionEngine:
         key = ("decode", B, T, max_len)
         if key in self._ws:
             return self._ws[key]
+        self._check_lengths(T + 1, max_len - 1)
         D = self.dims
         d, M = D.d, T + 1
         cdt, f32 = _TDT[self.cdt], torch.float32

@@ -115,7 +115,7 @@ class DecoderFn(torch.autograd.Function):
         ctx.engine, ctx.ws, ctx.module, ctx.version = engine, ws, module, ws.dec_version
         V = engine.dims.V
         if want_logits:
-            logits = ws.logits.view(B, S, ws.Vp)[:, :, :V].clone()
+            logits = ws.logits.view(B, S, ws.Vp)[:, :, :V].to(torch.float32, copy=True)
         else:
             logits = ws.logits.new_empty(0)         # caption_forward discards the logits (model/MMT4Caption.py:120-121)
         loss = ws.loss[0].clone()

@@ -103,6 +103,7 @@ SIGNATURES = {
     "vct_adam_rows": (i32, [vp, vp, vp, vp, vp, i32, i32, vp, f32, vp, vp, i32, vp]),
     "vct_embed_zero": (i32, [vp, ll, vp, i32, i32, i32, i32, vp]),
     "vct_sce": (i32, [vp, ll, vp, ll, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, i32, ll, vp, vp]),
+    "vct_sce_typed": (i32, [vp, i32, ll, vp, ll, i32, i32, i32, f32, f32, i32, vp, vp, vp, vp, i32, ll, vp, vp]),
     "vct_colsum_workspace_floats": (ll, [i32, i32]),
     "vct_colsum": (i32, [vp, i32, ll, i32, i32, vp, vp, vp, vp]),
     "vct_adam": (i32, [vp, vp, i32, vp, vp, vp, ll, vp, f32, vp]),

@@ -329,6 +329,53 @@ class CaptionTrainer:
             done_comm.record(comm)
             main.wait_event(done_comm)
 
+    # ---- input prefetch ---------------------------------------------------------------------------------
+    def prefetch(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: torch.Tensor) -> None:
+        """Start the host -> device copy of the NEXT batch on a copy stream while the current step is still running (the
+        reference's loop copies inside the step, train.py:120-121: ``.to(device)`` per modality + a tokenizer pass).  The
+        next ``step()`` called with the same three tensors (or ``step_prefetched()``) consumes the staged copy with a
+        device-to-device move instead of crossing PCIe on the critical path.  Pinned host tensors make the copy truly
+        asynchronous."""
+        eng = self.engine
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=eng.device)
+            self._staged = None
+        B, T, Din = feats.shape
+        key = (B, T, Din, ids.shape[1], vid_pad is not None)
+        bufs = getattr(self, "_stage_bufs", {})
+        if key not in bufs:
+            bufs[key] = (torch.empty((B, T, Din), dtype=torch.float32, device=eng.device),
+                         torch.empty((B, T), dtype=torch.bool, device=eng.device) if vid_pad is not None else None,
+                         torch.empty(tuple(ids.shape), dtype=torch.int64, device=eng.device), torch.cuda.Event())
+            self._stage_bufs = bufs
+        f, v, i, ev = bufs[key]
+        cs = self._copy_stream
+        free = getattr(self, "_stage_free", None)
+        if free is not None:
+            cs.wait_event(free)          # the previous consumer (a device-to-device move at the START of a step) is done;
+                                         # waiting for the whole stream would push this copy behind the running step
+        with torch.cuda.stream(cs):
+            f.copy_(feats, non_blocking=True)
+            if v is not None:
+                v.copy_(vid_pad, non_blocking=True)
+            i.copy_(ids, non_blocking=True)
+            ev.record(cs)
+        self._staged = (feats, vid_pad, ids, f, v, i, ev)
+
+    def step_prefetched(self) -> torch.Tensor:
+        if getattr(self, "_staged", None) is None:
+            raise RuntimeError("step_prefetched() without a preceding prefetch()")
+        feats, vid_pad, ids = self._staged[:3]
+        return self.step(feats, vid_pad, ids)
+
+    def _take_staged(self, feats, vid_pad, ids):
+        st = getattr(self, "_staged", None)
+        if st is None or st[0] is not feats or st[1] is not vid_pad or st[2] is not ids:
+            return feats, vid_pad, ids
+        self._staged = None
+        torch.cuda.current_stream(self.engine.device).wait_event(st[6])
+        return st[3], st[4], st[5]
+
     def step(self, feats: torch.Tensor, vid_pad: Optional[torch.Tensor], ids: torch.Tensor) -> torch.Tensor:
         """feats fp32 [B,T,Din], vid_pad bool [B,T] | None, ids int64 [B,S+1] (host -- ideally pinned -- or
         device tensors).  Returns the step's loss as a device scalar (no host sync).
@@ -343,7 +390,13 @@ class CaptionTrainer:
         ws = eng.workspace(B, T, S, True)
         eng.check_arena()
         eng.refresh_shadow()               # no-op unless the masters were edited outside vct_adam
+        staged = getattr(self, "_staged", None) is not None
+        feats, vid_pad, ids = self._take_staged(feats, vid_pad, ids)
         eng.stage_inputs(ws, feats, vid_pad, ids)
+        if staged:
+            if getattr(self, "_stage_free", None) is None:
+                self._stage_free = torch.cuda.Event()
+            self._stage_free.record(torch.cuda.current_stream(eng.device))
         if self.world == 1 and self.fuse_adam and os.environ.get("VCT_FORCE_SEGMENTED") == "1":
             # test hook: the N > 1 execution scheme (forward graph + backward graph segments + eager optimizer lane) on one GPU
             self._graphed((B, T, S, "forward"), lambda: self._forward(ws), ws=ws)
