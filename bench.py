@@ -623,6 +623,13 @@ def main():
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     note("e2e done")
     clocks = sampler.stop() if rank == 0 else None
+    comm = "single GPU"
+    if world > 1 and trainer is not None:
+        comm = "nccl"
+        if getattr(trainer, "peer", None) is not None:
+            comm = "peer-memory kernels (NVLink, vct_peer_allreduce_bf16 / vct_peer_allgather), one CUDA graph per step"
+            if trainer.peer.status() != 0:                       # a cross-GPU barrier timed out: the numbers are garbage
+                raise SystemExit(f"[bench rank {rank}] peer-memory exchange reported a barrier time-out")
 
     # ---- rooflines (rank 0): per-launch CUDA-event times of one eager pass + every distinct call alone in a graph ------
     rooflines, attn_roof, breakdown, phase_ms, roofline = None, None, None, None, None
@@ -678,7 +685,7 @@ def main():
                 "data": "synthetic",
                 "config": {"workload": cfg["name"], "name": args.config, "global_batch": B * world, "per_gpu_batch": B,
                            "parallelism": f"dp{world}", "gemm": {0: "simt", 1: "tcgen05", 2: "tcgen05 split-bf16 x3", 3: "tcgen05 split-bf16 x6"}[eng.gemm_impl],
-                           "cuda_graph": not args.no_graph,
+                           "cuda_graph": not args.no_graph, "gradient_exchange": comm,
                            "l2": "no explicit flush: one step streams ~2.5 GB of weights/moments/activations, 20x the 126 MB L2"},
                 "e2e": {"value": B * world * args.steps / float(e2e_s.item()), "unit": "captions/s",
                         "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},

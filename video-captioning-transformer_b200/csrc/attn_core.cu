@@ -357,21 +357,20 @@ attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
                    const unsigned char* __restrict__ key_pad, float* __restrict__ probs, Dims D) {
     pdl_launch_dependents();
     pdl_wait();
+    __shared__ __align__(16) float qs[kDecWarps][DHP];            // the warp's query row (read as broadcast float4)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int bh = blockIdx.x * kDecWarps + warp;
     if (bh >= D.B * D.H) return;
     const int b = bh / D.H, h = bh % D.H;
     const int dh = D.dh, Lk = D.Lk;
-    // the query row in registers (every lane holds all of it)
-    float qr[DHP];
     {
         const T* qrow = q + (long long)b * D.q_bs + h * dh;
-#pragma unroll
-        for (int c4 = 0; c4 < DHP / 4; ++c4) {
-            const float4 t = 4 * c4 < dh ? ld4(qrow + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
-            qr[4 * c4] = t.x; qr[4 * c4 + 1] = t.y; qr[4 * c4 + 2] = t.z; qr[4 * c4 + 3] = t.w;
+        for (int c = 4 * lane; c < DHP; c += 128) {
+            const float4 t = c < dh ? ld4(qrow + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+            *reinterpret_cast<float4*>(&qs[warp][c]) = t;
         }
     }
+    __syncwarp();
     const unsigned char* pad_row = key_pad ? key_pad + (long long)b * Lk : nullptr;
     float s[2];
 #pragma unroll
@@ -382,13 +381,14 @@ attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
             const T* krow = k + (long long)b * D.k_bs + (long long)j * D.k_ld + h * dh;
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
-            for (int c4 = 0; c4 < DHP / 4; ++c4) {
-                if (4 * c4 < dh) {
-                    const float4 kv = ld4(krow + 4 * c4);
-                    a0 = fmaf(qr[4 * c4], kv.x, a0);
-                    a1 = fmaf(qr[4 * c4 + 1], kv.y, a1);
-                    a2 = fmaf(qr[4 * c4 + 2], kv.z, a2);
-                    a3 = fmaf(qr[4 * c4 + 3], kv.w, a3);
+            for (int c8 = 0; c8 < DHP / 8; ++c8) {
+                if (8 * c8 < dh) {                               // dh % 8 == 0 on this path (checked by the launcher)
+                    float kv[8];
+                    ld8(krow + 8 * c8, kv);
+                    const float4 q0 = *reinterpret_cast<const float4*>(&qs[warp][8 * c8]);
+                    const float4 q1 = *reinterpret_cast<const float4*>(&qs[warp][8 * c8 + 4]);
+                    a0 = fmaf(q0.x, kv[0], a0); a1 = fmaf(q0.y, kv[1], a1); a2 = fmaf(q0.z, kv[2], a2); a3 = fmaf(q0.w, kv[3], a3);
+                    a0 = fmaf(q1.x, kv[4], a0); a1 = fmaf(q1.y, kv[5], a1); a2 = fmaf(q1.z, kv[6], a2); a3 = fmaf(q1.w, kv[7], a3);
                 }
             }
             s[t] = ((a0 + a1) + (a2 + a3)) * D.scale;
@@ -405,18 +405,17 @@ attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __
         if (lane < Lk) pr[lane] = p0;
         if (lane + 32 < Lk) pr[lane + 32] = p1;
     }
-    // o[c] = sum_j p_j V[j][c]; lane owns columns 4 lane .. 4 lane + 3
+    // o[c] = sum_j p_j V[j][c]; lane owns columns 4 lane .. 4 lane + 3; four V rows in flight per pass
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     const bool colok = 4 * lane < dh;
     const T* vbase = v + (long long)b * D.v_bs + h * dh + 4 * lane;
-    // eight V rows in flight per pass (a one-row-per-iteration loop is a chain of L2 latencies)
-    for (int j0 = 0; j0 < Lk; j0 += 8) {
-        float4 vv[8];
+    for (int j0 = 0; j0 < Lk; j0 += 4) {
+        float4 vv[4];
 #pragma unroll
-        for (int u = 0; u < 8; ++u)
+        for (int u = 0; u < 4; ++u)
             vv[u] = (colok && j0 + u < Lk) ? ld4(vbase + (long long)(j0 + u) * D.v_ld) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
+        for (int u = 0; u < 4; ++u) {
             const int j = j0 + u;
             const float pj = __shfl_sync(0xffffffffu, j < 32 ? p0 : p1, j & 31);
             acc.x = fmaf(pj, vv[u].x, acc.x); acc.y = fmaf(pj, vv[u].y, acc.y);
@@ -442,7 +441,7 @@ int dispatch(const vct_attn_args* a, cudaStream_t st, bool bwd) {
     if (!bwd && dec_on && a->Lq == 1 && !(a->drop_p > 0.f)) {
         const bool al = ((reinterpret_cast<uintptr_t>(a->q) | reinterpret_cast<uintptr_t>(a->k) | reinterpret_cast<uintptr_t>(a->v) |
                           reinterpret_cast<uintptr_t>(a->o)) & 15) == 0 && (a->q_bs % 4 == 0) && (a->k_bs % 4 == 0) && (a->v_bs % 4 == 0) &&
-                        (a->o_bs % 4 == 0) && a->dh % 4 == 0;
+                        (a->o_bs % 8 == 0) && a->dh % 8 == 0 && a->q_bs % 8 == 0 && a->k_bs % 8 == 0 && a->k_ld % 8 == 0;
         if (al) {
             if (dh <= 32) return launch_decode<T, 32>(a, st);
             if (dh <= 64) return launch_decode<T, 64>(a, st);
