@@ -253,8 +253,8 @@ class CaptionEngine:
             self.launches += 1
             self._shadow_version = ver
 
-    def check_arena(self) -> None:
-        if not self.arena.is_current():
+    def check_arena(self, quick: bool = False) -> None:
+        if not self.arena.is_current(quick):
             raise RuntimeError("model parameters were re-allocated after the vct engine was built "
                                "(.to()/.half()?); rebuild the engine (model.reset_engine())")
 
