@@ -9,7 +9,8 @@ snapshot; ``/root/reference`` does not exist there).
    The reference is a script collection without setup.py / pyproject.toml, so pip answers "Directory is not
    installable" (recorded in baseline/_ref/INSTALL.txt and DESIGN.md).
 2. Fallback = what an install of a pure-Python project amounts to: its first-party sources (model/, utils.py, train.py,
-   eval.py, predict_video.py, dataloader.py, configs/) are copied byte for byte.  submodules/ (213 MB of offline feature
+   eval.py, predict_video.py, dataloader.py, configs/) are copied byte for byte, plus the *.py files of
+   submodules/pycocoevalcap (eval.py imports them at module level).  The rest of submodules/ (340 MB of offline feature
    extractors and Java metric jars, none of it on the hot path) stays behind.
 
 Nothing under baseline/_ref is tracked by git and nothing in the product imports it: it is the reference arm of bench.py
@@ -52,6 +53,15 @@ def main():
                 shutil.copytree(s, d, ignore=shutil.ignore_patterns("__pycache__", "*.pyc"))
             elif os.path.isfile(s):
                 shutil.copy2(s, d)
+        # the metric package eval.py imports at module level (train.py:8 -> eval.py:11-15): python files only -- the Java
+        # jars / models next to them (130 MB) are only needed to SCORE captions, which stays with the reference's scripts
+        coco_src = os.path.join(SRC, "submodules", "pycocoevalcap")
+        if os.path.isdir(coco_src):
+            def only_py(d, names):
+                return [n for n in names if not (os.path.isdir(os.path.join(d, n)) or n.endswith(".py"))] + \
+                       [n for n in names if n in ("__pycache__", "example")]
+            shutil.copytree(coco_src, os.path.join(DST, "submodules", "pycocoevalcap"), ignore=only_py)
+            note.append("submodules/pycocoevalcap: *.py only (import-time dependency of eval.py)")
         for root, _dirs, files in sorted(os.walk(DST)):
             for f in sorted(files):
                 if f.endswith((".py", ".json")):

@@ -13,3 +13,4 @@ VCT_RUN_DIR=$PWD/gpurun_out/run timeout 600 python -m torch.distributed.run --nn
     tools/run_reference.py $PWD/baseline/_ref train.py -c $OUT/config.json --multi_gpu -ws $N > gpurun_out/reference_train_n$N.log 2>&1
 echo "rc=$?"
 grep -v "Warning\|warn\|^\s*$" gpurun_out/reference_train_n$N.log | tail -25 | cut -c1-220
+rm -rf $OUT/checkpoint $OUT/feats gpurun_out/run    # keep gpurun_out under the 64 MiB copy-back limit (the reference saves a 300 MB checkpoint)

@@ -54,7 +54,8 @@ def main():
             for k in ("save_dir", "log_dir"):
                 if k in cfg["train"] and not os.path.isabs(cfg["train"][k]):
                     cfg["train"][k] = os.path.join(run_dir, os.path.basename(cfg["train"][k]))
-                    os.makedirs(cfg["train"][k], exist_ok=True)
+                if k in cfg["train"]:
+                    os.makedirs(cfg["train"][k], exist_ok=True)      # the reference assumes ./checkpoint and ./log exist
         patched = os.path.join(run_dir, f"config_{os.getpid()}.json")
         with open(patched, "w") as f:
             json.dump(cfg, f)
