@@ -366,6 +366,8 @@ def family_of(name):
     base = name.split(":")[0]
     if base == "vct_gemm":
         return "vct_gemm:generator" if "generator" in name else "vct_gemm:layers"
+    if base == "vct_gemm_grouped":
+        return "vct_gemm:layers"
     if base == "vct_attn_bwd":
         return "vct_attn_bwd"
     return base
@@ -380,6 +382,13 @@ def algorithmic_work(name, a, eng):
         fl = 2.0 * g.M * g.N * g.K
         cb = 4.0 if g.c_dtype == 0 else 2.0
         by = es * (g.M * g.K + g.N * g.K) + cb * g.M * g.N + (2.0 * g.M * g.N if g.C2 else 0.0)
+        return by, fl
+    if base == "vct_gemm_grouped":                          # a[0] = ctypes array of vct_gemm_args, a[1] = count
+        by = fl = 0.0
+        for i in range(a[1]):
+            g = a[0][i]
+            fl += 2.0 * g.M * g.N * g.K
+            by += es * (g.M * g.K + g.N * g.K) + 4.0 * g.M * g.N
         return by, fl
     if base in ("vct_attn_enc_self_fwd", "vct_attn_dec_self_fwd"):
         o = a[0]._obj

@@ -103,6 +103,11 @@ typedef struct {
 } vct_gemm_args;
 
 int vct_gemm(const vct_gemm_args* args, vct_stream_t stream);
+/* `count` independent GEMMs (an array of vct_gemm_args).  A group of weight-gradient GEMMs -- tcgen05, bf16 operands stored
+ * [K, M] and [K, N] (a_trans = b_trans = 1), fp32 C, no epilogue extras, count <= 8: the dW = dY^T X products of one
+ * transformer layer (autograd of the nn.Linear calls listed above) -- runs as ONE persistent launch over the tiles of all
+ * problems; any other group is executed problem by problem with vct_gemm. */
+int vct_gemm_grouped(const vct_gemm_args* args, int count, vct_stream_t stream);
 long long vct_gemm_split_workspace_bytes(int M, int N, int K, int a_trans, int b_trans, int terms);
 /* The operand decomposition on its own: src fp32 [rows, cols] -> dst bf16 with the `terms` (3 or 6) pieces of side
  * 0 (A: h h m | h h m m h l) or 1 (B: h m h | h m h m l h) laid along the contraction axis (1: columns, dst [rows,

@@ -83,6 +83,38 @@ def test_gemm_simt_layouts(lib, dtype, a_trans, b_trans, M, N, K):
     torch.testing.assert_close(Cc.double(), want, rtol=1e-4, atol=1e-4 * math.sqrt(K))
 
 
+@pytest.mark.parametrize("shapes", [[(768, 2048, 1280), (2048, 768, 1280), (768, 768, 1280), (1536, 768, 832), (2304, 768, 1280)],
+                                    [(200, 136, 72)], [(768, 512, 832), (136, 264, 64), (128, 256, 200)]])
+def test_gemm_grouped_matches_individual_gemms(lib, shapes):
+    """vct_gemm_grouped (one persistent launch over the tiles of up to 8 weight-gradient GEMMs, bf16 operands stored
+    [K, M] / [K, N]) against fp32 matmul of the same bf16 operands, and a group the fast path does not cover."""
+    args = (L.GemmArgs * len(shapes))()
+    keep, want = [], []
+    for i, (M, N, K) in enumerate(shapes):
+        Ad, Bd, Ar, Br = make_operands(M, N, K, 1, 1, torch.bfloat16, seed=10 + i)
+        Cc = torch.full((M, N), float("nan"), dtype=torch.float32, device=DEV)
+        g = args[i]
+        g.M, g.N, g.K = M, N, K
+        g.A, g.a_dtype, g.lda, g.a_trans = Ad.data_ptr(), L.BF16, Ad.stride(0), 1
+        g.B, g.b_dtype, g.ldb, g.b_trans = Bd.data_ptr(), L.BF16, Bd.stride(0), 1
+        g.C, g.c_dtype, g.ldc = Cc.data_ptr(), L.F32, N
+        g.impl = L.GEMM_TCGEN05
+        keep.append((Ad, Bd, Cc))
+        want.append(Ar.double() @ Br.double().t())
+    for _ in range(2):
+        L.check(lib.vct_gemm_grouped(args, len(shapes), stream()), "vct_gemm_grouped")
+    torch.cuda.synchronize()
+    for (_, _, Cc), w, (M, N, K) in zip(keep, want, shapes):
+        torch.testing.assert_close(Cc.double(), w, rtol=1e-4, atol=1e-4 * math.sqrt(K))
+    # a group with a bias (not a weight-gradient shape) falls back to one vct_gemm per problem
+    bias = torch.randn(shapes[0][1], device=DEV)
+    args[0].bias = bias.data_ptr()
+    keep[0][2].fill_(float("nan"))
+    L.check(lib.vct_gemm_grouped(args, len(shapes), stream()), "vct_gemm_grouped (fallback)")
+    torch.cuda.synchronize()
+    torch.testing.assert_close(keep[0][2].double(), want[0] + bias.double(), rtol=1e-4, atol=1e-4 * math.sqrt(shapes[0][2]))
+
+
 def test_gemm_epilogue_bias_table_addend_and_bf16_out(lib):
     M, N, K = 130, 96, 64
     Ad, Bd, Ar, Br = make_operands(M, N, K, 0, 0, torch.float32, seed=1)

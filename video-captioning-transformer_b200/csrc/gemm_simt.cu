@@ -143,6 +143,7 @@ int gemm_simt(const vct_gemm_args* a, cudaStream_t st) {
 }
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st);   // gemm_tc.cu
 int gemm_split(const vct_gemm_args* a, int terms, cudaStream_t st);   // gemm_split.cu
+int gemm_grouped(const vct_gemm_args* args, int count, cudaStream_t st);   // gemm_tc.cu
 void gemm_tune(int bn, int splits, int low);                  // gemm_tc.cu
 void gemm_trace(long long* dev_buf);                          // gemm_tc.cu
 }  // namespace vct
@@ -180,4 +181,16 @@ extern "C" int vct_gemm(const vct_gemm_args* a, vct_stream_t stream) {
     if (a->impl == VCT_GEMM_TCGEN05_X3) return vct::gemm_split(a, 3, (cudaStream_t)stream);
     if (a->impl == VCT_GEMM_TCGEN05_X6) return vct::gemm_split(a, 6, (cudaStream_t)stream);
     return vct::gemm_simt(a, (cudaStream_t)stream);
+}
+
+// Several independent GEMMs in one call.  Weight-gradient groups (bf16 operands stored [K, M] / [K, N], fp32 output, no
+// epilogue extras, <= 8 problems, tcgen05) run as ONE persistent launch over the tiles of all problems; any other group is
+// issued problem by problem.
+extern "C" int vct_gemm_grouped(const vct_gemm_args* args, int count, vct_stream_t stream) {
+    VCT_REQUIRE(args != nullptr && count >= 1, "vct_gemm_grouped: empty group");
+    const int r = vct::gemm_grouped(args, count, (cudaStream_t)stream);
+    if (r <= 0) return r;
+    for (int i = 0; i < count; ++i)
+        if (int e = vct_gemm(&args[i], stream)) return e;
+    return 0;
 }

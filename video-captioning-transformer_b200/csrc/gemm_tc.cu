@@ -409,6 +409,196 @@ gemm_tc_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Grouped persistent GEMM: up to kMaxGroup independent problems C_g[M_g, N_g] = A_g^T-stored x B_g^T-stored (both operands
+// MN-major: the weight-gradient GEMMs dW = dY^T X of one transformer layer) in ONE launch.  The 128 x 256 tiles of all
+// problems form one list that the persistent CTAs walk round-robin, with the same warp roles, operand ring and
+// double-buffered TMEM accumulator as gemm_tc_persistent_kernel.  A layer's 5-7 weight gradients were 5-7 launches of
+// 18-54 CTAs each (6-9 us apiece, mostly fixed cost); together they are ~240 tiles = 1.6 waves of one launch.
+// ---------------------------------------------------------------------------------------------------
+constexpr int kMaxGroup = 8;
+struct GroupProblem {
+    int M, N, K, tiles_n, tile_start, vec_ok;
+    float* C;
+    long long ldc;
+};
+struct GroupArgs {
+    int count, total_tiles;
+    GroupProblem p[kMaxGroup];
+    CUtensorMap tmA[kMaxGroup];
+    CUtensorMap tmB[kMaxGroup];
+};
+
+__device__ __forceinline__ int group_of_tile(const GroupArgs& g, int tile) {
+    int q = 0;
+#pragma unroll
+    for (int i = 1; i < kMaxGroup; ++i)
+        if (i < g.count && tile >= g.p[i].tile_start) q = i;
+    return q;
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tc_grouped_kernel(const __grid_constant__ GroupArgs g) {
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    const uint32_t stage = smem_u32(smem + P_STAGES * kPStage);   // epilogue staging, shared-space address
+    __shared__ __align__(8) unsigned long long full_bar[P_STAGES];
+    __shared__ __align__(8) unsigned long long empty_bar[P_STAGES];
+    __shared__ __align__(8) unsigned long long tmem_full_bar[2];
+    __shared__ __align__(8) unsigned long long tmem_empty_bar[2];
+    __shared__ uint32_t tmem_base_slot;
+
+    pdl_launch_dependents();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_tiles = g.total_tiles;
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < g.count; ++i) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA[i]) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB[i]) : "memory");
+        }
+        for (int s = 0; s < P_STAGES; ++s) {
+            mbar_init(smem_u32(&full_bar[s]), 2);
+            mbar_init(smem_u32(&empty_bar[s]), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(smem_u32(&tmem_full_bar[a]), 1);
+            mbar_init(smem_u32(&tmem_empty_bar[a]), 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_slot)),
+                     "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = tmem_base_slot;
+    pdl_wait();
+
+    const uint32_t smem0 = smem_u32(smem);
+    const uint32_t full0 = smem_u32(&full_bar[0]), empty0 = smem_u32(&empty_bar[0]);
+    if (warp == 0 || warp == 6) {
+        const bool is_a = warp == 0;                           // warp 0 loads the A tiles, warp 6 the B tiles
+        uint32_t s = 0, ph = 1u;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            const int q = group_of_tile(g, tile);
+            const GroupProblem& pr = g.p[q];
+            const int local = tile - pr.tile_start;
+            const int m0 = (local / pr.tiles_n) * BLOCK_M, n0 = (local % pr.tiles_n) * P_BN;
+            const int num_kb = (pr.K + BLOCK_K - 1) / BLOCK_K;
+            const CUtensorMap* tm = is_a ? &g.tmA[q] : &g.tmB[q];
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait_fast(empty0 + 8u * s, ph);
+                const uint32_t full = full0 + 8u * s;
+                const uint32_t sa = smem0 + s * kPStage, sb = sa + kABytes;
+                const int k0 = kb * BLOCK_K;
+                if (elect_one()) {
+                    if (is_a) {
+                        mbar_expect_tx(full, kABytes);
+#pragma unroll
+                        for (int c = 0; c < BLOCK_M / 64; ++c) tma_load_2d(sa + c * 8192, tm, m0 + c * 64, k0, full);
+                    } else {
+                        mbar_expect_tx(full, kPBBytes);
+#pragma unroll
+                        for (int c = 0; c < P_BN / 64; ++c) tma_load_2d(sb + c * 8192, tm, n0 + c * 64, k0, full);
+                    }
+                }
+                __syncwarp();
+                if (++s == P_STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(P_BN >> 3) << 17) |
+                               ((uint32_t)(BLOCK_M >> 4) << 24);
+        const uint64_t adesc0 = make_desc(smem0, 8192, 1024);
+        const uint64_t bdesc0 = make_desc(smem0 + kABytes, 8192, 1024);
+        uint32_t s = 0, ph = 0u, ti = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int q = group_of_tile(g, tile);
+            const int num_kb = (g.p[q].K + BLOCK_K - 1) / BLOCK_K;
+            const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+            mbar_wait_fast(smem_u32(&tmem_empty_bar[acc]), aph ^ 1u);     // epilogue has drained this accumulator
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t d_tmem = tmem_base + acc * (uint32_t)P_BN;
+            uint32_t accum = 0u;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait_fast(full0 + 8u * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint64_t adesc = adesc0 + (uint64_t)((s * kPStage) >> 4);
+                const uint64_t bdesc = bdesc0 + (uint64_t)((s * kPStage) >> 4);
+                if (elect_one()) {
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint64_t ak = adesc + (uint64_t)(2048u * k >> 4);
+                        const uint64_t bk = bdesc + (uint64_t)(2048u * k >> 4);
+                        umma_bf16(d_tmem, ak, bk, idesc, (accum | (uint32_t)k) != 0u ? 1u : 0u);
+                    }
+                    umma_commit(empty0 + 8u * s);
+                }
+                __syncwarp();
+                accum = 1u;
+                if (++s == P_STAGES) { s = 0; ph ^= 1u; }
+            }
+            if (elect_one()) umma_commit(smem_u32(&tmem_full_bar[acc]));
+            __syncwarp();
+        }
+    } else {
+        const int qd = warp & 3;
+        const int row = qd * 32 + lane;
+        const int t = threadIdx.x - 64;
+        const Rng rng = make_rng(nullptr, 0.f);
+        uint32_t ti = 0;
+        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++ti) {
+            const int q = group_of_tile(g, tile);
+            const GroupProblem& pr = g.p[q];
+            const int local = tile - pr.tile_start;
+            const int m0 = (local / pr.tiles_n) * BLOCK_M, n0 = (local % pr.tiles_n) * P_BN;
+            Epilogue epi;
+            epi.M = pr.M; epi.N = pr.N;
+            epi.C = pr.C; epi.c_dtype = VCT_F32; epi.ldc = pr.ldc;
+            epi.C2 = nullptr; epi.c2_dtype = VCT_F32; epi.ldc2 = 0;
+            epi.bias = nullptr; epi.row_table = nullptr; epi.row_period = 0;
+            epi.addend = nullptr; epi.ld_addend = 0; epi.act = VCT_ACT_NONE;
+            epi.aux = nullptr; epi.aux_dtype = VCT_F32; epi.ld_aux = 0;
+            epi.drop_p = 0.f; epi.rng_state = nullptr; epi.site = 0u;
+            epi.vec_ok = pr.vec_ok; epi.trace = nullptr;
+            const uint32_t acc = ti & 1u, aph = (ti >> 1) & 1u;
+            mbar_wait(smem_u32(&tmem_full_bar[acc]), aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll 1
+            for (int ch = 0; ch < P_BN / P_CH; ++ch) {
+#pragma unroll
+                for (int c = 0; c < P_CH / 32; ++c) {
+                    uint32_t r[32];
+                    const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + acc * (uint32_t)P_BN + (uint32_t)(ch * P_CH + c * 32);
+                    tmem_ld16(taddr, r);
+                    tmem_ld16(taddr + 16, r + 16);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    const uint32_t dst = stage + (uint32_t)(row * P_RS + c * 32) * 4u;
+#pragma unroll
+                    for (int gg = 0; gg < 8; ++gg) sts128(dst + 16u * gg, r[4 * gg], r[4 * gg + 1], r[4 * gg + 2], r[4 * gg + 3]);
+                }
+                if (ch == P_BN / P_CH - 1) {
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tmem_empty_bar[acc])) : "memory");
+                }
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                epilogue_tile_plain<P_CH, 128>(epi, rng, stage, P_RS, m0, n0 + ch * P_CH, t);
+                asm volatile("bar.sync 1, 128;" ::: "memory");       // staging buffer is reused by the next chunk
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
 // split-K second pass: sum the partial tiles in a fixed order and apply the fused epilogue
 template <int ACT>
 __global__ void __launch_bounds__(256)
@@ -625,6 +815,46 @@ int get_tensor_map_3d(const void* ptr, const unsigned long long dims[3], const u
     if (cache.size() > 4096) cache.clear();
     cache[key] = *out;
     return 0;
+}
+
+// vct_gemm_grouped: every problem must be a bf16 x bf16 -> fp32 GEMM with both operands MN-major (a_trans = b_trans = 1), no
+// epilogue extras.  Returns > 0 when the group is not of that shape (the caller issues the GEMMs one by one).
+int gemm_grouped(const vct_gemm_args* args, int count, cudaStream_t st) {
+    if (count < 1 || count > kMaxGroup) return 1;
+    static const bool on = [] { const char* e = getenv("VCT_GEMM_GROUPED"); return e == nullptr || e[0] != '0'; }();
+    if (!on) return 1;
+    GroupArgs g;
+    memset(&g, 0, sizeof(g));
+    g.count = count;
+    int tiles = 0;
+    for (int i = 0; i < count; ++i) {
+        const vct_gemm_args* a = &args[i];
+        if (a->impl != VCT_GEMM_TCGEN05 || a->a_dtype != VCT_BF16 || a->b_dtype != VCT_BF16 || !a->a_trans || !a->b_trans ||
+            a->c_dtype != VCT_F32 || a->C2 || a->bias || a->row_table || a->addend || a->act != VCT_ACT_NONE)
+            return 1;
+        if (a->lda % 8 || a->ldb % 8 || (reinterpret_cast<uintptr_t>(a->A) & 15) || (reinterpret_cast<uintptr_t>(a->B) & 15) ||
+            (reinterpret_cast<uintptr_t>(a->C) & 15))
+            return 1;
+        GroupProblem& p = g.p[i];
+        p.M = a->M; p.N = a->N; p.K = a->K;
+        p.tiles_n = (a->N + P_BN - 1) / P_BN;
+        p.tile_start = tiles;
+        tiles += ((a->M + BLOCK_M - 1) / BLOCK_M) * p.tiles_n;
+        p.C = reinterpret_cast<float*>(a->C);
+        p.ldc = a->ldc;
+        p.vec_ok = (a->ldc % 4 == 0) ? 1 : 0;
+        if (int e = get_tensor_map(a->A, a->M, a->K, a->lda, 64, BLOCK_K, &g.tmA[i])) return e;
+        if (int e = get_tensor_map(a->B, a->N, a->K, a->ldb, 64, BLOCK_K, &g.tmB[i])) return e;
+    }
+    g.total_tiles = tiles;
+    static bool once = false;
+    if (!once) {
+        VCT_CUDA(cudaFuncSetAttribute(gemm_tc_grouped_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPSmem));
+        once = true;
+    }
+    const int grid = tiles < kNumSMs ? tiles : kNumSMs;
+    vct::launch(gemm_tc_grouped_kernel, dim3(grid), dim3(kThreads), kPSmem, st, g);
+    return check_launch("vct_gemm_grouped");
 }
 
 int gemm_tcgen05(const vct_gemm_args* a, cudaStream_t st) {

@@ -183,6 +183,8 @@ class CaptionEngine:
         self.emb_stamp = torch.zeros(max(1, int(self.dims.V)), dtype=torch.int32, device=device)
         self.side_streams = [torch.cuda.Stream(device=device) for _ in range(3)] \
             if os.environ.get("VCT_SIDE_STREAM", "1") != "0" else None
+        # one grouped persistent launch per layer for the weight-gradient GEMMs (csrc/gemm_tc.cu gemm_tc_grouped_kernel)
+        self.group_wgrads = self.gemm_impl == L.GEMM_TCGEN05 and os.environ.get("VCT_GROUP_WGRADS", "1") != "0"
         self.peer = None             # vct.peer.PeerComm once the data-parallel trainer has attached one (attach_peer)
         self._tempo: Dict[int, torch.Tensor] = {}
         self._ws: Dict[Tuple, SimpleNamespace] = {}
@@ -451,7 +453,9 @@ class CaptionEngine:
     # ------------------------------------------------------------------------------------------
     def _gemm(self, plan: Plan, tag: str, M, N, K, A, lda, a_trans, B, ldb, b_trans, Cp, c_dtype, ldc, *, bias=None,
               C2=None, c2_dtype=F32, ldc2=0, row_table=None, row_period=0, addend=None, ld_addend=0, act=L.ACT_NONE,
-              aux=None, ld_aux=0, drop_p=0.0, site=0, in_dtype=None):
+              aux=None, ld_aux=0, drop_p=0.0, site=0, in_dtype=None, defer=False):
+        """defer: a weight-gradient GEMM that only has to be finished by the end of its layer's backward -- collected
+        and issued by _flush_group as ONE grouped persistent launch (bf16 tcgen05 engines; issued at once otherwise)."""
         g = L.GemmArgs()
         g.M, g.N, g.K = M, N, K
         dt = self.cdt if in_dtype is None else in_dtype
@@ -473,7 +477,25 @@ class CaptionEngine:
         if self.split_terms:
             g.split_ws, g.split_ws_bytes = self._split_ws(ws, 1 if plan.lane else 0)
         plan.keep.append(g)
+        if defer and self.group_wgrads:
+            plan.__dict__.setdefault("_group", []).append((tag, g))
+            return
         plan.add("vct_gemm:" + tag, self.lib.vct_gemm, C.byref(g))
+
+    def _flush_group(self, plan: Plan, tag: str):
+        """Issue the deferred weight-gradient GEMMs of the layer just finished as one vct_gemm_grouped call (side lane)."""
+        group = plan.__dict__.get("_group") or []
+        if not group:
+            return
+        plan._group = []
+        for i in range(0, len(group), 8):
+            chunk = group[i:i + 8]
+            arr = (L.GemmArgs * len(chunk))()
+            for k, (_t, g) in enumerate(chunk):
+                C.memmove(C.byref(arr, k * C.sizeof(L.GemmArgs)), C.byref(g), C.sizeof(L.GemmArgs))
+            plan.keep.append(arr)
+            with self._side(plan):
+                plan.add(f"vct_gemm_grouped:{tag}" + (f".{i // 8}" if len(group) > 8 else ""), self.lib.vct_gemm_grouped, arr, len(chunk))
 
     def _split_ws(self, ws, lane: int):
         """(pointer, bytes) of the lane's operand-split scratch (precision bf16x3 / bf16x6)."""
@@ -913,13 +935,13 @@ class CaptionEngine:
                          self._g(pre + "linear2.bias"), Rd, pd, _dec_site(l, 5), ws)
             with side(p):
                 self._gemm(p, f"dec{l}.linear2.wgrad", d, D.F_dec, Rd, g_r3, d, 1, e.h.data_ptr(), D.F_dec, 1,
-                           self._g(pre + "linear2.weight"), F32, D.F_dec)
+                           self._g(pre + "linear2.weight"), F32, D.F_dec, defer=True)
             self._gemm(p, f"dec{l}.linear2.dgrad", Rd, D.F_dec, d, g_r3, d, 0, self._w(pre + "linear2.weight"),
                        D.F_dec, 1, g_z, cd, D.F_dec, act=L.ACT_MUL_AUX, aux=e.z.data_ptr(), ld_aux=D.F_dec,
                        drop_p=pd, site=_dec_site(l, 4))
             with side(p):
                 self._gemm(p, f"dec{l}.linear1.wgrad", D.F_dec, d, Rd, g_z, D.F_dec, 1, e.x2_c.data_ptr(), d, 1,
-                           self._g(pre + "linear1.weight"), F32, d)
+                           self._g(pre + "linear1.weight"), F32, d, defer=True)
                 self._colsum(p, f"dec{l}.linear1.bias", g_z, D.F_dec, Rd, D.F_dec, self._g(pre + "linear1.bias"), ws)
             self._gemm(p, f"dec{l}.linear1.dgrad", Rd, d, D.F_dec, g_z, D.F_dec, 0, self._w(pre + "linear1.weight"),
                        d, 1, other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
@@ -930,7 +952,7 @@ class CaptionEngine:
                          self._g(pre + "multihead_attn.out_proj.bias"), Rd, pd, _dec_site(l, 3), ws)
             with side(p):
                 self._gemm(p, f"dec{l}.cross.out_proj.wgrad", d, d, Rd, g_r2, d, 1, e.ao2.data_ptr(), d, 1,
-                           self._g(pre + "multihead_attn.out_proj.weight"), F32, d)
+                           self._g(pre + "multihead_attn.out_proj.weight"), F32, d, defer=True)
             self._gemm(p, f"dec{l}.cross.out_proj.dgrad", Rd, d, d, g_r2, d, 0,
                        self._w(pre + "multihead_attn.out_proj.weight"), d, 1, g_o, cd, d)
             self._attn(p, f"dec{l}.cross", True, B=B, H=D.H_dec, Lq=S, Lk=M, q=e.q.data_ptr(), q_ld=d,
@@ -940,9 +962,9 @@ class CaptionEngine:
                        dbias=self._g(pre + "multihead_attn.in_proj_bias"), ws=ws)
             wname, bname = pre + "multihead_attn.in_proj_weight", pre + "multihead_attn.in_proj_bias"
             with side(p):
-                self._gemm(p, f"dec{l}.cross.q.wgrad", d, d, Rd, g_q, d, 1, e.x1_c.data_ptr(), d, 1, self._g(wname), F32, d)
+                self._gemm(p, f"dec{l}.cross.q.wgrad", d, d, Rd, g_q, d, 1, e.x1_c.data_ptr(), d, 1, self._g(wname), F32, d, defer=True)
                 self._gemm(p, f"dec{l}.cross.kv.wgrad", 2 * d, d, Re, g_kv, 2 * d, 1, ws.mem_c.data_ptr(), d, 1,
-                           self._g(wname, d * d), F32, d)
+                           self._g(wname, d * d), F32, d, defer=True)
             self._gemm(p, f"dec{l}.cross.q.dgrad", Rd, d, d, g_q, d, 0, self._w(wname), d, 1,
                        other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
             self._gemm(p, f"dec{l}.cross.kv.dgrad", Re, d, 2 * d, g_kv, 2 * d, 0, self._w(wname, d), d, 1,
@@ -955,7 +977,7 @@ class CaptionEngine:
                          self._g(pre + "self_attn.out_proj.bias"), Rd, pd, _dec_site(l, 1), ws)
             with side(p):
                 self._gemm(p, f"dec{l}.self.out_proj.wgrad", d, d, Rd, g_r1, d, 1, e.ao.data_ptr(), d, 1,
-                           self._g(pre + "self_attn.out_proj.weight"), F32, d)
+                           self._g(pre + "self_attn.out_proj.weight"), F32, d, defer=True)
             self._gemm(p, f"dec{l}.self.out_proj.dgrad", Rd, d, d, g_r1, d, 0,
                        self._w(pre + "self_attn.out_proj.weight"), d, 1, g_o, cd, d)
             qkv = e.qkv.data_ptr()
@@ -967,10 +989,11 @@ class CaptionEngine:
             wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
             with side(p):
                 self._gemm(p, f"dec{l}.self.in_proj.wgrad", 3 * d, d, Rd, gq, 3 * d, 1, xin_c.data_ptr(), d, 1,
-                           self._g(wname), F32, d)
+                           self._g(wname), F32, d, defer=True)
             self._gemm(p, f"dec{l}.self.in_proj.dgrad", Rd, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
                        addend=ws.g_s.data_ptr(), ld_addend=d)
             dx, other = other, dx           # dx = grad wrt the layer input
+            self._flush_group(p, f"dec{l}.wgrads")
             self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm3.bias")
         # ---- embedding ---------------------------------------------------------------------------
         emb, e_lo, e_hi = self._emb_range()
@@ -1062,13 +1085,13 @@ class CaptionEngine:
                          self._g(pre + "linear2.bias"), Re, pd, _enc_site(l, 3), ws)
             with side(p):
                 self._gemm(p, f"enc{l}.linear2.wgrad", d, D.F_enc, Re, g_r2, d, 1, e.h.data_ptr(), D.F_enc, 1,
-                           self._g(pre + "linear2.weight"), F32, D.F_enc)
+                           self._g(pre + "linear2.weight"), F32, D.F_enc, defer=True)
             self._gemm(p, f"enc{l}.linear2.dgrad", Re, D.F_enc, d, g_r2, d, 0, self._w(pre + "linear2.weight"),
                        D.F_enc, 1, g_z, cd, D.F_enc, act=L.ACT_MUL_AUX, aux=e.z.data_ptr(), ld_aux=D.F_enc,
                        drop_p=pd, site=_enc_site(l, 2))
             with side(p):
                 self._gemm(p, f"enc{l}.linear1.wgrad", D.F_enc, d, Re, g_z, D.F_enc, 1, e.x1_c.data_ptr(), d, 1,
-                           self._g(pre + "linear1.weight"), F32, d)
+                           self._g(pre + "linear1.weight"), F32, d, defer=True)
                 self._colsum(p, f"enc{l}.linear1.bias", g_z, D.F_enc, Re, D.F_enc, self._g(pre + "linear1.bias"), ws)
             self._gemm(p, f"enc{l}.linear1.dgrad", Re, d, D.F_enc, g_z, D.F_enc, 0, self._w(pre + "linear1.weight"),
                        d, 1, other.data_ptr(), F32, d, addend=ws.g_s.data_ptr(), ld_addend=d)
@@ -1078,7 +1101,7 @@ class CaptionEngine:
                          self._g(pre + "self_attn.out_proj.bias"), Re, pd, _enc_site(l, 1), ws)
             with side(p):
                 self._gemm(p, f"enc{l}.out_proj.wgrad", d, d, Re, g_r1, d, 1, e.ao.data_ptr(), d, 1,
-                           self._g(pre + "self_attn.out_proj.weight"), F32, d)
+                           self._g(pre + "self_attn.out_proj.weight"), F32, d, defer=True)
             self._gemm(p, f"enc{l}.out_proj.dgrad", Re, d, d, g_r1, d, 0, self._w(pre + "self_attn.out_proj.weight"),
                        d, 1, g_o, cd, d)
             qkv = e.qkv.data_ptr()
@@ -1089,23 +1112,29 @@ class CaptionEngine:
                        dbias=self._g(pre + "self_attn.in_proj_bias"), ws=ws)
             wname, bname = pre + "self_attn.in_proj_weight", pre + "self_attn.in_proj_bias"
             with side(p):
-                self._gemm(p, f"enc{l}.in_proj.wgrad", 3 * d, d, Re, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d)
+                self._gemm(p, f"enc{l}.in_proj.wgrad", 3 * d, d, Re, gq, 3 * d, 1, xin_c.data_ptr(), d, 1, self._g(wname), F32, d, defer=True)
             last = l == 0
             self._gemm(p, f"enc{l}.in_proj.dgrad", Re, d, 3 * d, gq, 3 * d, 0, self._w(wname), d, 1, other.data_ptr(), F32, d,
                        addend=ws.g_s.data_ptr(), ld_addend=d,
                        C2=ws.g_x0_c.data_ptr() if (last and cd == BF16) else None, c2_dtype=cd, ldc2=d)
             dx, other = other, dx
-            if not merge:
-                self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm2.bias")
-            elif l > 0:
-                self._adam_slice(p, pre + "self_attn.in_proj_weight",
-                                 "video_encoder.transformer_encoder.norm.bias" if l == D.L_enc - 1 else pre + "norm2.bias")
+            if l > 0:                                        # (layer 0's weight gradients are grouped with unify's, below)
+                self._flush_group(p, f"enc{l}.wgrads")
+                if not merge:
+                    self._adam_slice(p, pre + "self_attn.in_proj_weight", pre + "norm2.bias")
+                else:
+                    self._adam_slice(p, pre + "self_attn.in_proj_weight",
+                                     "video_encoder.transformer_encoder.norm.bias" if l == D.L_enc - 1 else pre + "norm2.bias")
         g_x0_c = ws.g_x0_c.data_ptr() if cd == BF16 else dx.data_ptr()
         with side(p):
             self._gemm(p, "unify.wgrad", d, D.Din, Re, g_x0_c, d, 1, ws.a0.data_ptr(), D.Din, 1,
-                       self._g("video_encoder.unify.0.weight"), F32, D.Din)
+                       self._g("video_encoder.unify.0.weight"), F32, D.Din, defer=True)
             self._colsum(p, "unify.bias", g_x0_c, d, Re, d, self._g("video_encoder.unify.0.bias"), ws)
+        self._flush_group(p, "enc0.wgrads+unify")
         if not merge:
+            if D.L_enc > 0:
+                pre0 = "video_encoder.transformer_encoder.layers.0."
+                self._adam_slice(p, pre0 + "self_attn.in_proj_weight", pre0 + "norm2.bias")
             self._adam_slice(p, "video_encoder.unify.0.weight", "video_encoder.unify.0.bias")
         elif D.L_enc == 0:
             self._adam_slice(p, "video_encoder.unify.0.weight", "video_encoder.transformer_encoder.norm.bias")

@@ -78,6 +78,7 @@ SIGNATURES = {
     "vct_device_info": (i32, [C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]),
     "vct_step_tick": (i32, [vp, vp, vp]),
     "vct_gemm": (i32, [C.POINTER(GemmArgs), vp]),
+    "vct_gemm_grouped": (i32, [C.POINTER(GemmArgs), i32, vp]),
     "vct_gemm_split_workspace_bytes": (ll, [i32, i32, i32, i32, i32, i32]),
     "vct_split_bf16": (i32, [vp, ll, i32, i32, i32, i32, i32, vp, ll, vp]),
     "vct_gemm_tune": (i32, [i32, i32, i32]),
