@@ -342,7 +342,7 @@ int vct_argmax_append(const float* logits, long long ld_logits, int B, int V, lo
  *       writes the result into every region): identical results on all ranks.  n_elems % 8 == 0, offsets % 16 == 0.
  *   vct_peer_allgather: the range is [world][slot_bytes]; rank r has written slot r of its own region; afterwards every
  *       region holds every slot.  slot_bytes % 16 == 0.
- *   vct_comm_status: 0, or 1 after a barrier timed out (~4 s: a peer died or the ranks diverged); synchronises.
+ *   vct_comm_status: 0, or 1 after a barrier timed out (~20 s: a peer died or the ranks diverged); synchronises.
  *   vct_comm_connect_in_process: ranks that live in ONE process (tests): peer_bases[p] = vct_comm_base(handle of rank p). */
 int vct_comm_create(int rank, int world, long long bytes, int ctas, void** handle_out);
 void* vct_comm_base(void* handle);

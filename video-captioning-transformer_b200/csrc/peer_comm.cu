@@ -12,7 +12,7 @@
 // Synchronisation: CTA b of rank r only ever waits for CTA b of the other ranks (same grid size everywhere), through a
 // monotone counter per (channel, source rank, CTA) in the destination's flag array: barrier k is passed once every peer's
 // counter is >= k.  Counters live in device memory and advance by two per collective, so a captured graph can be
-// replayed forever.  A spin that lasts longer than ~4 s sets a status word and gives up (no hung GPU box).
+// replayed forever.  A spin that lasts longer than ~20 s sets a status word and gives up (no hung GPU box).
 #include "common.cuh"
 
 using namespace vct;
@@ -71,9 +71,9 @@ __device__ __forceinline__ void peer_barrier(const CommDev& c, int channel, unsi
         const unsigned int* mine = c.flags[c.rank] + ((size_t)channel * kMaxWorld + p) * kMaxCtas + b;
         const long long t0 = clock64();
         // (once a barrier has timed out every later one gives up after a short wait: the run is lost, do not hang the box)
-        const long long limit = *reinterpret_cast<volatile unsigned int*>(c.status) ? 2000000LL : 8000000000LL;
+        const long long limit = *reinterpret_cast<volatile unsigned int*>(c.status) ? 2000000LL : 40000000000LL;
         while ((int)(ld_acquire_sys(mine) - target) < 0) {
-            if (clock64() - t0 > limit) {                  // ~4 s at 1.9 GHz: a peer died or the ranks diverged
+            if (clock64() - t0 > limit) {                  // ~20 s at 1.9 GHz: a peer died or the ranks diverged
                 atomicExch(c.status, 1u);
                 break;
             }
