@@ -580,7 +580,7 @@ def main():
     else:
         from vct.trainer import CaptionTrainer
         model.train()
-        trainer = CaptionTrainer(model, lr=1e-4, betas=(0.9, 0.999), use_graph=not args.no_graph)
+        trainer = CaptionTrainer(model, lr=1e-4, betas=(0.9, 0.999), use_graph=not args.no_graph, uniform_shapes=True)
         eng = trainer.engine
 
         def step_dev():

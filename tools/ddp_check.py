@@ -33,7 +33,7 @@ def build():
 
 
 m = build()
-tr = CaptionTrainer(m, lr=1e-3, use_graph=True)
+tr = CaptionTrainer(m, lr=1e-3, use_graph=True, uniform_shapes=os.environ.get("UNIFORM", "1") == "1")
 sl = slice(rank * 8, (rank + 1) * 8)
 losses = []
 for _ in range(4):

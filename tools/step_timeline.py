@@ -26,7 +26,7 @@ torch.manual_seed(666)
 model = MMT4Caption(shipped_model_config(tok), device=dev).to(dev)
 model.vct_precision, model.vct_gemm = "bf16", None
 model.mode("caption"); model.train()
-tr = CaptionTrainer(model, lr=1e-4)
+tr = CaptionTrainer(model, lr=1e-4, uniform_shapes=True)
 x, vm, ids = synth_batch(args.batch, 12, 512, 21, seed=1234 + rank)
 x, vm, ids = x.to(dev), vm.to(dev), ids.to(dev)
 for _ in range(6):

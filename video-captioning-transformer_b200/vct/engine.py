@@ -365,7 +365,12 @@ class CaptionEngine:
             return "dense" if world > 1 else "local-unsplit"
         if world == 1:
             return "local"
-        ok = world * ws.B * ws.S <= self.PEER_MAX_TOKENS and self.dims.V <= 32768 and os.environ.get("VCT_SPARSE_EMB", "1") != "0"
+        # the sparse exchange moves [B*S, d] rows and [B, S+1] ids per rank: every rank must present the SAME (B, S) in a step.
+        # The trainer only enables it when its caller promises that (CaptionTrainer(uniform_shapes=True): synthetic batches,
+        # loaders that pad captions to a fixed length); otherwise -- ragged caption lengths differ from rank to rank -- the
+        # dense table gradient is exchanged, which is shape-independent like every other slice.
+        ok = world * ws.B * ws.S <= self.PEER_MAX_TOKENS and self.dims.V <= 32768 and os.environ.get("VCT_SPARSE_EMB", "1") != "0" \
+            and getattr(self, "uniform_shapes", False)
         if self.peer is not None and (ws.B * (ws.S + 1)) % 2:
             ok = False                                    # the peer all-gather moves 16-byte vectors: ids slots must be even
         return "sparse" if ok else "dense"

@@ -109,12 +109,18 @@ def all_reduce_flat(flat: torch.Tensor, buckets: List[Tuple[int, int]], group=No
 
 class CaptionTrainer:
     def __init__(self, model, lr: float = 1e-4, betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0,
-                 use_graph: bool = True, process_group=None, world_size: Optional[int] = None):
+                 use_graph: bool = True, process_group=None, world_size: Optional[int] = None, uniform_shapes: bool = False):
+        """uniform_shapes (data parallel only): the caller promises that every rank calls ``step`` with the same batch size
+        and the same caption length in a given step (synthetic batches; loaders that pad to a fixed length).  The
+        embedding-table gradient is then exchanged in its sparse form (<= B*S rows per rank instead of the dense [V, d]
+        table).  Without the promise -- ragged batches whose longest caption differs from rank to rank, as the reference's
+        loader produces them -- the dense gradient is exchanged, which needs no agreement on shapes."""
         import torch.distributed as dist
         self.model = model
         self.engine = model._engine()
         if model.f_type != "caption":
             raise ValueError("CaptionTrainer drives the caption task: call model.mode('caption') first")
+        self.engine.uniform_shapes = bool(uniform_shapes)
         self.engine.set_adam(lr, betas, eps, weight_decay)
         self.engine.refresh_shadow(force=True)
         # invariant of the native step: the embedding-table gradient is all-zero when a step starts (each step re-zeroes
