@@ -140,7 +140,12 @@ int vct_prep_frames(const float* feats, void* out, int out_dtype, int B, int T, 
  * probs: optional fp32 [B,H,Lq,Lk] post-softmax, pre-dropout probabilities (need_weights).
  * Replaces F.scaled_dot_product_attention / the softmax path of
  * torch/nn/functional.py multi_head_attention_forward incl. mask merge (:6607-6620) and
- * attention-probability dropout.  Limits: Lq, Lk <= 64, dh <= 128, dh % 4 == 0. */
+ * attention-probability dropout.  Limits: Lq, Lk <= 1024, dh <= 128, dh % 4 == 0.
+ * Lq, Lk <= 64 (every shipped config): the whole head lives in one CTA / one tcgen05 tile.  Longer sequences (the
+ * reference truncates neither captions nor frames, train.py / dataloader.py) run the tiled kernels: 16-row tiles,
+ * the other operand streamed in 32-row blocks; their backward needs the `row_stats` workspace and does not produce
+ * `dbias` (vct_colsum over dq | dk | dv does).  The dropout mask of probability (row r, key j) is element
+ * r * 64 + j of `site` for Lk <= 64 and element r * 8 * ceil(Lk / 8) + j otherwise (vct_dropout_mask). */
 typedef struct {
     int B, H, Lq, Lk, dh;
     int dtype;                          /* storage type of q, k, v, o and their gradients */
@@ -166,6 +171,9 @@ typedef struct {
      * dbias_partials: fp32 workspace [B, 3 * H * dh]; dbias_counters: H zero-initialised uint32 (self-resetting).
      * Deterministic (per-CTA partials, fixed-order final sum by the last CTA of each head). */
     float* dbias; float* dbias_partials; unsigned int* dbias_counters;
+    /* backward only, required when Lq > 64 or Lk > 64: fp32 workspace [B * H * Lq, 4], 16-byte aligned (row max,
+     * 1 / row sum and sum_j P dP of every probability row, handed from the query-tile to the key-tile kernel). */
+    float* row_stats;
 } vct_attn_args;
 
 int vct_attn_fwd(const vct_attn_args* args, vct_stream_t stream);

@@ -6,6 +6,7 @@ present on the GPU box):
 
 Writes
   tests/golden/tiny_a.npz, tiny_b.npz     tiny dims, every weight/input/output/gradient
+  tests/golden/long_a.npz   (``--long``) a tiny model on sequences longer than 64 rows (T = 70, 81 tokens)
   tests/golden/extra_anchors.json, extra_samples.npz   (``--extra``) round-2 anchors: the bench workload (B = 64),
                                            cfg 5 dims (6+6, T = 32), the eval fast path with padded frames and the cfg 3
                                            greedy decode (B = 256, max_len 30) -- see make_extra
@@ -300,6 +301,11 @@ def main():
     torch.backends.mha.set_fastpath_enabled(False)
     torch.set_num_threads(os.cpu_count())
     ref = ref_shims.import_reference_model()
+    if "--long" in sys.argv:
+        # sequences beyond the 64 rows one attention tile holds (memory 71 rows, 80 decoder positions, greedy to 82
+        # tokens): pins the tiled long-sequence kernels (csrc/attn_core.cu) to the reference, which has no length limit
+        make_tiny(ref, "long_a", Din=24, d=64, h=2, F=96, Le=1, Ld=2, V=211, T=70, S1=81, B=3, alpha=0.5, seed=37)
+        return
     if "--extra" in sys.argv:
         make_extra(ref, ref_shims.make_tokenizer_dir(os.path.join(ROOT, "gpurun_out", "_tok")))
         return

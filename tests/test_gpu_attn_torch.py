@@ -187,3 +187,95 @@ def test_attention_backward_vs_torch_autograd_fp32(lib, B, H, Lq, Lk, dh, causal
     close(dv, vf.grad, "dv")
     ref_b = torch.cat([qf.grad.reshape(-1, d).sum(0), kf.grad.reshape(-1, d).sum(0), vf.grad.reshape(-1, d).sum(0)])
     assert float((dbias - ref_b).norm() / ref_b.norm()) < 1.5e-2
+
+
+# ---- sequences longer than one tile (Lq or Lk > 64): the tiled kernels of csrc/attn_core.cu -------------------------
+def keep_mask_long(lib, rng, site, p, B, H, Lq, Lk):
+    """Long-path index space: probability row r owns ceil(Lk / 8) groups of 8 keys (include/vct.h, vct_attn_args)."""
+    if p <= 0.0:
+        return torch.ones(B, H, Lq, Lk, device=DEV)
+    w = (Lk + 7) // 8 * 8
+    n = B * H * Lq * w
+    m = torch.zeros(n, dtype=torch.uint8, device=DEV)
+    L.check(lib.vct_dropout_mask(m.data_ptr(), n, p, rng.data_ptr(), site, stream()))
+    return m.view(B, H, Lq, w)[..., :Lk].float() / (1.0 - p)
+
+
+LONG_CASES = [(2, 4, 70, 70, 96, 1, True), (2, 2, 100, 33, 64, 0, False), (1, 2, 20, 130, 96, 0, True),
+              (2, 2, 65, 65, 32, 1, True), (1, 1, 300, 300, 128, 1, False), (3, 2, 1, 200, 96, 0, False),
+              (1, 2, 257, 513, 64, 0, True), (2, 8, 81, 81, 96, 0, True)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("B,H,Lq,Lk,dh,causal,pad", LONG_CASES)
+@pytest.mark.parametrize("p", [0.0, 0.3])
+def test_long_sequence_attention_vs_torch_fp32(lib, dtype, B, H, Lq, Lk, dh, causal, pad, p):
+    """Forward (probabilities, output) and backward (dq, dk, dv) of the tiled kernels against fp32 PyTorch autograd on the
+    same inputs, with the exact dropout mask.  fp32 storage: |err| <= 5e-5 + 2e-4 |ref|; bf16 storage: the tolerances of
+    this file's header."""
+    g = torch.Generator().manual_seed(3 * B + 7 * Lq + Lk + dh + causal)
+    d = H * dh
+    q = torch.randn(B, Lq, H, dh, generator=g).to(DEV, dtype)
+    k = torch.randn(B, Lk, H, dh, generator=g).to(DEV, dtype)
+    v = torch.randn(B, Lk, H, dh, generator=g).to(DEV, dtype)
+    do = torch.randn(B, Lq, H, dh, generator=g).to(DEV, dtype)
+    key_pad = None
+    if pad:
+        key_pad = torch.zeros(B, Lk, dtype=torch.uint8)
+        key_pad[0, Lk - 5:] = 1                           # (position 0 is never padded, SURVEY Q8)
+        if B > 1:
+            key_pad[1, Lk // 2:] = 1
+        key_pad = key_pad.to(DEV)
+    rng = torch.tensor([123, 4], dtype=torch.int64, device=DEV)
+    site = 29
+    o = torch.full_like(q, float("nan"))
+    probs = torch.full((B, H, Lq, Lk), float("nan"), device=DEV)
+    dq, dk, dv = (torch.full_like(t, float("nan")) for t in (q, k, v))
+    stats = torch.empty(B * H * Lq, 4, device=DEV)
+    a = L.AttnArgs()
+    a.B, a.H, a.Lq, a.Lk, a.dh = B, H, Lq, Lk, dh
+    a.dtype = L.BF16 if dtype == torch.bfloat16 else L.F32
+    a.q, a.q_ld, a.k, a.k_ld, a.v, a.v_ld, a.o, a.o_ld = q.data_ptr(), d, k.data_ptr(), d, v.data_ptr(), d, o.data_ptr(), d
+    a.key_pad = key_pad.data_ptr() if key_pad is not None else None
+    a.causal, a.scale = causal, 1.0 / math.sqrt(dh)
+    a.drop_p, a.rng_state, a.site = p, rng.data_ptr(), site
+    a.probs = probs.data_ptr()
+    a.d_o, a.do_ld, a.dq, a.dq_ld, a.dk, a.dk_ld, a.dv, a.dv_ld = do.data_ptr(), d, dq.data_ptr(), d, dk.data_ptr(), d, dv.data_ptr(), d
+    a.row_stats = stats.data_ptr()
+    L.check(lib.vct_attn_fwd(C.byref(a), stream()), "fwd")
+    L.check(lib.vct_attn_bwd(C.byref(a), stream()), "bwd")
+    torch.cuda.synchronize()
+    qf, kf, vf = (t.float().requires_grad_(True) for t in (q, k, v))
+    keep = keep_mask_long(lib, rng, site, p, B, H, Lq, Lk)
+    if p > 0:
+        rate = float((keep > 0).float().mean())
+        assert abs(rate - (1 - p)) < 0.02, rate
+    pr, orf = torch_attention(qf, kf, vf, key_pad, causal, keep)
+    orf.backward(do.float())
+    torch.testing.assert_close(probs, pr.detach(), rtol=1e-4, atol=1e-5)
+    if dtype == torch.float32:
+        for got, want, what in ((o, orf.detach(), "o"), (dq, qf.grad, "dq"), (dk, kf.grad, "dk"), (dv, vf.grad, "dv")):
+            torch.testing.assert_close(got, want, rtol=2e-4, atol=5e-5, msg=lambda m, what=what: f"{what}: {m}")
+    else:
+        close(o, orf.detach(), "attention output")
+        close(dq, qf.grad, "dq")
+        close(dk, kf.grad, "dk")
+        close(dv, vf.grad, "dv")
+
+
+def test_long_sequence_backward_needs_its_workspace(lib):
+    """Loud failure instead of a wild write: the tiled backward refuses to run without row_stats, and does not pretend to
+    produce the in-projection bias gradient."""
+    B, H, L_, dh = 1, 2, 80, 32
+    d = H * dh
+    t = [torch.zeros(B, L_, H, dh, device=DEV) for _ in range(7)]
+    a = L.AttnArgs()
+    a.B, a.H, a.Lq, a.Lk, a.dh, a.dtype = B, H, L_, L_, dh, L.F32
+    a.q, a.q_ld, a.k, a.k_ld, a.v, a.v_ld = t[0].data_ptr(), d, t[1].data_ptr(), d, t[2].data_ptr(), d
+    a.scale = 1.0
+    a.d_o, a.do_ld, a.dq, a.dq_ld, a.dk, a.dk_ld, a.dv, a.dv_ld = t[3].data_ptr(), d, t[4].data_ptr(), d, t[5].data_ptr(), d, t[6].data_ptr(), d
+    assert lib.vct_attn_bwd(C.byref(a), stream()) != 0
+    assert b"row_stats" in lib.vct_last_error()
+    a.Lq = a.Lk = 1025
+    assert lib.vct_attn_fwd(C.byref(a), stream()) != 0
+    assert b"1024" in lib.vct_last_error()

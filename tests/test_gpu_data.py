@@ -92,22 +92,36 @@ def test_prefetched_steps_equal_direct_steps(tokenizer_dir):
     assert out[0] == out[1], out
 
 
-def test_too_long_sequences_fail_up_front_with_a_clear_error(tokenizer_dir):
-    """the attention kernels cover sequences up to 64 rows; anything longer must be rejected before the first
-    launch (not in the middle of an epoch) with a message that names the remedy."""
+def test_long_sequences_run_and_over_long_ones_fail_up_front(tokenizer_dir):
+    """the fused attention kernels cover sequences up to 64 rows.  Longer ones (the reference truncates neither
+    frames nor training captions) now run on the tiled kernels -- checked here at the shipped dims against the oracle --
+    and anything beyond their 1024-row limit is rejected before the first launch (not in the middle of an epoch) with a
+    message that names the remedy."""
+    from oracle import vct_oracle as O
     model = _model(tokenizer_dir, "bf16")
     model.train()
-    x = torch.randn(2, 70, 512, device=DEV)                       # 70 frames -> memory length 71
-    vm = torch.zeros(2, 70, dtype=torch.bool, device=DEV)
-    ids = torch.randint(1000, 30522, (2, 21), device=DEV)
+    sd = {k: v.detach().float().cpu().clone() for k, v in model.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(2, 70, 512, generator=g)                      # 70 frames -> memory length 71
+    vm = torch.zeros(2, 70, dtype=torch.bool)
+    vm[1, 50:] = True
+    ids = torch.randint(1000, 30522, (2, 80), generator=g)        # 79 decoder positions
+    ids[:, 0], ids[0, -1], ids[1, 40], ids[1, 41:] = 101, 102, 102, 0
+    loss = model([x.to(DEV)], [vm.to(DEV)], ids.to(DEV))
+    loss.backward()
+    _, _, oloss = O.caption_forward(sd, x, vm, ids, 8, 8, 0.5)
+    assert abs(float(loss) - float(oloss)) <= 5e-3 * float(oloss), (float(loss), float(oloss))
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in model.parameters() if p.requires_grad)
+    x = torch.randn(2, 1100, 512, device=DEV)                     # beyond the tiled kernels (and the reference's 512-row table)
+    vm = torch.zeros(2, 1100, dtype=torch.bool, device=DEV)
     with pytest.raises(ValueError, match="sequence too long"):
-        model([x], [vm], ids)
+        model([x], [vm], ids.to(DEV))
     x = torch.randn(2, 12, 512, device=DEV)
     vm = torch.zeros(2, 12, dtype=torch.bool, device=DEV)
-    ids = torch.randint(1000, 30522, (2, 80), device=DEV)         # 79 decoder positions
+    long_ids = torch.randint(1000, 30522, (2, 1100), device=DEV)
     with pytest.raises(ValueError, match="sequence too long"):
-        model([x], [vm], ids)
+        model([x], [vm], long_ids)
     model.eval()
     with pytest.raises(ValueError, match="sequence too long"):
-        model.greedy_decode([x], [vm], max_len=100)
+        model.greedy_decode([x], [vm], max_len=1100)
     assert len(model.greedy_decode([x], [vm], max_len=6)) == 2    # the engine is still usable afterwards

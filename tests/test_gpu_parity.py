@@ -42,7 +42,7 @@ def rel_l2(a, b):
 
 
 @pytest.mark.parametrize("precision,gemm", MODES)
-@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b", "long_a"])          # long_a: 71 memory rows, 80 decoder positions
 def test_tiny_forward_backward_matches_reference_golden(name, precision, gemm):
     cfg, enc, dec, ins, outs, grads = build_tiny(name, precision, gemm)
     enc.train(), dec.train()                      # dropout p = 0: train-mode plans, eval-mode numbers
@@ -92,7 +92,19 @@ def test_tiny_eval_loss_and_decode_word(name):
     torch.testing.assert_close(lw.cpu()[full], torch.from_numpy(outs["logits"])[:, t - 1][full], rtol=0, atol=2e-4)
 
 
-@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+def _assert_ids_equal_up_to_ties(ys, want, margins):
+    """Token ids must equal the reference's; a row may only part ways with it at a step where the reference's own
+    top-1 / top-2 logit margin is below 1e-4 (fp32 summation order decides such a step, SURVEY "argmax exact")."""
+    ys, want = ys.cpu(), torch.as_tensor(want)
+    assert ys.shape == want.shape, (ys.shape, want.shape)
+    for b in range(ys.shape[0]):
+        diff = (ys[b] != want[b]).nonzero()
+        if diff.numel():
+            t = int(diff[0])
+            assert float(margins[b, t - 1]) < 1e-4, (b, t, float(margins[b, t - 1]), ys[b].tolist(), want[b].tolist())
+
+
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b", "long_a"])          # long_a decodes 82 tokens over 71 memory rows
 def test_tiny_greedy_decode_ids_exact(name):
     """K/V-cached incremental decoding reproduces the reference's recompute-everything loop token for token."""
     cfg, enc, dec, ins, outs, _ = build_tiny(name, "fp32", "simt", dropout=0.3)
@@ -102,7 +114,15 @@ def test_tiny_greedy_decode_ids_exact(name):
     x = ins["feats"].to(DEV)
     for max_len, key in ((cfg["S1"] + 2, "greedy_ys"), (4, "greedy_ys_len4")):
         ys = eng.greedy_decode(x, None, max_len, 101, 102)
+        if name == "long_a" and ys.cpu().tolist() != outs[key].tolist():
+            from oracle import vct_oracle as O
+            sd = load_tiny(name)[1]
+            _, margins = O.greedy_decode_ids(sd, ins["feats"], None, cfg["nhead"], cfg["nhead"], max_len=max_len, return_margins=True)
+            _assert_ids_equal_up_to_ties(ys, outs[key], margins)
+            continue
         assert ys.cpu().tolist() == outs[key].tolist()
+    if name == "long_a":
+        return
     ys5 = eng.greedy_decode(x, None, cfg["S1"] + 2, 101, 102, sync_every=5)
     from oracle import vct_oracle as O
     cut = [" ".join(str(t) for t in O.cut_caption_ids(r)) for r in ys5.cpu().tolist()]

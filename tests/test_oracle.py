@@ -13,7 +13,7 @@ from helpers import load_tiny, load_anchors, synth_inputs, load_extra, sampled, 
 TOL = dict(rtol=2e-5, atol=2e-6)
 
 
-@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b", "long_a"])
 def test_oracle_forward_matches_reference_golden(name):
     cfg, sd, ins, outs, _ = load_tiny(name)
     mem, logits, loss = O.caption_forward(sd, ins["feats"], ins["vid_pad"], ins["ids"], cfg["nhead"], cfg["nhead"],
@@ -23,7 +23,7 @@ def test_oracle_forward_matches_reference_golden(name):
     assert abs(float(loss) - float(outs["loss"])) < 2e-6 * max(1.0, abs(float(outs["loss"])))
 
 
-@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b", "long_a"])
 def test_oracle_gradients_match_reference_golden(name):
     cfg, sd, ins, _, grads = load_tiny(name)
     _, g = O.caption_grads(sd, ins["feats"], ins["vid_pad"], ins["ids"], cfg["nhead"], cfg["nhead"], cfg["alpha"])
@@ -32,7 +32,7 @@ def test_oracle_gradients_match_reference_golden(name):
         torch.testing.assert_close(g[k], grads[k], rtol=1e-4, atol=2e-6, msg=lambda m, k=k: f"{k}: {m}")
 
 
-@pytest.mark.parametrize("name", ["tiny_a", "tiny_b"])
+@pytest.mark.parametrize("name", ["tiny_a", "tiny_b", "long_a"])
 def test_oracle_greedy_matches_reference_golden(name):
     cfg, sd, ins, outs, _ = load_tiny(name)
     ys = O.greedy_decode_ids(sd, ins["feats"], None, cfg["nhead"], cfg["nhead"], max_len=cfg["S1"] + 2)

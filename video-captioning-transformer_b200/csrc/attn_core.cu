@@ -1,8 +1,8 @@
 // Attention core: softmax(scale * Q K^T + mask) V, forward and backward.
 //
-// One CTA (4 warps) per (batch, head).  Sequence lengths on this path are 13..33, so the
+// One CTA (4 warps) per (batch, head).  Sequence lengths of the shipped configs are 13..33, so the
 // whole head -- Q, K, V (and dO) -- is staged once in shared memory as fp32; each warp owns a contiguous block
-// of query rows.
+// of query rows.  (Sequences beyond 64 rows: the tiled kernels under "Long sequences" below.)
 //   scores   : one key per lane; the lane keeps its K row in REGISTERS and the query row is read from shared
 //              memory as broadcast float4 -> FMA-bound, not shared-memory-bound
 //   softmax  : warp-shuffle max / sum over the key lanes; key-padding and causal masks are implicit
@@ -281,10 +281,335 @@ attn_bwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Long sequences (Lq or Lk > 64: more frames than CLIP4Clip's 12, captions beyond 64 word pieces -- the reference has no
+// limit: train.py does not truncate captions and T is whatever the feature file holds).  Same arithmetic as the
+// kernels above, tiled over the sequence:
+//   forward     CTA = (batch * head, tile of 16 query rows, 4 per warp).  K, then V, stream through shared memory in
+//               blocks of 32 rows (lane = key for the scores, lane = head-dim column for P V); the tile's complete score
+//               rows [16][Lk] stay in shared memory, so the softmax is the plain two-pass one
+//   backward Q  same tiling: recomputes P and dP = dO V^T, dS = P (dP - sum_j P dP) scale, dQ = dS K, and leaves
+//               (row max, 1 / row sum, sum_j P dP) of every query row in `row_stats`
+//   backward KV CTA = (batch * head, tile of 16 keys): S^T and dP^T of its keys against every query block, P rebuilt from
+//               the row statistics, dK = dS^T Q, dV = Pd^T dO.  No atomics: bit-reproducible
+// Dropout index space of this path: probability row r = (b*H + h)*Lq + i owns ceil(Lk / 8) groups of 8 keys, group g of
+// row r is Philox index r * ceil(Lk / 8) + g (the short kernels give every row exactly 8 groups).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kLongRows = 16;       // tile rows per CTA
+constexpr int kLongBlk = 32;        // rows of the streamed operand per block (one per lane)
+constexpr int kLongMax = 1024;      // longest sequence: 2 x [16][Lk] fp32 score tiles + operands fit 200 KB
+
+__device__ __forceinline__ uint32_t long_group_bits(const Rng& rng, unsigned int site, long long row, int nG, int g) {
+    return g < nG ? dropout_bits8(rng, site, (unsigned long long)row * (unsigned long long)nG + (unsigned long long)g) : 0u;
+}
+
+// masked, scaled scores of one row -> exponentials (in place); m = row maximum (-inf: every key masked), inv = 1 / row sum
+__device__ __forceinline__ void long_softmax_row(float* __restrict__ srow, int Lk, int gi, int lane, bool causal,
+                                                 const unsigned char* __restrict__ pad_row, float scale, float& m, float& inv) {
+    float mx = -INFINITY;
+    for (int j = lane; j < Lk; j += 32) {
+        const bool ok = !(causal && j > gi) && !(pad_row != nullptr && pad_row[j]);
+        float s = -INFINITY;
+        if (ok) s = srow[j] * scale;             // (columns of causally skipped blocks were never written: not read either)
+        srow[j] = s;
+        mx = fmaxf(mx, s);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < Lk; j += 32) {
+        const float s = srow[j];
+        const float e = s == -INFINITY ? 0.f : expf(s - mx);
+        srow[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    m = mx;
+    inv = sum > 0.f ? 1.f / sum : 0.f;
+}
+
+// acc[k][cc] += sum_{j < n} w[(r0 + k) * ldw + j] * mat[j][lane + 32 cc]  for k < nrows <= 4  (w broadcast, mat coalesced)
+template <int DHP>
+__device__ __forceinline__ void long_accumulate(const float* __restrict__ w, int ldw, int r0, int nrows,
+                                                const float* __restrict__ mat, int MS, int n, int lane,
+                                                float (&acc)[4][DHP / 32]) {
+    for (int j = 0; j < n; ++j) {
+        float wk[4];
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) wk[kk] = kk < nrows ? w[(r0 + kk) * ldw + j] : 0.f;
+#pragma unroll
+        for (int cc = 0; cc < DHP / 32; ++cc) {
+            const float x = mat[j * MS + lane + 32 * cc];
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) acc[kk][cc] = fmaf(wk[kk], x, acc[kk][cc]);
+        }
+    }
+}
+
+template <typename T, int DHP>
+__device__ __forceinline__ void long_store_rows(T* __restrict__ base, long long ld, int nrows, int dh, int lane,
+                                                const float (&acc)[4][DHP / 32]) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        if (kk < nrows) {
+#pragma unroll
+            for (int cc = 0; cc < DHP / 32; ++cc) {
+                const int c = lane + 32 * cc;
+                if (c < dh) base[(long long)kk * ld + c] = from_f32<T>(acc[kk][cc]);
+            }
+        }
+    }
+}
+
+template <int DHP>
+__device__ __forceinline__ void long_zero(float (&acc)[4][DHP / 32]) {
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk)
+#pragma unroll
+        for (int cc = 0; cc < DHP / 32; ++cc) acc[kk][cc] = 0.f;
+}
+
+template <typename T, int DHP>
+__global__ void __launch_bounds__(kThreads)
+attn_long_fwd_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, T* __restrict__ o,
+                     const unsigned char* __restrict__ key_pad, float* __restrict__ probs, Dims D, float drop_p,
+                     const unsigned long long* __restrict__ rng_state, unsigned int site) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
+    const int dh = D.dh, Lk = D.Lk, Lq = D.Lq;
+    const int q0 = blockIdx.y * kLongRows, nq = min(kLongRows, Lq - q0);
+    constexpr int KS = DHP + 1;
+    const int LkP = (Lk + 3) & ~3;
+    float* Qs = sm;                               // [16][DHP]   the tile's query rows
+    float* Bs = Qs + kLongRows * DHP;             // [32][KS]    streamed block of K, later V
+    float* Ss = Bs + kLongBlk * KS;               // [16][LkP]   scores -> (dropped) probabilities
+    const Rng rng = make_rng(rng_state, drop_p);
+    const int r0 = warp * 4, r1 = min(nq, r0 + 4);                  // this warp's rows of the tile
+    const int kend = D.causal ? min(Lk, q0 + nq) : Lk;              // keys >= kend are masked for every row of the tile
+    const T* kb = k + (long long)b * D.k_bs + h * dh;
+    const T* vb = v + (long long)b * D.v_bs + h * dh;
+    stage_tile<T, DHP>(q + (long long)b * D.q_bs + (long long)q0 * D.q_ld + h * dh, D.q_ld, nq, dh, Qs, DHP);
+    for (int j0 = 0; j0 < kend; j0 += kLongBlk) {
+        const int nk = min(kLongBlk, Lk - j0);
+        __syncthreads();
+        stage_tile<T, DHP>(kb + (long long)j0 * D.k_ld, D.k_ld, nk, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) rows_dot_keys<DHP>(Qs, DHP, Bs, KS, nk, LkP, r0, r1, lane, Ss + j0);
+    }
+    __syncwarp();
+    const unsigned char* pad_row = key_pad ? key_pad + (long long)b * Lk : nullptr;
+    const int nG = (Lk + 7) >> 3;
+    for (int il = r0; il < r1; ++il) {
+        const int gi = q0 + il;
+        float* srow = Ss + il * LkP;
+        float m, inv;
+        long_softmax_row(srow, Lk, gi, lane, D.causal != 0, pad_row, D.scale, m, inv);
+        const long long row = (long long)bh * Lq + gi;
+        for (int c0 = 0; c0 < Lk; c0 += 256) {                      // 256 keys = 32 groups: one Philox call per lane
+            const uint32_t bits = rng.p > 0.f ? long_group_bits(rng, site, row, nG, (c0 >> 3) + lane) : 0xFFu;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (c0 + 32 * t < Lk) {                             // warp-uniform
+                    const uint32_t gb = __shfl_sync(0xffffffffu, bits, 4 * t + (lane >> 3));
+                    const int j = c0 + 32 * t + lane;
+                    if (j < Lk) {
+                        float p = srow[j] * inv;
+                        if (probs) probs[row * Lk + j] = p;
+                        if (rng.p > 0.f) p = ((gb >> (lane & 7)) & 1u) ? p * rng.inv_keep : 0.f;
+                        srow[j] = p;
+                    }
+                }
+            }
+        }
+    }
+    __syncwarp();
+    float acc[4][DHP / 32];
+    long_zero<DHP>(acc);
+    for (int j0 = 0; j0 < kend; j0 += kLongBlk) {
+        const int nk = min(kLongBlk, Lk - j0);
+        __syncthreads();
+        stage_tile<T, DHP>(vb + (long long)j0 * D.v_ld, D.v_ld, nk, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) long_accumulate<DHP>(Ss + j0, LkP, r0, r1 - r0, Bs, KS, nk, lane, acc);
+    }
+    if (r0 < r1)
+        long_store_rows<T, DHP>(o + (long long)b * D.o_bs + (long long)(q0 + r0) * D.o_ld + h * dh, D.o_ld, r1 - r0, dh, lane, acc);
+}
+
+template <typename T, int DHP>
+__global__ void __launch_bounds__(kThreads)
+attn_long_bwd_q_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ d_o,
+                       T* __restrict__ dq, const unsigned char* __restrict__ key_pad, Dims D, float drop_p,
+                       const unsigned long long* __restrict__ rng_state, unsigned int site, float* __restrict__ row_stats) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
+    const int dh = D.dh, Lk = D.Lk, Lq = D.Lq;
+    const int q0 = blockIdx.y * kLongRows, nq = min(kLongRows, Lq - q0);
+    constexpr int KS = DHP + 1;
+    const int LkP = (Lk + 3) & ~3;
+    float* Qs = sm;                               // [16][DHP]
+    float* dOs = Qs + kLongRows * DHP;            // [16][DHP]
+    float* Bs = dOs + kLongRows * DHP;            // [32][KS]    streamed block of K / V
+    float* Ss = Bs + kLongBlk * KS;               // [16][LkP]   scores -> P -> dS
+    float* dPs = Ss + kLongRows * LkP;            // [16][LkP]   dO . V -> dropped dP
+    const Rng rng = make_rng(rng_state, drop_p);
+    const int r0 = warp * 4, r1 = min(nq, r0 + 4);
+    const int kend = D.causal ? min(Lk, q0 + nq) : Lk;
+    const T* kb = k + (long long)b * D.k_bs + h * dh;
+    const T* vb = v + (long long)b * D.v_bs + h * dh;
+    stage_tile<T, DHP>(q + (long long)b * D.q_bs + (long long)q0 * D.q_ld + h * dh, D.q_ld, nq, dh, Qs, DHP);
+    stage_tile<T, DHP>(d_o + (long long)b * D.do_bs + (long long)q0 * D.do_ld + h * dh, D.do_ld, nq, dh, dOs, DHP);
+    for (int j0 = 0; j0 < kend; j0 += kLongBlk) {
+        const int nk = min(kLongBlk, Lk - j0);
+        __syncthreads();
+        stage_tile<T, DHP>(kb + (long long)j0 * D.k_ld, D.k_ld, nk, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) rows_dot_keys<DHP>(Qs, DHP, Bs, KS, nk, LkP, r0, r1, lane, Ss + j0);
+        __syncthreads();
+        stage_tile<T, DHP>(vb + (long long)j0 * D.v_ld, D.v_ld, nk, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) rows_dot_keys<DHP>(dOs, DHP, Bs, KS, nk, LkP, r0, r1, lane, dPs + j0);
+    }
+    __syncwarp();
+    const unsigned char* pad_row = key_pad ? key_pad + (long long)b * Lk : nullptr;
+    const int nG = (Lk + 7) >> 3;
+    for (int il = r0; il < r1; ++il) {
+        const int gi = q0 + il;
+        float* srow = Ss + il * LkP;
+        float* drow = dPs + il * LkP;
+        float m, inv;
+        long_softmax_row(srow, Lk, gi, lane, D.causal != 0, pad_row, D.scale, m, inv);
+        const long long row = (long long)bh * Lq + gi;
+        float dsum = 0.f;
+        for (int c0 = 0; c0 < Lk; c0 += 256) {
+            const uint32_t bits = rng.p > 0.f ? long_group_bits(rng, site, row, nG, (c0 >> 3) + lane) : 0xFFu;
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                if (c0 + 32 * t < Lk) {
+                    const uint32_t gb = __shfl_sync(0xffffffffu, bits, 4 * t + (lane >> 3));
+                    const int j = c0 + 32 * t + lane;
+                    if (j < Lk) {
+                        const float p = srow[j] * inv;
+                        const float sc = rng.p > 0.f ? (((gb >> (lane & 7)) & 1u) ? rng.inv_keep : 0.f) : 1.f;
+                        const float dP = p != 0.f ? drow[j] * sc : 0.f;     // (masked columns may hold unwritten memory)
+                        dsum += p * dP;
+                        srow[j] = p;
+                        drow[j] = dP;
+                    }
+                }
+            }
+        }
+        dsum = warp_sum(dsum);
+        for (int j = lane; j < Lk; j += 32) srow[j] = srow[j] * (drow[j] - dsum) * D.scale;
+        if (lane == 0) *reinterpret_cast<float4*>(row_stats + row * 4) = make_float4(m, inv, dsum, 0.f);
+    }
+    __syncwarp();
+    float acc[4][DHP / 32];
+    long_zero<DHP>(acc);
+    for (int j0 = 0; j0 < kend; j0 += kLongBlk) {
+        const int nk = min(kLongBlk, Lk - j0);
+        __syncthreads();
+        stage_tile<T, DHP>(kb + (long long)j0 * D.k_ld, D.k_ld, nk, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) long_accumulate<DHP>(Ss + j0, LkP, r0, r1 - r0, Bs, KS, nk, lane, acc);
+    }
+    if (r0 < r1)
+        long_store_rows<T, DHP>(dq + (long long)b * D.dq_bs + (long long)(q0 + r0) * D.dq_ld + h * dh, D.dq_ld, r1 - r0, dh, lane, acc);
+}
+
+template <typename T, int DHP>
+__global__ void __launch_bounds__(kThreads)
+attn_long_bwd_kv_kernel(const T* __restrict__ q, const T* __restrict__ k, const T* __restrict__ v, const T* __restrict__ d_o,
+                        T* __restrict__ dk, T* __restrict__ dv, const unsigned char* __restrict__ key_pad, Dims D,
+                        float drop_p, const unsigned long long* __restrict__ rng_state, unsigned int site,
+                        const float* __restrict__ row_stats) {
+    pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ __align__(16) float sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int bh = blockIdx.x, b = bh / D.H, h = bh % D.H;
+    const int dh = D.dh, Lk = D.Lk, Lq = D.Lq;
+    const int k0 = blockIdx.y * kLongRows, nkk = min(kLongRows, Lk - k0);
+    constexpr int KS = DHP + 1;
+    const int LqP = (Lq + 3) & ~3;
+    float* Kt = sm;                               // [16][DHP]   the tile's keys
+    float* Vt = Kt + kLongRows * DHP;             // [16][DHP]   ... and values
+    float* Bs = Vt + kLongRows * DHP;             // [32][KS]    streamed block of Q / dO
+    float* St = Bs + kLongBlk * KS;               // [16][LqP]   S^T -> dS^T
+    float* Pt = St + kLongRows * LqP;             // [16][LqP]   dP^T -> dropped P^T
+    const Rng rng = make_rng(rng_state, drop_p);
+    const int r0 = warp * 4, r1 = min(nkk, r0 + 4);                 // this warp's keys of the tile
+    const int i_begin = D.causal ? (k0 & ~(kLongBlk - 1)) : 0;      // causal: queries i < k0 see none of these keys
+    const T* qb = q + (long long)b * D.q_bs + h * dh;
+    const T* gb_ = d_o + (long long)b * D.do_bs + h * dh;
+    stage_tile<T, DHP>(k + (long long)b * D.k_bs + (long long)k0 * D.k_ld + h * dh, D.k_ld, nkk, dh, Kt, DHP);
+    stage_tile<T, DHP>(v + (long long)b * D.v_bs + (long long)k0 * D.v_ld + h * dh, D.v_ld, nkk, dh, Vt, DHP);
+    for (int i0 = i_begin; i0 < Lq; i0 += kLongBlk) {
+        const int ni = min(kLongBlk, Lq - i0);
+        __syncthreads();
+        stage_tile<T, DHP>(qb + (long long)i0 * D.q_ld, D.q_ld, ni, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) rows_dot_keys<DHP>(Kt, DHP, Bs, KS, ni, LqP, r0, r1, lane, St + i0);
+        __syncthreads();
+        stage_tile<T, DHP>(gb_ + (long long)i0 * D.do_ld, D.do_ld, ni, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) rows_dot_keys<DHP>(Vt, DHP, Bs, KS, ni, LqP, r0, r1, lane, Pt + i0);
+    }
+    __syncwarp();
+    if (r0 < r1) {
+        const unsigned char* pad_row = key_pad ? key_pad + (long long)b * Lk : nullptr;
+        const int nG = (Lk + 7) >> 3;
+        const int g = (k0 + r0) >> 3, bit0 = (k0 + r0) & 7;        // the warp's 4 keys sit in ONE group of 8 (bit0 = 0 or 4)
+        for (int i = i_begin + lane; i < Lq; i += 32) {
+            const long long row = (long long)bh * Lq + i;
+            const float4 st = *reinterpret_cast<const float4*>(row_stats + row * 4);      // row max, 1 / row sum, sum_j P dP
+            const uint32_t bits = rng.p > 0.f ? long_group_bits(rng, site, row, nG, g) : 0xFFu;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int jl = r0 + kk;
+                if (jl < r1) {
+                    const int j = k0 + jl;
+                    const bool ok = !(D.causal && j > i) && !(pad_row != nullptr && pad_row[j]);
+                    float p = 0.f;
+                    if (ok && st.x != -INFINITY) p = expf(St[jl * LqP + i] * D.scale - st.x) * st.y;
+                    const float sc = rng.p > 0.f ? (((bits >> (bit0 + kk)) & 1u) ? rng.inv_keep : 0.f) : 1.f;
+                    const float dP = p != 0.f ? Pt[jl * LqP + i] * sc : 0.f;
+                    St[jl * LqP + i] = p * (dP - st.z) * D.scale;
+                    Pt[jl * LqP + i] = p * sc;
+                }
+            }
+        }
+    }
+    __syncwarp();
+    float ak[4][DHP / 32], av[4][DHP / 32];
+    long_zero<DHP>(ak);
+    long_zero<DHP>(av);
+    for (int i0 = i_begin; i0 < Lq; i0 += kLongBlk) {
+        const int ni = min(kLongBlk, Lq - i0);
+        __syncthreads();
+        stage_tile<T, DHP>(qb + (long long)i0 * D.q_ld, D.q_ld, ni, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) long_accumulate<DHP>(St + i0, LqP, r0, r1 - r0, Bs, KS, ni, lane, ak);
+        __syncthreads();
+        stage_tile<T, DHP>(gb_ + (long long)i0 * D.do_ld, D.do_ld, ni, dh, Bs, KS);
+        __syncthreads();
+        if (r0 < r1) long_accumulate<DHP>(Pt + i0, LqP, r0, r1 - r0, Bs, KS, ni, lane, av);
+    }
+    if (r0 < r1) {
+        long_store_rows<T, DHP>(dk + (long long)b * D.dk_bs + (long long)(k0 + r0) * D.dk_ld + h * dh, D.dk_ld, r1 - r0, dh, lane, ak);
+        long_store_rows<T, DHP>(dv + (long long)b * D.dv_bs + (long long)(k0 + r0) * D.dv_ld + h * dh, D.dv_ld, r1 - r0, dh, lane, av);
+    }
+}
+
 int validate(const vct_attn_args* a, const char* who) {
     VCT_REQUIRE(a != nullptr, "%s: null args", who);
     VCT_REQUIRE(a->B > 0 && a->H > 0 && a->Lq > 0 && a->Lk > 0, "%s: empty problem", who);
-    VCT_REQUIRE(a->Lq <= 64 && a->Lk <= 64, "%s: Lq, Lk must be <= 64 (got %d, %d)", who, a->Lq, a->Lk);
+    VCT_REQUIRE(a->Lq <= kLongMax && a->Lk <= kLongMax, "%s: Lq, Lk must be <= %d (got %d, %d)", who, kLongMax, a->Lq, a->Lk);
     VCT_REQUIRE(a->dh % 4 == 0 && a->dh <= 128, "%s: dh must be a multiple of 4 and <= 128 (got %d)", who, a->dh);
     VCT_REQUIRE(!a->causal || a->Lq == a->Lk, "%s: causal needs Lq == Lk", who);
     VCT_REQUIRE(a->q_ld % 4 == 0 && a->k_ld % 4 == 0 && a->v_ld % 4 == 0 && a->o_ld % 4 == 0,
@@ -433,9 +758,55 @@ int launch_decode(const vct_attn_args* a, cudaStream_t st) {
     return check_launch("vct_attn_fwd(decode)");
 }
 
+// ---- long sequences: forward = one launch, backward = the query-tile kernel, then the key-tile kernel ----
+template <typename T, int DHP>
+int launch_long_fwd(const vct_attn_args* a, cudaStream_t st) {
+    const int LkP = (a->Lk + 3) & ~3;
+    const size_t smem = sizeof(float) * ((size_t)kLongRows * DHP + (size_t)kLongBlk * (DHP + 1) + (size_t)kLongRows * LkP);
+    VCT_REQUIRE(smem <= kSmemBudget, "vct_attn_fwd: key rows do not fit shared memory");
+    auto kern = attn_long_fwd_kernel<T, DHP>;
+    static bool once = false;
+    if (!once) { VCT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget)); once = true; }
+    vct::launch(kern, dim3(a->B * a->H, (a->Lq + kLongRows - 1) / kLongRows), dim3(kThreads), smem, st, (const T*)a->q, (const T*)a->k,
+                (const T*)a->v, (T*)a->o, a->key_pad, a->probs, make_dims(a), a->drop_p, a->rng_state, a->site);
+    return check_launch("vct_attn_fwd(long)");
+}
+
+template <typename T, int DHP>
+int launch_long_bwd(const vct_attn_args* a, cudaStream_t st) {
+    VCT_REQUIRE(a->row_stats != nullptr && (reinterpret_cast<uintptr_t>(a->row_stats) & 15) == 0,
+                "vct_attn_bwd: sequences longer than 64 need the 16-byte aligned row_stats workspace (fp32 [B*H*Lq, 4])");
+    VCT_REQUIRE(a->dbias == nullptr, "vct_attn_bwd: dbias is produced in-kernel only for Lq, Lk <= 64 (use vct_colsum on dq | dk | dv)");
+    const int LP = ((a->Lq > a->Lk ? a->Lq : a->Lk) + 3) & ~3;
+    const size_t smem = sizeof(float) * (2 * (size_t)kLongRows * DHP + (size_t)kLongBlk * (DHP + 1) + 2 * (size_t)kLongRows * LP);
+    VCT_REQUIRE(smem <= kSmemBudget, "vct_attn_bwd: score rows do not fit shared memory");
+    auto kq = attn_long_bwd_q_kernel<T, DHP>;
+    auto kkv = attn_long_bwd_kv_kernel<T, DHP>;
+    static bool once = false;
+    if (!once) {
+        VCT_CUDA(cudaFuncSetAttribute(kq, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        VCT_CUDA(cudaFuncSetAttribute(kkv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget));
+        once = true;
+    }
+    const Dims D = make_dims(a);
+    vct::launch(kq, dim3(a->B * a->H, (a->Lq + kLongRows - 1) / kLongRows), dim3(kThreads), smem, st, (const T*)a->q, (const T*)a->k,
+                (const T*)a->v, (const T*)a->d_o, (T*)a->dq, a->key_pad, D, a->drop_p, a->rng_state, a->site, a->row_stats);
+    if (int e = check_launch("vct_attn_bwd(long, q)")) return e;
+    vct::launch(kkv, dim3(a->B * a->H, (a->Lk + kLongRows - 1) / kLongRows), dim3(kThreads), smem, st, (const T*)a->q, (const T*)a->k,
+                (const T*)a->v, (const T*)a->d_o, (T*)a->dk, (T*)a->dv, a->key_pad, D, a->drop_p, a->rng_state, a->site,
+                (const float*)a->row_stats);
+    return check_launch("vct_attn_bwd(long, kv)");
+}
+
 template <typename T>
 int dispatch(const vct_attn_args* a, cudaStream_t st, bool bwd) {
     const int dh = a->dh;
+    if (a->Lq > 64 || a->Lk > 64) {
+        if (dh <= 32) return bwd ? launch_long_bwd<T, 32>(a, st) : launch_long_fwd<T, 32>(a, st);
+        if (dh <= 64) return bwd ? launch_long_bwd<T, 64>(a, st) : launch_long_fwd<T, 64>(a, st);
+        if (dh <= 96) return bwd ? launch_long_bwd<T, 96>(a, st) : launch_long_fwd<T, 96>(a, st);
+        return bwd ? launch_long_bwd<T, 128>(a, st) : launch_long_fwd<T, 128>(a, st);
+    }
     // one query row, no dropout (greedy decoding): the warp-per-head kernel
     static const bool dec_on = [] { const char* e = getenv("VCT_ATTN_DECODE"); return e == nullptr || e[0] != '0'; }();
     if (!bwd && dec_on && a->Lq == 1 && !(a->drop_p > 0.f)) {

@@ -129,19 +129,36 @@ ln_fwd_kernel(const float* __restrict__ x, const float* r, const float* __restri
     const int nv = d >> 3;
     const Rng rng = make_rng(rng_state, x != nullptr ? drop_p : 0.f);
     const long long base = (long long)row * d;
-    float v[NV][8];
-    float sum = 0.f;
+    // every global load of the row (branch output, residual, gamma, beta) is issued before anything consumes one: ONE
+    // memory round trip per row.  (Interleaved with the Philox rounds the compiler emitted three batches of loads, each
+    // waiting for the previous batch's arithmetic, and fetched gamma / beta only after the statistics.)
+    float v[NV][8], xv[NV][8], g[NV][8], bt[NV][8];
 #pragma unroll
     for (int i = 0; i < NV; ++i) {
         const int c = lane + 32 * i;
         if (c < nv) {
             ld8(r + base + c * 8, v[i]);
-            if (x != nullptr) {
-                float sc[8], xv[8];
-                dropout_scale8(rng, site, (unsigned long long)(base >> 3) + c, sc);
-                ld8(x + base + c * 8, xv);
+            if (x != nullptr) ld8(x + base + c * 8, xv[i]);
+        }
+    }
 #pragma unroll
-                for (int q = 0; q < 8; ++q) v[i][q] = xv[q] + v[i][q] * sc[q];
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+            ld8(gamma + c * 8, g[i]);
+            ld8(beta + c * 8, bt[i]);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        if (c < nv) {
+            if (x != nullptr) {
+                float sc[8];
+                dropout_scale8(rng, site, (unsigned long long)(base >> 3) + c, sc);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v[i][q] = xv[i][q] + v[i][q] * sc[q];
             }
 #pragma unroll
             for (int q = 0; q < 8; ++q) sum += v[i][q];
@@ -167,11 +184,9 @@ ln_fwd_kernel(const float* __restrict__ x, const float* r, const float* __restri
         const int c = lane + 32 * i;
         if (c < nv) {
             if (s_out) st8(s_out + base + c * 8, v[i]);
-            float g[8], b[8], o[8];
-            ld8(gamma + c * 8, g);
-            ld8(beta + c * 8, b);
+            float o[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) o[q] = (v[i][q] - mean) * rstd * g[q] + b[q];
+            for (int q = 0; q < 8; ++q) o[q] = (v[i][q] - mean) * rstd * g[i][q] + bt[i][q];
             if (y) st8(y + base + c * 8, o);
             if (y_c) st8(y_c + base + c * 8, o);
         }

@@ -557,14 +557,28 @@ class CaptionEngine:
         a.probs = probs
         a.d_o, a.do_ld, a.dq, a.dq_ld, a.dk, a.dk_ld, a.dv, a.dv_ld = d_o, do_ld, dq, dq_ld, dk, dk_ld, dv, dv_ld
         a.q_bs, a.k_bs, a.v_bs, a.o_bs = q_bs, k_bs, v_bs, o_bs
-        if dbias is not None:
+        long_seq = max(Lq, Lk) > 64          # tiled kernels (csrc/attn_core.cu "Long sequences")
+        if dbias is not None and not long_seq:
             # in-projection bias gradient (column sums of dq | dk | dv) produced by the backward kernel itself; the
             # partials buffer is per call site, the counters are self-resetting
             part = self._scratch(ws, "attn_dbias:" + tag, B, 3 * self.dims.d, torch.float32)
             a.dbias, a.dbias_partials, a.dbias_counters = dbias, part.data_ptr(), self.counters.data_ptr() + 4 * 512
+        if bwd and long_seq:
+            # per-row softmax statistics handed from the query-tile kernel to the key-tile kernel
+            a.row_stats = self._scratch(ws, "attn_row_stats:" + tag, B * H * Lq, 4, torch.float32).data_ptr()
         plan.keep.append(a)
         plan.add(("vct_attn_bwd:" if bwd else "vct_attn_fwd:") + tag,
                  self.lib.vct_attn_bwd if bwd else self.lib.vct_attn_fwd, C.byref(a))
+        if bwd and long_seq and dbias is not None:
+            # the tiled backward leaves the in-projection bias gradient to column sums over dq | dk | dv (same lane as the
+            # attention call; own partials and counters, so the side lane's column sums cannot interfere)
+            d = self.dims.d
+            n = int(self.lib.vct_colsum_workspace_floats(B * max(Lq, Lk), d))
+            part = self._scratch(ws, "attn_dbias_long:" + tag, 1, n, torch.float32).data_ptr()
+            cnt = self.counters.data_ptr() + 4 * 768
+            for sec, (X, ld, rows) in enumerate(((dq, dq_ld, B * Lq), (dk, dk_ld, B * Lk), (dv, dv_ld, B * Lk))):
+                plan.add(f"vct_colsum:{tag}.in_proj_bias[{sec}]", self.lib.vct_colsum, X, self.cdt, ld, rows, d,
+                         dbias + 4 * sec * d, part, cnt)
 
     # ------------------------------------------------------------------------------------------
     # workspaces
@@ -685,19 +699,20 @@ class CaptionEngine:
         self._ws[key] = ws
         return ws
 
-    MAX_LEN = 64        # longest sequence the attention kernels cover (memory rows T + 1, decoder positions S)
+    MAX_LEN = 1024      # longest sequence the attention kernels cover (memory rows T + 1, decoder positions S)
 
     def _check_lengths(self, M: int, S: int) -> None:
-        """The attention kernels (fused tcgen05 and SIMT alike) hold a whole (batch, head) in one tile / one warp's key
-        lanes: sequences are limited to 64 rows, and the dropout counter space assigns 8 groups of 8 keys to a row.  The
-        reference has no such limit (captions are not truncated for training); fail BEFORE the first launch, with the
-        remedy, instead of in the middle of an epoch."""
+        """Sequences up to 64 rows (every shipped config: 13 / 33 memory rows, captions below 40 word pieces) run on the
+        fused tcgen05 attention kernels, which hold a whole (batch, head) in one tile; longer ones -- the reference
+        truncates neither captions nor frames for training -- run the tiled SIMT kernels of csrc/attn_core.cu, whose
+        score tiles fit shared memory up to 1024 rows (the reference's own tables end at 512 frames,
+        model/MMEncoder.py:65, and 5000 positions, model/Embedding.py:11).  Beyond that: fail BEFORE the first launch,
+        with the remedy, instead of in the middle of an epoch."""
         if M > self.MAX_LEN or S > self.MAX_LEN:
             raise ValueError(
                 f"vct_b200: sequence too long for the attention kernels (memory length T+1 = {M}, decoder positions = {S}; "
                 f"limit {self.MAX_LEN}).  Sample at most {self.MAX_LEN - 1} frames per video and truncate captions to "
-                f"{self.MAX_LEN} word pieces (+1 for the shifted target) in the data pipeline -- the shipped CLIP4Clip "
-                f"features have 12 frames and MSR-VTT / MSVD captions stay below 40 word pieces (see INTEGRATION.md).")
+                f"{self.MAX_LEN} word pieces (+1 for the shifted target) in the data pipeline (see INTEGRATION.md).")
 
     def _evict_workspaces(self) -> None:
         """Bound the per-shape workspace cache (batches built by caption length have a new S almost every step): keep the

@@ -53,6 +53,7 @@ class AttnArgs(C.Structure):
         ("d_o", vp), ("do_ld", ll), ("dq", vp), ("dq_ld", ll), ("dk", vp), ("dk_ld", ll), ("dv", vp), ("dv_ld", ll),
         ("q_bs", ll), ("k_bs", ll), ("v_bs", ll), ("o_bs", ll), ("do_bs", ll), ("dq_bs", ll), ("dk_bs", ll), ("dv_bs", ll),
         ("dbias", vp), ("dbias_partials", vp), ("dbias_counters", vp),
+        ("row_stats", vp),
     ]
 
 
