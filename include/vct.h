@@ -244,6 +244,17 @@ int vct_ln_residual_bwd(const float* dy, const float* s, const float* mean, cons
  * encoder layer's output right before vct_ln_residual_fwd. */
 int vct_zero_rows(float* x, const unsigned char* mask, int R, int d, vct_stream_t stream);
 
+/* ---- input staging ----------------------------------------------------------------------------
+ * One launch moves a step's DEVICE-resident batch into the buffers the launch plans read (what the reference does with
+ * `.to(device)` per modality, train.py:120-121, plus CapPreprocessor's mask, model/CapPreprocessor.py:35):
+ *   feats_src fp32 [B,T,Din] -> feats_dst (16-byte aligned, Din % 4 == 0); vid_src bytes [B,T] (NULL: nothing padded)
+ *   -> vid_dst [B,T+1] whose column 0 (the global token) is never padded (model/MMEncoder.py:252-260);
+ *   ids_src int64 [B,S1] -> ids_dst; tok_dst [B,S1-1] = tok_src (explicit key-padding mask) or ids[:, :-1] == pad_id.
+ * feats_src NULL skips the feature half, ids_src NULL the token half. */
+int vct_stage_inputs(const float* feats_src, float* feats_dst, const unsigned char* vid_src, unsigned char* vid_dst,
+                     int B, int T, int Din, const long long* ids_src, long long* ids_dst,
+                     const unsigned char* tok_src, unsigned char* tok_dst, int S1, long long pad_id, vct_stream_t stream);
+
 /* ---- token embedding + positional table ------------------------------------------------------
  * x[b,s,:] = dropout(E[ids[b*ids_ld + s], :] + pos[s, :])   (no sqrt(d) scaling)
  * model/CapDecoder.py:48 + model/Embedding.py:23-25.  ids int64.  Writes x fp32 and optional x_c.

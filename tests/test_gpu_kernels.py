@@ -765,3 +765,36 @@ def test_gemm_saved_gelu_factor_pair_matches_recompute_pair(lib, impl):
     d2, _ = run_gemm(lib, G, W, 0, 0, M, N, K, act=L.ACT_MUL_AUX, aux=f, c_dtype=L.BF16, impl=impl)
     assert torch.isfinite(d2.float()).all()
     assert float((d2.float() - d1.float()).norm() / d1.float().norm()) < 1e-2
+
+
+@pytest.mark.parametrize("B,T,Din,S1", [(64, 12, 512, 21), (3, 5, 24, 8), (2, 70, 512, 81)])
+@pytest.mark.parametrize("with_masks", [False, True])
+def test_stage_inputs_matches_the_torch_copies(lib, B, T, Din, S1, with_masks):
+    """vct_stage_inputs == feats copy, [B,T+1] frame mask with an unpadded global column, ids copy, ids[:, :-1] == pad
+    (or the caller's mask); either half can be skipped."""
+    g = torch.Generator().manual_seed(B + T)
+    feats = torch.randn(B, T, Din, generator=g).to(DEV)
+    vid = (torch.rand(B, T, generator=g) < 0.3).to(DEV) if with_masks else None
+    ids = torch.randint(0, 5, (B, S1), generator=g).to(DEV)
+    tok = (torch.rand(B, S1 - 1, generator=g) < 0.5).to(DEV) if with_masks else None
+    f2 = torch.full((B, T, Din), float("nan"), device=DEV)
+    v2 = torch.full((B, T + 1), 7, dtype=torch.uint8, device=DEV)
+    i2 = torch.full((B, S1), -1, dtype=torch.int64, device=DEV)
+    t2 = torch.full((B, S1 - 1), 7, dtype=torch.uint8, device=DEV)
+    L.check(lib.vct_stage_inputs(feats.data_ptr(), f2.data_ptr(), vid.data_ptr() if vid is not None else None, v2.data_ptr(),
+                                 B, T, Din, ids.data_ptr(), i2.data_ptr(), tok.data_ptr() if tok is not None else None,
+                                 t2.data_ptr(), S1, 0, stream()))
+    torch.cuda.synchronize()
+    assert torch.equal(f2, feats) and torch.equal(i2, ids)
+    want_v = torch.zeros(B, T + 1, dtype=torch.uint8, device=DEV)
+    if vid is not None:
+        want_v[:, 1:] = vid.to(torch.uint8)
+    assert torch.equal(v2, want_v)
+    assert torch.equal(t2, (tok if tok is not None else ids[:, :-1] == 0).to(torch.uint8))
+    # token half only: the feature buffers stay untouched
+    f2.fill_(1.0), v2.fill_(9)
+    L.check(lib.vct_stage_inputs(None, f2.data_ptr(), None, v2.data_ptr(), B, T, Din, ids.data_ptr(), i2.data_ptr(), None,
+                                 t2.data_ptr(), S1, 3, stream()))
+    torch.cuda.synchronize()
+    assert float(f2.min()) == 1.0 and int(v2.min()) == 9
+    assert torch.equal(t2, (ids[:, :-1] == 3).to(torch.uint8))

@@ -270,24 +270,38 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const f
 #pragma unroll 1
     for (int row = blockIdx.x * rows_per_cta + warp; row < row_end; row += kLnBwdWarps) {
         const long long base = (long long)row * d;
+        // all loads of the row first (ONE memory round trip per row; written chunk by chunk the compiler emitted one batch
+        // of loads per chunk, each behind the previous chunk's arithmetic), the Philox rounds while they are in flight
+        float g[NV][8], xh[NV][8];              // raw dy / s, then dy * gamma / x-hat in place
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            if (c < nv) {
+                ld8(dy + base + c * 8, g[i]);
+                ld8(s + base + c * 8, xh[i]);
+            }
+        }
         const float mu = mean[row], rs = rstd[row];
-        float g[NV][8], xh[NV][8];
+        uint32_t keep[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int c = lane + 32 * i;
+            keep[i] = c < nv ? dropout_bits8(rng, site, (unsigned long long)(base >> 3) + c) : 0u;
+        }
         float c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < nv) {
-                float dyv[8], sv[8];
-                ld8(dy + base + c * 8, dyv);
-                ld8(s + base + c * 8, sv);
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    xh[i][q] = (sv[q] - mu) * rs;
-                    g[i][q] = dyv[q] * gam[i][q];
+                    const float dyv = g[i][q];
+                    xh[i][q] = (xh[i][q] - mu) * rs;
+                    g[i][q] = dyv * gam[i][q];
                     c1 += g[i][q];
                     c2 += g[i][q] * xh[i][q];
-                    acc_g[i][q] += dyv[q] * xh[i][q];
-                    acc_b[i][q] += dyv[q];
+                    acc_g[i][q] += dyv * xh[i][q];
+                    acc_b[i][q] += dyv;
                 }
             }
         }
@@ -297,12 +311,11 @@ ln_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ s, const f
         for (int i = 0; i < NV; ++i) {
             const int c = lane + 32 * i;
             if (c < nv) {
-                float o[8], sc[8], dr[8];
-                dropout_scale8(rng, site, (unsigned long long)(base >> 3) + c, sc);
+                float o[8], dr[8];
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                     o[q] = rs * (g[i][q] - c1 - xh[i][q] * c2);
-                    dr[q] = o[q] * sc[q];
+                    dr[q] = o[q] * (((keep[i] >> q) & 1u) ? rng.inv_keep : 0.f);     // (p = 0: all bits set, inv_keep = 1)
                     acc_r[i][q] += dr[q];
                 }
                 if (ds) st8(ds + base + c * 8, o);
@@ -911,6 +924,72 @@ extern "C" int vct_zero_rows(float* x, const unsigned char* mask, int R, int d, 
     const long long n = (long long)R * (d / 4);
     vct::launch(zero_rows_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, x, mask, R, d);
     return check_launch("vct_zero_rows");
+}
+
+// ------------------------------------------------------------------------------------------------
+// input staging: ONE launch moves a step's device-resident batch into the workspace the launch plans read
+//   feats  [B,T,Din] fp32 -> copy                                    (feats_src NULL: skip feats and vid_pad)
+//   vid_pad [B,T] bytes (NULL = nothing padded) -> [B,T+1], column 0 (the global token) never padded,
+//           model/MMEncoder.py:252-260
+//   ids    [B,S1] int64 -> copy; tok_pad [B,S1-1] = the caller's mask, or ids[:, :-1] == pad_id as
+//           model/CapPreprocessor.py:35 builds it               (ids_src NULL: skip)
+// (five torch copy / fill / compare launches before: ~20 us of host time per step on the e2e path)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stage_inputs_kernel(const float4* __restrict__ feats_src, float4* __restrict__ feats_dst, long long n4,
+                    const unsigned char* __restrict__ vid_src, unsigned char* __restrict__ vid_dst, int B, int T,
+                    const long long* __restrict__ ids_src, long long* __restrict__ ids_dst,
+                    const unsigned char* __restrict__ tok_src, unsigned char* __restrict__ tok_dst, int S1, long long pad_id) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (feats_src != nullptr) {
+        for (long long i = tid; i < n4; i += stride) feats_dst[i] = feats_src[i];
+        const long long nv = (long long)B * (T + 1);
+        for (long long i = tid; i < nv; i += stride) {
+            const long long b = i / (T + 1);
+            const int m = (int)(i % (T + 1));
+            vid_dst[i] = (m == 0 || vid_src == nullptr) ? (unsigned char)0 : (unsigned char)(vid_src[b * T + m - 1] != 0);
+        }
+    }
+    if (ids_src != nullptr) {
+        const long long ni = (long long)B * S1;
+        for (long long i = tid; i < ni; i += stride) {
+            const long long v = ids_src[i];
+            ids_dst[i] = v;
+            const long long b = i / S1;
+            const int sidx = (int)(i % S1);
+            if (sidx < S1 - 1) {
+                const long long o = b * (S1 - 1) + sidx;
+                tok_dst[o] = tok_src != nullptr ? (unsigned char)(tok_src[o] != 0) : (unsigned char)(v == pad_id);
+            }
+        }
+    }
+}
+
+extern "C" int vct_stage_inputs(const float* feats_src, float* feats_dst, const unsigned char* vid_src, unsigned char* vid_dst,
+                                int B, int T, int Din, const long long* ids_src, long long* ids_dst,
+                                const unsigned char* tok_src, unsigned char* tok_dst, int S1, long long pad_id,
+                                vct_stream_t stream) {
+    VCT_REQUIRE(B > 0 && (feats_src != nullptr || ids_src != nullptr), "vct_stage_inputs: nothing to stage");
+    long long n4 = 0, work = 0;
+    if (feats_src != nullptr) {
+        VCT_REQUIRE(feats_dst && vid_dst && T > 0 && Din > 0 && Din % 4 == 0, "vct_stage_inputs: bad feature arguments (Din %% 4 must be 0)");
+        VCT_REQUIRE(((reinterpret_cast<uintptr_t>(feats_src) | reinterpret_cast<uintptr_t>(feats_dst)) & 15) == 0,
+                    "vct_stage_inputs: feature buffers must be 16-byte aligned");
+        n4 = (long long)B * T * (Din / 4);
+        work = n4;
+    }
+    if (ids_src != nullptr) {
+        VCT_REQUIRE(ids_dst && tok_dst && S1 >= 2, "vct_stage_inputs: bad id arguments");
+        if ((long long)B * S1 > work) work = (long long)B * S1;
+    }
+    long long blocks = (work + 255) / 256;
+    if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
+    vct::launch(stage_inputs_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const float4*)feats_src, (float4*)feats_dst, n4,
+                vid_src, vid_dst, B, T, ids_src, ids_dst, tok_src, tok_dst, S1, pad_id);
+    return check_launch("vct_stage_inputs");
 }
 
 // ------------------------------------------------------------------------------------------------

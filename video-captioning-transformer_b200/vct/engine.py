@@ -1171,6 +1171,8 @@ class CaptionEngine:
         """Copy the step's inputs into the workspace (host or device sources; async on the current stream).
         tok_pad: optional bool [B, S] key-padding mask of the decoder inputs (default: ids[:, :-1] == pad_id, which is
         what the reference's CapPreprocessor produces, model/CapPreprocessor.py:35)."""
+        if self._stage_native(ws, feats, vid_pad, ids, tok_pad):
+            return
         ws.feats.copy_(feats.reshape(ws.feats.shape), non_blocking=True)
         ws.vid_pad[:, 0] = 0
         if vid_pad is None:
@@ -1180,7 +1182,37 @@ class CaptionEngine:
         if ids is not None:
             self.stage_ids(ws, ids, tok_pad)
 
+    def _stage_native(self, ws, feats, vid_pad, ids, tok_pad) -> bool:
+        """Device-resident sources in the layouts the loaders / ``CaptionTrainer.prefetch`` produce: ONE vct_stage_inputs
+        launch instead of five torch copy / fill / compare launches.  Anything else (host tensors, other dtypes, strided
+        views) keeps the torch copies below, which convert as they go."""
+        def dev_ok(t, dtypes, shape):
+            return (t.is_cuda and t.device == ws.feats.device and t.dtype in dtypes and t.is_contiguous()
+                    and tuple(t.shape) == tuple(shape))
+        B, T, S = ws.B, ws.T, ws.S
+        byte = (torch.bool, torch.uint8)
+        if feats is not None and not (dev_ok(feats, (torch.float32,), (B, T, self.dims.Din)) and feats.data_ptr() % 16 == 0
+                                      and self.dims.Din % 4 == 0):
+            return False
+        if vid_pad is not None and not dev_ok(vid_pad, byte, (B, T)):
+            return False
+        if ids is not None and not dev_ok(ids, (torch.int64,), (B, S + 1)):
+            return False
+        if tok_pad is not None and (ids is None or not dev_ok(tok_pad, byte, (B, S))):
+            return False
+        if feats is None and ids is None:
+            return False
+        L.check(self.lib.vct_stage_inputs(
+            feats.data_ptr() if feats is not None else None, ws.feats.data_ptr(),
+            vid_pad.data_ptr() if (vid_pad is not None and feats is not None) else None, ws.vid_pad.data_ptr(),
+            B, T, self.dims.Din, ids.data_ptr() if ids is not None else None, ws.ids.data_ptr(),
+            tok_pad.data_ptr() if tok_pad is not None else None, ws.tok_pad.data_ptr(), S + 1, int(self.dims.pad_id),
+            self._stream()), "vct_stage_inputs")
+        return True
+
     def stage_ids(self, ws, ids: torch.Tensor, tok_pad: Optional[torch.Tensor] = None) -> None:
+        if self._stage_native(ws, None, None, ids, tok_pad):
+            return
         ws.ids.copy_(ids, non_blocking=True)
         if tok_pad is None:
             torch.eq(ws.ids[:, :-1], self.dims.pad_id, out=ws.tok_pad.view(torch.bool))

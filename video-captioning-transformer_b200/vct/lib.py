@@ -95,6 +95,7 @@ SIGNATURES = {
     "vct_ln_residual_bwd": (i32, [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp, vp, i32, i32, f32, vp, u32, vp]),
     "vct_ln_bwd_reduce": (i32, [vp, i32, i32, vp, vp, vp, vp]),
     "vct_zero_rows": (i32, [vp, vp, i32, i32, vp]),
+    "vct_stage_inputs": (i32, [vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, i32, ll, vp]),
     "vct_embed_fwd": (i32, [vp, ll, vp, vp, vp, vp, i32, i32, i32, i32, i32, i32, f32, vp, u32, vp]),
     "vct_embed_bwd": (i32, [vp, ll, vp, vp, i32, i32, i32, i32, i32, f32, vp, u32, vp]),
     "vct_embed_bwd_rows": (i32, [vp, vp, i32, i32, i32, f32, vp, u32, vp]),
