@@ -940,8 +940,7 @@ stage_inputs_kernel(const float4* __restrict__ feats_src, float4* __restrict__ f
                     const unsigned char* __restrict__ vid_src, unsigned char* __restrict__ vid_dst, int B, int T,
                     const long long* __restrict__ ids_src, long long* __restrict__ ids_dst,
                     const unsigned char* __restrict__ tok_src, unsigned char* __restrict__ tok_dst, int S1, long long pad_id) {
-    pdl_launch_dependents();
-    pdl_wait();
+    // (a plain launch, no programmatic dependent launch: this kernel sits between two steps' CUDA graphs, outside any graph)
     const long long stride = (long long)gridDim.x * blockDim.x;
     const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (feats_src != nullptr) {
@@ -987,8 +986,9 @@ extern "C" int vct_stage_inputs(const float* feats_src, float* feats_dst, const 
     }
     long long blocks = (work + 255) / 256;
     if (blocks > 4 * kNumSMs) blocks = 4 * kNumSMs;
-    vct::launch(stage_inputs_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, (const float4*)feats_src, (float4*)feats_dst, n4,
-                vid_src, vid_dst, B, T, ids_src, ids_dst, tok_src, tok_dst, S1, pad_id);
+    stage_inputs_kernel<<<dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream>>>((const float4*)feats_src, (float4*)feats_dst, n4, vid_src,
+                                                                                        vid_dst, B, T, ids_src, ids_dst, tok_src, tok_dst, S1,
+                                                                                        pad_id);
     return check_launch("vct_stage_inputs");
 }
 

@@ -1185,10 +1185,18 @@ class CaptionEngine:
     def _stage_native(self, ws, feats, vid_pad, ids, tok_pad) -> bool:
         """Device-resident sources in the layouts the loaders / ``CaptionTrainer.prefetch`` produce: ONE vct_stage_inputs
         launch instead of five torch copy / fill / compare launches.  Anything else (host tensors, other dtypes, strided
-        views) keeps the torch copies below, which convert as they go."""
+        views) keeps the torch copies below, which convert as they go.
+
+        OFF by default (VCT_STAGE_NATIVE=1 turns it on).  Measured A/B on one B200 box (profiles/r02f_stage_inputs_ab.txt):
+        the device-resident loop gains 1 % (1.532 vs 1.546 ms/step), but the end-to-end loop -- where the host is on the
+        critical path after every ``loss.item()`` -- dropped from 39.4-39.5k to 35.3-38.3k captions/s and became noisy,
+        with and without programmatic dependent launch on the kernel; the cause was not found within the round's GPU
+        budget, and the end-to-end number is the one users see."""
         def dev_ok(t, dtypes, shape):
             return (t.is_cuda and t.device == ws.feats.device and t.dtype in dtypes and t.is_contiguous()
                     and tuple(t.shape) == tuple(shape))
+        if os.environ.get("VCT_STAGE_NATIVE", "0") != "1":
+            return False
         B, T, S = ws.B, ws.T, ws.S
         byte = (torch.bool, torch.uint8)
         if feats is not None and not (dev_ok(feats, (torch.float32,), (B, T, self.dims.Din)) and feats.data_ptr() % 16 == 0
