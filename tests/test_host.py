@@ -58,6 +58,24 @@ def test_ctypes_structs_match_header_field_order():
     assert fields("vct_mha_args") == [f[0] for f in L.MhaArgs._fields_]
 
 
+def test_ctypes_struct_sizes_match_the_c_compiler(tmp_path):
+    """Field ORDER is checked above; sizes / padding are checked by compiling include/vct.h with gcc (plain C: the header
+    must stay free of C++ and torch types) and comparing sizeof with the ctypes mirrors."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from vct import lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include "vct.h"\nint main(void){printf("%zu %zu %zu\\n", sizeof(vct_gemm_args), '
+                   'sizeof(vct_attn_args), sizeof(vct_mha_args));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    sizes = [int(v) for v in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    assert sizes == [C.sizeof(L.GemmArgs), C.sizeof(L.AttnArgs), C.sizeof(L.MhaArgs)]
+
+
 def test_dropin_api_surface_and_state_dict(tokenizer_dir):
     from model.MMT4Caption import MMT4Caption
     from vct.synthetic import shipped_model_config
