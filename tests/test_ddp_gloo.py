@@ -114,3 +114,34 @@ def test_sparse_embedding_exchange_equals_dense_allreduce_and_bf16_bucket_is_clo
     assert ret["sparse_equals_dense"]
     assert ret["shapes"] == ((2 * 15, 8), (2 * 3, 6))
     assert ret["bf16_rel"] < 8e-3
+
+
+def test_embedding_exchange_mode_needs_the_uniform_shape_promise(monkeypatch):
+    """The sparse exchange of the embedding-table gradient has fixed per-rank slots for [B*S, d] rows and [B, S+1] ids, so it
+    is only chosen when the caller promises equal (B, S) on every rank (CaptionTrainer(uniform_shapes=True)); ragged batches
+    -- what the reference's loader produces, dataloader.py:507-532 -- take the dense, shape-independent exchange.  The
+    decision is a pure function of the engine's attributes: checked here without a GPU."""
+    import sys
+    from types import SimpleNamespace
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "video-captioning-transformer_b200"))
+    from vct.engine import CaptionEngine
+    for k in ("VCT_SPLIT_EMB_ADAM", "VCT_SPARSE_EMB"):
+        monkeypatch.delenv(k, raising=False)
+    ws = SimpleNamespace(B=64, S=20)
+    eng = SimpleNamespace(dims=SimpleNamespace(V=30522), peer=None, PEER_MAX_TOKENS=CaptionEngine.PEER_MAX_TOKENS)
+    mode = lambda world: CaptionEngine.emb_mode(eng, ws, world)
+    assert mode(1) == "local"
+    assert mode(2) == "dense"                                   # no promise: ragged batches must work
+    eng.uniform_shapes = True
+    assert mode(2) == "sparse" and mode(8) == "sparse"
+    assert CaptionEngine.emb_mode(eng, SimpleNamespace(B=512, S=20), 8) == "dense"      # 81920 tokens > one-CTA sort
+    eng.dims.V = 50000
+    assert mode(2) == "dense"                                   # vocabulary beyond the sort's key width
+    eng.dims.V = 30522
+    eng.peer = object()                                         # peer all-gather moves 16-byte vectors: even id slots only
+    assert CaptionEngine.emb_mode(eng, SimpleNamespace(B=3, S=20), 2) == "dense"
+    assert CaptionEngine.emb_mode(eng, SimpleNamespace(B=4, S=20), 2) == "sparse"
+    monkeypatch.setenv("VCT_SPARSE_EMB", "0")
+    assert mode(2) == "dense"
+    monkeypatch.setenv("VCT_SPLIT_EMB_ADAM", "0")
+    assert mode(1) == "local-unsplit" and mode(2) == "dense"
